@@ -1,0 +1,662 @@
+// The C ABI (include/cudecomp.h): argument checking, struct versioning, lifecycle. Each entry point keeps
+// the contract of the reference function it replaces (reference src/cudecomp.cc:903-2045): same checks in
+// the same order, same result codes, no exception escapes.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <set>
+
+#include "cudecomp.h"
+#include "cudecomp_b200_ext.h"
+#include "engine.h"
+#include "errors.h"
+#include "mpi_shim.h"
+
+using namespace cdb;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// struct versioning (reference src/cudecomp.cc:209-414). Only layout version 1 exists.
+
+constexpr int64_t kConfigSizeV1 = 104;
+constexpr int64_t kOptionsSizeV1 = 320;
+constexpr int64_t kPencilInfoSizeV1 = 96;
+static_assert(sizeof(cudecompGridDescConfig_t) == kConfigSizeV1, "config ABI size changed");
+static_assert(sizeof(cudecompGridDescAutotuneOptions_t) == kOptionsSizeV1, "options ABI size changed");
+static_assert(sizeof(cudecompPencilInfo_t) == kPencilInfoSizeV1, "pencil info ABI size changed");
+
+int64_t configSizeForVersion(int32_t version) {
+  if (version > CUDECOMP_GRID_DESC_CONFIG_VERSION)
+    THROW_INVALID_USAGE("config was initialized with a newer cuDecomp header than this runtime library supports");
+  if (version != 1) THROW_INVALID_USAGE("config layout version is unsupported");
+  return kConfigSizeV1;
+}
+int64_t optionsSizeForVersion(int32_t version) {
+  if (version > CUDECOMP_GRID_DESC_AUTOTUNE_OPTIONS_VERSION)
+    THROW_INVALID_USAGE("options were initialized with a newer cuDecomp header than this runtime library supports");
+  if (version != 1) THROW_INVALID_USAGE("options layout version is unsupported");
+  return kOptionsSizeV1;
+}
+int64_t pencilInfoSizeForVersion(int32_t version) {
+  if (version > CUDECOMP_PENCIL_INFO_VERSION)
+    THROW_INVALID_USAGE("pencil_info was created with a newer cuDecomp header than this runtime library supports");
+  if (version != 1) THROW_INVALID_USAGE("pencil_info layout version is unsupported");
+  return kPencilInfoSizeV1;
+}
+
+void setConfigDefaults(cudecompGridDescConfig_t* c, int64_t struct_size, int32_t version) {
+  std::memset(c, 0, sizeof(*c));
+  c->transpose_comm_backend = CUDECOMP_TRANSPOSE_COMM_MPI_P2P;
+  c->halo_comm_backend = CUDECOMP_HALO_COMM_MPI;
+  c->rank_order = CUDECOMP_RANK_ORDER_DEFAULT;
+  for (auto& row : c->transpose_mem_order)
+    for (auto& v : row) v = -1;
+  c->struct_size = struct_size;
+  c->magic = CUDECOMP_GRID_DESC_CONFIG_MAGIC;
+  c->version = version;
+}
+
+void setOptionsDefaults(cudecompGridDescAutotuneOptions_t* o, int64_t struct_size, int32_t version) {
+  std::memset(o, 0, sizeof(*o));
+  o->n_warmup_trials = 3;
+  o->n_trials = 5;
+  o->grid_mode = CUDECOMP_AUTOTUNE_GRID_TRANSPOSE;
+  o->dtype = CUDECOMP_DOUBLE;
+  o->allow_uneven_decompositions = true;
+  o->skip_threshold = 0.0;
+  for (double& w : o->transpose_op_weights) w = 1.0;
+  o->struct_size = struct_size;
+  o->magic = CUDECOMP_GRID_DESC_AUTOTUNE_OPTIONS_MAGIC;
+  o->version = version;
+}
+
+void checkConfigStruct(const cudecompGridDescConfig_t* c) {
+  if (c->magic != CUDECOMP_GRID_DESC_CONFIG_MAGIC)
+    THROW_INVALID_USAGE(
+        "config is not initialized; call cudecompGridDescConfigSetDefaults() before cudecompGridDescCreate()");
+  if (c->struct_size != configSizeForVersion(c->version))
+    THROW_INVALID_USAGE("config struct_size does not match its cuDecomp layout version");
+}
+
+void checkOptionsStruct(const cudecompGridDescAutotuneOptions_t* o) {
+  if (o->magic != CUDECOMP_GRID_DESC_AUTOTUNE_OPTIONS_MAGIC)
+    THROW_INVALID_USAGE("options are not initialized; call cudecompGridDescAutotuneOptionsSetDefaults() before "
+                        "cudecompGridDescCreate()");
+  if (o->struct_size != optionsSizeForVersion(o->version))
+    THROW_INVALID_USAGE("options struct_size does not match its cuDecomp layout version");
+}
+
+void copyConfigToCaller(cudecompGridDescConfig_t* dst, int64_t struct_size, int32_t version,
+                        const cudecompGridDesc_t gd) {
+  if (struct_size != configSizeForVersion(version))
+    THROW_INVALID_USAGE("config struct_size does not match its cuDecomp layout version");
+  *dst = gd->config;
+  dst->struct_size = struct_size;
+  dst->magic = CUDECOMP_GRID_DESC_CONFIG_MAGIC;
+  dst->version = version;
+  // settings the caller left unset are reported as unset (reference src/cudecomp.cc:1250-1265)
+  if (!gd->gdims_dist_set)
+    for (auto& v : dst->gdims_dist) v = 0;
+  if (!gd->transpose_mem_order_set)
+    for (auto& row : dst->transpose_mem_order)
+      for (auto& v : row) v = -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// argument checks (reference src/cudecomp.cc:136-207,445-481)
+
+void checkHandle(cudecompHandle_t h) {
+  if (!h || !h->initialized) THROW_INVALID_USAGE("invalid handle");
+}
+void checkGridDesc(cudecompHandle_t h, cudecompGridDesc_t gd) {
+  if (!gd || !gd->initialized) THROW_INVALID_USAGE("invalid grid descriptor");
+  if (gd->handle != h) THROW_INVALID_USAGE("grid descriptor belongs to a different handle");
+}
+void checkTransposeBackend(int b) {
+  if (b < CUDECOMP_TRANSPOSE_COMM_MPI_P2P || b > CUDECOMP_TRANSPOSE_COMM_NVSHMEM_SM)
+    THROW_INVALID_USAGE("unknown transpose communication type");
+}
+void checkHaloBackend(int b) {
+  if (b < CUDECOMP_HALO_COMM_MPI || b > CUDECOMP_HALO_COMM_NVSHMEM_BLOCKING)
+    THROW_INVALID_USAGE("unknown halo communication type");
+}
+void checkDataType(cudecompDataType_t d) {
+  if (d != CUDECOMP_FLOAT && d != CUDECOMP_DOUBLE && d != CUDECOMP_FLOAT_COMPLEX && d != CUDECOMP_DOUBLE_COMPLEX)
+    THROW_INVALID_USAGE("unknown data type");
+}
+void checkRankOrder(int r) {
+  if (r < CUDECOMP_RANK_ORDER_DEFAULT || r > CUDECOMP_RANK_ORDER_COL_MAJOR) THROW_INVALID_USAGE("unknown rank order");
+}
+
+void checkConfig(cudecompHandle_t h, const cudecompGridDescConfig_t* c, bool autotune_transpose, bool autotune_halo) {
+  if (!autotune_transpose) checkTransposeBackend(c->transpose_comm_backend);
+  if (!autotune_halo) checkHaloBackend(c->halo_comm_backend);
+  checkRankOrder(c->rank_order);
+  if (c->pdims[0] < 0 || c->pdims[1] < 0) THROW_INVALID_USAGE("pdims values are invalid");
+  const int64_t prod = static_cast<int64_t>(c->pdims[0]) * c->pdims[1];
+  if (prod == 0) {
+    if (c->pdims[0] != 0 || c->pdims[1] != 0) THROW_INVALID_USAGE("pdims values are invalid");
+  } else if (prod != h->nranks) {
+    THROW_INVALID_USAGE("product of pdims values must equal number of ranks");
+  }
+  const bool set = c->transpose_mem_order[0][0] >= 0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      if ((c->transpose_mem_order[i][j] >= 0) != set) THROW_INVALID_USAGE("transpose_mem_order only partially set");
+  if (set) {
+    for (int i = 0; i < 3; ++i) {
+      std::set<int32_t> vals(c->transpose_mem_order[i], c->transpose_mem_order[i] + 3);
+      if (vals.size() != 3 || *vals.begin() != 0 || *vals.rbegin() != 2)
+        THROW_INVALID_USAGE("transpose_mem_order setting is invalid");
+    }
+  }
+}
+
+bool envFlag(const char* name) {
+  const char* v = std::getenv(name);
+  return v && *v && std::strcmp(v, "0") != 0;
+}
+
+cudecompResult_t report(const cdb::Error& e) {
+  std::cerr << e.what();
+  return e.code();
+}
+cudecompResult_t report(const std::exception& e, bool bootstrap) {
+  if (bootstrap) {
+    std::cerr << "CUDECOMP:ERROR: Bootstrap (MPI) error. (" << e.what() << ")\n";
+    return CUDECOMP_RESULT_MPI_ERROR;
+  }
+  std::cerr << "CUDECOMP:ERROR: Internal error. (" << e.what() << ")\n";
+  return CUDECOMP_RESULT_INTERNAL_ERROR;
+}
+
+void destroyGridDescResources(cudecompGridDesc_t gd, bool collective) {
+  if (!gd) return;
+  cudecompHandle_t h = gd->handle;
+  if (gd->pads.valid()) gd->pads.destroy(collective ? h->comm.get() : nullptr);
+  gd->mbox.destroy();
+}
+
+} // namespace
+
+#define API_TRY try {
+#define API_CATCH(...)                                                                                                 \
+  }                                                                                                                    \
+  catch (const cdb::Error& e) {                                                                                        \
+    __VA_ARGS__;                                                                                                       \
+    return report(e);                                                                                                  \
+  }                                                                                                                    \
+  catch (const cdb::BootstrapError& e) {                                                                               \
+    __VA_ARGS__;                                                                                                       \
+    return report(e, true);                                                                                            \
+  }                                                                                                                    \
+  catch (const std::exception& e) {                                                                                    \
+    __VA_ARGS__;                                                                                                       \
+    return report(e, false);                                                                                           \
+  }                                                                                                                    \
+  catch (...) {                                                                                                        \
+    __VA_ARGS__;                                                                                                       \
+    std::cerr << "CUDECOMP:ERROR: Internal error. (unknown exception)\n";                                              \
+    return CUDECOMP_RESULT_INTERNAL_ERROR;                                                                             \
+  }                                                                                                                    \
+  return CUDECOMP_RESULT_SUCCESS;
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------ lifecycle
+
+cudecompResult_t cudecompInit(cudecompHandle_t* handle_in, MPI_Comm mpi_comm) {
+  cudecompHandle_t h = nullptr;
+  API_TRY
+  if (!handle_in) THROW_INVALID_USAGE("handle argument cannot be null");
+  CommPtr parent = commFromHandle(static_cast<int>(mpi_comm));
+  if (!parent) THROW_INVALID_USAGE("invalid communicator");
+  h = new cudecompHandle;
+  h->comm = dup(*parent); // private copy: library traffic never interleaves with the caller's collectives
+  h->rank = h->comm->rank();
+  h->nranks = h->comm->size();
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && cudaGetDevice(&h->device) == cudaSuccess) {
+    h->have_device = true;
+    CHECK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
+  } else {
+    (void)cudaGetLastError();
+  }
+  h->env_col_major = envFlag("CUDECOMP_USE_COL_MAJOR_RANK_ORDER");
+  if (const char* v = std::getenv("CUDECOMP_B200_DIRECT")) h->allow_direct = std::strcmp(v, "0") != 0;
+  double spin_s = 60.0;
+  if (const char* v = std::getenv("CUDECOMP_B200_DEVICE_TIMEOUT")) spin_s = std::atof(v);
+  h->spin_timeout_ns = static_cast<uint64_t>(spin_s * 1e9);
+  h->token = sharedToken(*h->comm);
+  h->initialized = true;
+  *handle_in = h;
+  API_CATCH(delete h)
+}
+
+cudecompResult_t cudecompInit_F(cudecompHandle_t* handle_in, MPI_Fint mpi_comm_f) {
+  return cudecompInit(handle_in, MPI_Comm_f2c(mpi_comm_f));
+}
+
+cudecompResult_t cudecompFinalize(cudecompHandle_t handle) {
+  API_TRY
+  checkHandle(handle);
+  handle->peers.clear();
+  handle->initialized = false;
+  delete handle;
+  API_CATCH()
+}
+
+// --------------------------------------------------------------------------------------- grid descriptor
+
+cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudecompGridDesc_t* grid_desc_in,
+                                                 cudecompGridDescConfig_t* config, int64_t config_struct_size,
+                                                 int32_t config_version,
+                                                 const cudecompGridDescAutotuneOptions_t* options,
+                                                 int64_t options_struct_size, int32_t options_version) {
+  cudecompGridDesc_t gd = nullptr;
+  API_TRY
+  checkHandle(handle);
+  if (!grid_desc_in) THROW_INVALID_USAGE("grid_desc argument cannot be null");
+  if (!config) THROW_INVALID_USAGE("config argument cannot be null");
+  if (config_struct_size != configSizeForVersion(config_version))
+    THROW_INVALID_USAGE("config struct_size does not match its cuDecomp layout version");
+  checkConfigStruct(config);
+  if (config->struct_size != config_struct_size || config->version != config_version)
+    THROW_INVALID_USAGE("config metadata does not match the requested cuDecomp layout version");
+  if (options) {
+    if (options_struct_size != optionsSizeForVersion(options_version))
+      THROW_INVALID_USAGE("options struct_size does not match its cuDecomp layout version");
+    checkOptionsStruct(options);
+    if (options->struct_size != options_struct_size || options->version != options_version)
+      THROW_INVALID_USAGE("options metadata does not match the requested cuDecomp layout version");
+  }
+  const bool autotune_transpose = options && options->autotune_transpose_backend;
+  const bool autotune_halo = options && options->autotune_halo_backend;
+  checkConfig(handle, config, autotune_transpose, autotune_halo);
+  const bool autotune_pdims = (config->pdims[0] == 0 && config->pdims[1] == 0);
+  if (autotune_pdims && !options) THROW_INVALID_USAGE("options argument cannot be null if autotuning pdims");
+
+  gd = new cudecompGridDesc;
+  gd->initialized = true;
+  gd->handle = handle;
+  gd->config = *config;
+  if (gd->config.rank_order == CUDECOMP_RANK_ORDER_DEFAULT)
+    gd->config.rank_order = handle->env_col_major ? CUDECOMP_RANK_ORDER_COL_MAJOR : CUDECOMP_RANK_ORDER_ROW_MAJOR;
+
+  // memory order per pencil axis (reference src/cudecomp.cc:1120-1133)
+  gd->transpose_mem_order_set = (config->transpose_mem_order[0][0] >= 0);
+  if (!gd->transpose_mem_order_set)
+    for (int axis = 0; axis < 3; ++axis)
+      for (int i = 0; i < 3; ++i)
+        gd->config.transpose_mem_order[axis][i] = gd->config.transpose_axis_contiguous[axis] ? (axis + i) % 3 : i;
+
+  // distribution grid (reference src/cudecomp.cc:1135-1150)
+  for (int i = 0; i < 3; ++i)
+    if (gd->config.gdims_dist[i] > gd->config.gdims[i])
+      THROW_INVALID_USAGE("gdims_dist entries must be less than or equal to gdims entries");
+  gd->gdims_dist_set = gd->config.gdims_dist[0] != 0 && gd->config.gdims_dist[1] != 0 && gd->config.gdims_dist[2] != 0;
+  if (!gd->gdims_dist_set)
+    for (int i = 0; i < 3; ++i) gd->config.gdims_dist[i] = gd->config.gdims[i];
+
+  // Device-side plumbing shared by every operation on this descriptor (collective).
+  if (handle->have_device && handle->nranks > 1) {
+    gd->pads.create(*handle->comm);
+    gd->mbox.create(*handle->comm, handle->token, handle->next_instance);
+  } else if (handle->have_device) {
+    gd->pads.create(*handle->comm);
+  }
+  handle->next_instance++;
+
+  if (autotune_pdims || autotune_transpose || autotune_halo) {
+    autotune(handle, gd, options);
+  }
+  setGeometry(gd, {gd->config.pdims[0], gd->config.pdims[1]});
+  if (gd->mbox.valid()) gd->mbox.reset(*handle->comm);
+
+  handle->live_grid_descs++;
+  *grid_desc_in = gd;
+  copyConfigToCaller(config, config_struct_size, config_version, gd);
+  API_CATCH(if (gd) {
+    destroyGridDescResources(gd, false);
+    delete gd;
+  })
+}
+
+cudecompResult_t cudecompGridDescDestroy(cudecompHandle_t handle, cudecompGridDesc_t grid_desc) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (handle->have_device) cudaDeviceSynchronize();
+  destroyGridDescResources(grid_desc, true);
+  grid_desc->initialized = false;
+  handle->live_grid_descs--;
+  delete grid_desc;
+  API_CATCH()
+}
+
+cudecompResult_t cudecompGridDescConfigSetDefaultsVersioned(cudecompGridDescConfig_t* config, int64_t struct_size,
+                                                            int32_t version) {
+  API_TRY
+  if (!config) THROW_INVALID_USAGE("config argument cannot be null");
+  if (struct_size != configSizeForVersion(version))
+    THROW_INVALID_USAGE("config struct_size does not match its cuDecomp layout version");
+  setConfigDefaults(config, struct_size, version);
+  API_CATCH()
+}
+
+cudecompResult_t cudecompGridDescAutotuneOptionsSetDefaultsVersioned(cudecompGridDescAutotuneOptions_t* options,
+                                                                     int64_t struct_size, int32_t version) {
+  API_TRY
+  if (!options) THROW_INVALID_USAGE("options argument cannot be null");
+  if (struct_size != optionsSizeForVersion(version))
+    THROW_INVALID_USAGE("options struct_size does not match its cuDecomp layout version");
+  setOptionsDefaults(options, struct_size, version);
+  API_CATCH()
+}
+
+// ------------------------------------------------------------------------------------------------ queries
+
+cudecompResult_t cudecompGetPencilInfoVersioned(cudecompHandle_t handle, cudecompGridDesc_t grid_desc,
+                                                cudecompPencilInfo_t* pencil_info, int64_t pencil_info_struct_size,
+                                                int32_t pencil_info_version, int32_t axis, const int32_t halo_extents[],
+                                                const int32_t padding[]) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (!pencil_info) THROW_INVALID_USAGE("pencil_info argument cannot be null.");
+  if (pencil_info_struct_size != pencilInfoSizeForVersion(pencil_info_version))
+    THROW_INVALID_USAGE("pencil_info struct_size does not match its cuDecomp layout version");
+  if (axis < 0 || axis > 2) THROW_INVALID_USAGE("axis argument out of range");
+  const Pencil p = pencilInfo(grid_desc->geom, grid_desc->pidx, axis, halo_extents, padding);
+  cudecompPencilInfo_t out;
+  std::memset(&out, 0, sizeof(out));
+  for (int i = 0; i < 3; ++i) {
+    out.shape[i] = p.shape[i];
+    out.lo[i] = p.lo[i];
+    out.hi[i] = p.hi[i];
+    out.order[i] = p.order[i];
+    out.halo_extents[i] = p.halo[i];
+    out.padding[i] = p.pad[i];
+  }
+  out.size = p.size;
+  out.struct_size = pencil_info_struct_size;
+  out.magic = CUDECOMP_PENCIL_INFO_MAGIC;
+  out.version = pencil_info_version;
+  *pencil_info = out;
+  API_CATCH()
+}
+
+cudecompResult_t cudecompGetGridDescConfigVersioned(cudecompHandle_t handle, cudecompGridDesc_t grid_desc,
+                                                    cudecompGridDescConfig_t* config, int64_t struct_size,
+                                                    int32_t version) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (!config) THROW_INVALID_USAGE("config argument cannot be null.");
+  copyConfigToCaller(config, struct_size, version, grid_desc);
+  API_CATCH()
+}
+
+cudecompResult_t cudecompGetTransposeWorkspaceSize(cudecompHandle_t handle, cudecompGridDesc_t grid_desc,
+                                                   int64_t* workspace_size) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (!workspace_size) THROW_INVALID_USAGE("workspace_size argument cannot be null.");
+  *workspace_size = transposeWorkspaceSize(grid_desc->geom);
+  API_CATCH()
+}
+
+cudecompResult_t cudecompGetHaloWorkspaceSize(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t axis,
+                                              const int32_t halo_extents[], int64_t* workspace_size) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (axis < 0 || axis > 2) THROW_INVALID_USAGE("axis argument out of range");
+  if (!halo_extents) THROW_INVALID_USAGE("halo_extents argument cannot be null.");
+  if (!workspace_size) THROW_INVALID_USAGE("workspace_size argument cannot be null.");
+  *workspace_size = haloWorkspaceSize(grid_desc->geom, grid_desc->pidx, axis, halo_extents);
+  API_CATCH()
+}
+
+cudecompResult_t cudecompGetDataTypeSize(cudecompDataType_t dtype, int64_t* dtype_size) {
+  API_TRY
+  checkDataType(dtype);
+  if (!dtype_size) THROW_INVALID_USAGE("dtype_size cannot be null.");
+  *dtype_size = dtypeSize(dtype);
+  API_CATCH()
+}
+
+cudecompResult_t cudecompGetShiftedRank(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t axis,
+                                        int32_t dim, int32_t displacement, bool periodic, int32_t* shifted_rank) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (axis < 0 || axis > 2) THROW_INVALID_USAGE("axis argument out of range");
+  if (dim < 0 || dim > 2) THROW_INVALID_USAGE("dim argument out of range");
+  if (!shifted_rank) THROW_INVALID_USAGE("shifted_rank argument cannot be null.");
+  *shifted_rank = shiftedRank(grid_desc->geom, handle->rank, axis, dim, displacement, periodic);
+  API_CATCH()
+}
+
+const char* cudecompTransposeCommBackendToString(cudecompTransposeCommBackend_t comm_backend) {
+  switch (comm_backend) {
+  case CUDECOMP_TRANSPOSE_COMM_NCCL: return "NCCL";
+  case CUDECOMP_TRANSPOSE_COMM_NCCL_PL: return "NCCL (pipelined)";
+  case CUDECOMP_TRANSPOSE_COMM_MPI_P2P: return "MPI_P2P";
+  case CUDECOMP_TRANSPOSE_COMM_MPI_P2P_PL: return "MPI_P2P (pipelined)";
+  case CUDECOMP_TRANSPOSE_COMM_MPI_A2A: return "MPI_A2A";
+  case CUDECOMP_TRANSPOSE_COMM_NVSHMEM: return "NVSHMEM";
+  case CUDECOMP_TRANSPOSE_COMM_NVSHMEM_PL: return "NVSHMEM (pipelined)";
+  case CUDECOMP_TRANSPOSE_COMM_NVSHMEM_SM: return "NVSHMEM_SM";
+  default: return "ERROR";
+  }
+}
+
+const char* cudecompHaloCommBackendToString(cudecompHaloCommBackend_t comm_backend) {
+  switch (comm_backend) {
+  case CUDECOMP_HALO_COMM_NCCL: return "NCCL";
+  case CUDECOMP_HALO_COMM_MPI: return "MPI";
+  case CUDECOMP_HALO_COMM_MPI_BLOCKING: return "MPI (blocking)";
+  case CUDECOMP_HALO_COMM_NVSHMEM: return "NVSHMEM";
+  case CUDECOMP_HALO_COMM_NVSHMEM_BLOCKING: return "NVSHMEM (blocking)";
+  default: return "ERROR";
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- workspaces
+
+cudecompResult_t cudecompMalloc(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, void** buffer,
+                                size_t buffer_size_bytes) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (!buffer) THROW_INVALID_USAGE("buffer argument cannot be null");
+  if (buffer_size_bytes == 0) THROW_INVALID_USAGE("buffer size cannot be zero");
+  if (!handle->have_device)
+    CDB_THROW(CUDECOMP_RESULT_CUDA_ERROR, "CUDA error.", "no CUDA device is available to this process");
+  // Plain device memory: peers import it with CUDA IPC the first time an operation names it, so no
+  // symmetric-size agreement is needed (the reference's NVSHMEM arm MAX-reduces the size, src/cudecomp.cc:1474).
+  void* p = nullptr;
+  CHECK_CUDA(cudaMalloc(&p, buffer_size_bytes));
+  grid_desc->allocations.insert(p);
+  *buffer = p;
+  API_CATCH()
+}
+
+cudecompResult_t cudecompFree(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, void* buffer) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (handle->have_device) {
+    // Collective: every rank drops its import of every buffer being freed before any owner releases it.
+    CHECK_CUDA(cudaDeviceSynchronize());
+    if (handle->nranks > 1) {
+      BufDesc mine;
+      describeBuffer(buffer, &mine);
+      std::vector<BufDesc> all(handle->nranks);
+      allgather(*handle->comm, &mine, sizeof(BufDesc), all.data());
+      for (int r = 0; r < handle->nranks; ++r)
+        if (r != handle->rank && all[r].exportable) handle->peers.forget(r, all[r]);
+      barrier(*handle->comm);
+    }
+    if (buffer) CHECK_CUDA(cudaFree(buffer));
+  }
+  for (cudecompGridDesc_t gd : {grid_desc}) gd->allocations.erase(buffer);
+  API_CATCH()
+}
+
+// ---------------------------------------------------------------------------------------------- hot path
+
+#define TRANSPOSE_ENTRY(NAME, AX, DIR)                                                                                 \
+  cudecompResult_t NAME(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, void* input, void* output, void* work,  \
+                        cudecompDataType_t dtype, const int32_t input_halo_extents[],                                  \
+                        const int32_t output_halo_extents[], const int32_t input_padding[],                            \
+                        const int32_t output_padding[], cudaStream_t stream) {                                         \
+    API_TRY                                                                                                            \
+    checkHandle(handle);                                                                                               \
+    checkGridDesc(handle, grid_desc);                                                                                  \
+    checkDataType(dtype);                                                                                              \
+    if (!input) THROW_INVALID_USAGE("input argument cannot be null");                                                  \
+    if (!output) THROW_INVALID_USAGE("output argument cannot be null");                                                \
+    if (!work) THROW_INVALID_USAGE("work argument cannot be null");                                                    \
+    runTranspose(handle, grid_desc, AX, DIR, input, output, work, dtype, input_halo_extents, output_halo_extents,      \
+                 input_padding, output_padding, stream);                                                               \
+    API_CATCH()                                                                                                        \
+  }
+
+// (ax, dir): XY = (0,+1), YZ = (1,+1), ZY = (2,-1), YX = (1,-1)  (reference include/internal/transpose.h:907-953)
+TRANSPOSE_ENTRY(cudecompTransposeXToY, 0, 1)
+TRANSPOSE_ENTRY(cudecompTransposeYToZ, 1, 1)
+TRANSPOSE_ENTRY(cudecompTransposeZToY, 2, -1)
+TRANSPOSE_ENTRY(cudecompTransposeYToX, 1, -1)
+
+#define HALO_ENTRY(NAME, AX)                                                                                           \
+  cudecompResult_t NAME(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, void* input, void* work,                \
+                        cudecompDataType_t dtype, const int32_t halo_extents[], const bool halo_periods[],             \
+                        int32_t dim, const int32_t padding[], cudaStream_t stream) {                                   \
+    API_TRY                                                                                                            \
+    checkHandle(handle);                                                                                               \
+    checkGridDesc(handle, grid_desc);                                                                                  \
+    checkDataType(dtype);                                                                                              \
+    if (!halo_extents) THROW_INVALID_USAGE("halo_extents argument cannot be null");                                    \
+    if (halo_extents[0] == 0 && halo_extents[1] == 0 && halo_extents[2] == 0) return CUDECOMP_RESULT_SUCCESS;          \
+    if (!input) THROW_INVALID_USAGE("input argument cannot be null");                                                  \
+    if (!work) THROW_INVALID_USAGE("work argument cannot be null");                                                    \
+    if (dim < 0 || dim > 2) THROW_INVALID_USAGE("dim argument out of range");                                          \
+    runHalo(handle, grid_desc, AX, input, work, dtype, halo_extents, halo_periods, dim, padding, stream);              \
+    API_CATCH()                                                                                                        \
+  }
+
+HALO_ENTRY(cudecompUpdateHalosX, 0)
+HALO_ENTRY(cudecompUpdateHalosY, 1)
+HALO_ENTRY(cudecompUpdateHalosZ, 2)
+
+// ---------------------------------------------------------------------------------------------- extensions
+
+cudecompResult_t cudecompB200GetLaunchCount(uint64_t* count) {
+  if (!count) return CUDECOMP_RESULT_INVALID_USAGE;
+  *count = launchCount();
+  return CUDECOMP_RESULT_SUCCESS;
+}
+
+cudecompResult_t cudecompB200GetLastPath(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t* path) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (!path) THROW_INVALID_USAGE("path argument cannot be null");
+  *path = grid_desc->last_path;
+  API_CATCH()
+}
+
+cudecompResult_t cudecompB200SetTuning(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t grid_ctas,
+                                       int32_t force_staged) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (grid_ctas < 0) THROW_INVALID_USAGE("grid_ctas must be >= 0");
+  grid_desc->grid_ctas = grid_ctas;
+  grid_desc->force_staged = force_staged != 0;
+  API_CATCH()
+}
+
+cudecompResult_t cudecompB200CheckErrors(cudecompHandle_t handle, cudecompGridDesc_t grid_desc) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  checkDeviceError(grid_desc);
+  API_CATCH()
+}
+
+int32_t cudecompB200DescribeTransposeBoxes(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t ax,
+                                           int32_t dir, const int32_t input_halo_extents[],
+                                           const int32_t output_halo_extents[], const int32_t input_padding[],
+                                           const int32_t output_padding[], int32_t staged,
+                                           cudecompB200Box_t* boxes, int32_t max_boxes) {
+  try {
+    checkHandle(handle);
+    checkGridDesc(handle, grid_desc);
+    TransposePlan plan =
+        buildTransposePlan(grid_desc->geom, grid_desc->pidx, ax, dir, input_halo_extents, output_halo_extents,
+                           input_padding, output_padding, staged ? DstKind::STAGE : DstKind::FINAL, false);
+    std::vector<BoxDesc> all = plan.push;
+    for (auto& u : plan.unpack) all.push_back(u);
+    int32_t n = 0;
+    for (size_t i = 0; i < all.size() && n < max_boxes; ++i, ++n) {
+      cudecompB200Box_t& o = boxes[n];
+      o.peer_rank = all[i].peer_world;
+      o.is_unpack = (i >= plan.push.size()) ? 1 : 0;
+      o.src_offset = all[i].src_off;
+      o.dst_offset = all[i].dst_off;
+      for (int k = 0; k < 3; ++k) {
+        o.extent[k] = all[i].ext[k];
+        o.src_stride[k] = all[i].sstr[k];
+        o.dst_stride[k] = all[i].dstr[k];
+      }
+    }
+    return static_cast<int32_t>(all.size());
+  } catch (const std::exception& e) {
+    std::cerr << e.what();
+    return -1;
+  }
+}
+
+int32_t cudecompB200DescribeHaloBoxes(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t ax, int32_t dim,
+                                      const int32_t halo_extents[], const bool halo_periods[], const int32_t padding[],
+                                      int32_t staged, cudecompB200Box_t* boxes, int32_t max_boxes) {
+  try {
+    checkHandle(handle);
+    checkGridDesc(handle, grid_desc);
+    HaloPlan plan = buildHaloPlan(grid_desc->geom, grid_desc->pidx, ax, dim, halo_extents, halo_periods, padding,
+                                  staged ? DstKind::STAGE : DstKind::FINAL);
+    if (plan.nothing) return 0;
+    std::vector<BoxDesc> all = plan.push;
+    for (auto& u : plan.unpack) all.push_back(u);
+    int32_t n = 0;
+    for (size_t i = 0; i < all.size() && n < max_boxes; ++i, ++n) {
+      cudecompB200Box_t& o = boxes[n];
+      o.peer_rank = all[i].peer_world;
+      o.is_unpack = (i >= plan.push.size()) ? 1 : 0;
+      o.src_offset = all[i].src_off;
+      o.dst_offset = all[i].dst_off;
+      for (int k = 0; k < 3; ++k) {
+        o.extent[k] = all[i].ext[k];
+        o.src_stride[k] = all[i].sstr[k];
+        o.dst_stride[k] = all[i].dstr[k];
+      }
+    }
+    return static_cast<int32_t>(all.size());
+  } catch (const std::exception& e) {
+    std::cerr << e.what();
+    return -1;
+  }
+}
+
+} // extern "C"

@@ -1,0 +1,440 @@
+// Grid-descriptor autotuning. Keeps the reference protocol (reference src/autotune.cc:275-769 transposes,
+// :771-1124 halos): sweep the factorisations of nranks in locality-first order, skip empty / disallowed
+// uneven grids, n_warmup_trials untimed + n_trials timed runs of the enabled operations with CUDA events
+// on one stream, score = rank-average of the weighted per-trial time, smallest wins, identical on all
+// ranks. What is swept per process grid is different: there are no MPI/NCCL/NVSHMEM libraries to choose
+// between, so a "backend" is a schedule of the one peer-store engine:
+//   backend values 1..5 (MPI*, NCCL*)  -> direct: peers store straight into the destination buffers
+//   backend values 6..8 (NVSHMEM*)     -> staged: peers store into the workspace, local unpack
+// and for each of them the CTA count of the copy kernels is swept too.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+
+#include "engine.h"
+#include "errors.h"
+
+namespace cdb {
+
+namespace {
+
+bool backendIsStaged(int b) { return b >= CUDECOMP_TRANSPOSE_COMM_NVSHMEM; }
+
+std::pair<int32_t, int32_t> parseRange(const char* name) {
+  // "lo:hi" or "n" (reference src/autotune.cc:192-253)
+  const char* v = std::getenv(name);
+  std::pair<int32_t, int32_t> r{1, std::numeric_limits<int32_t>::max()};
+  if (!v || !*v) return r;
+  std::string s(v);
+  try {
+    auto pos = s.find(':');
+    if (pos == std::string::npos) {
+      r.first = r.second = std::stoi(s);
+    } else {
+      if (pos > 0) r.first = std::stoi(s.substr(0, pos));
+      if (pos + 1 < s.size()) r.second = std::stoi(s.substr(pos + 1));
+    }
+  } catch (...) {
+    THROW_INVALID_USAGE(std::string(name) + " is malformed");
+  }
+  if (r.first < 1 || r.second < r.first) THROW_INVALID_USAGE(std::string(name) + " is malformed");
+  return r;
+}
+
+std::vector<std::array<int32_t, 2>> autotunePdims(cudecompHandle_t h, cudecompGridDesc_t gd) {
+  auto cand = pdimCandidates(h->nranks, gd->config.rank_order == CUDECOMP_RANK_ORDER_COL_MAJOR);
+  auto rows = parseRange("CUDECOMP_AUTOTUNE_P_ROW_RANGE");
+  auto cols = parseRange("CUDECOMP_AUTOTUNE_P_COL_RANGE");
+  cand.erase(std::remove_if(cand.begin(), cand.end(),
+                            [&](const std::array<int32_t, 2>& p) {
+                              return p[0] < rows.first || p[0] > rows.second || p[1] < cols.first || p[1] > cols.second;
+                            }),
+             cand.end());
+  if (cand.empty()) THROW_INVALID_USAGE("Process-grid autotuning has no usable candidates after applying filters");
+  return cand;
+}
+
+bool gridUsable(const cudecompGridDesc_t gd, const std::array<int32_t, 2>& p, bool allow_uneven) {
+  const auto& d = gd->config.gdims_dist;
+  if (p[0] > std::min(d[0], d[1]) || p[1] > std::min(d[1], d[2])) return false; // empty pencils
+  if (!allow_uneven && (d[0] % p[0] != 0 || d[1] % p[0] != 0 || d[1] % p[1] != 0 || d[2] % p[1] != 0)) return false;
+  return true;
+}
+
+struct Stats {
+  double min, max, avg, std;
+};
+
+// min/max/avg/std over (ranks x trials) (reference src/autotune.cc:167-188)
+Stats reduceTimes(cudecompHandle_t h, const std::vector<double>& t) {
+  double mn = std::numeric_limits<double>::max(), mx = 0, sum = 0, sq = 0;
+  for (double v : t) {
+    mn = std::min(mn, v);
+    mx = std::max(mx, v);
+    sum += v;
+    sq += v * v;
+  }
+  double n = static_cast<double>(t.size());
+  double red[3] = {sum, sq, n};
+  allreduceF64(*h->comm, red, 3, ReduceOp::SUM);
+  allreduceF64(*h->comm, &mn, 1, ReduceOp::MIN);
+  allreduceF64(*h->comm, &mx, 1, ReduceOp::MAX);
+  Stats s;
+  s.min = mn;
+  s.max = mx;
+  s.avg = red[0] / red[2];
+  s.std = std::sqrt(std::max(0.0, red[1] / red[2] - s.avg * s.avg));
+  return s;
+}
+
+struct DeviceBuffer {
+  void* p = nullptr;
+  ~DeviceBuffer() {
+    if (p) cudaFree(p);
+  }
+  void alloc(size_t bytes) { CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 256))); }
+};
+
+struct Events {
+  std::vector<cudaEvent_t> ev;
+  explicit Events(size_t n) : ev(n) {
+    for (auto& e : ev) CHECK_CUDA(cudaEventCreate(&e));
+  }
+  ~Events() {
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+};
+
+const int kOps[4][2] = {{0, 1}, {1, 1}, {2, -1}, {1, -1}}; // XY, YZ, ZY, YX as (ax, dir)
+
+void autotuneTransposes(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecompGridDescAutotuneOptions_t* o,
+                        bool tune_pdims, bool tune_backend) {
+  const double t_start = MPI_Wtime();
+  if (h->rank == 0) std::printf("CUDECOMP: Running transpose autotuning...\n");
+
+  std::vector<std::array<int32_t, 2>> grids;
+  if (tune_pdims)
+    grids = autotunePdims(h, gd);
+  else
+    grids.push_back({gd->config.pdims[0], gd->config.pdims[1]});
+
+  std::vector<int> backends;
+  if (tune_backend) {
+    // one representative per schedule family that the options leave enabled
+    if (!o->disable_nccl_backends)
+      backends.push_back(CUDECOMP_TRANSPOSE_COMM_NCCL);
+    else if (!o->disable_mpi_backends)
+      backends.push_back(CUDECOMP_TRANSPOSE_COMM_MPI_P2P);
+    if (!o->disable_nvshmem_backends) backends.push_back(CUDECOMP_TRANSPOSE_COMM_NVSHMEM);
+    if (backends.empty()) THROW_INVALID_USAGE("Transpose backend autotuning has no usable candidates");
+  } else {
+    backends.push_back(gd->config.transpose_comm_backend);
+  }
+
+  const int64_t es = dtypeSize(o->dtype);
+
+  // buffers large enough for every candidate
+  int64_t data_elems = 0, work_elems = 0;
+  for (auto& p : grids) {
+    if (!gridUsable(gd, p, o->allow_uneven_decompositions)) continue;
+    setGeometry(gd, p);
+    for (int op = 0; op < 4; ++op) {
+      TransposeAxes ax = transposeAxes(kOps[op][0], kOps[op][1]);
+      data_elems = std::max(data_elems, pencilInfo(gd->geom, gd->pidx, ax.a, o->transpose_input_halo_extents[op],
+                                                   o->transpose_input_padding[op]).size);
+      data_elems = std::max(data_elems, pencilInfo(gd->geom, gd->pidx, ax.b, o->transpose_output_halo_extents[op],
+                                                   o->transpose_output_padding[op]).size);
+    }
+    work_elems = std::max(work_elems, transposeWorkspaceSize(gd->geom));
+  }
+  bool need_data2 = false;
+  for (int op = 0; op < 4; ++op)
+    if (!o->transpose_use_inplace_buffers[op]) need_data2 = true;
+
+  double t_best = std::numeric_limits<double>::max();
+  std::array<int32_t, 2> best_grid{0, 0};
+  int best_backend = backends[0];
+  int best_ctas = 0;
+  bool valid = false;
+
+  if (!h->have_device) {
+    // nothing can be timed: take the first usable grid so that geometry queries still work on CPU-only hosts
+    for (auto& p : grids) {
+      if (!gridUsable(gd, p, o->allow_uneven_decompositions)) continue;
+      best_grid = p;
+      valid = true;
+      break;
+    }
+    if (h->rank == 0) std::printf("CUDECOMP:WARN: no CUDA device, autotuning skipped (first usable grid selected)\n");
+  } else {
+    DeviceBuffer data, data2, work;
+    if (data_elems > 0) {
+      data.alloc(static_cast<size_t>(data_elems * es));
+      CHECK_CUDA(cudaMemset(data.p, 0, static_cast<size_t>(data_elems * es)));
+      if (need_data2) {
+        data2.alloc(static_cast<size_t>(data_elems * es));
+        CHECK_CUDA(cudaMemset(data2.p, 0, static_cast<size_t>(data_elems * es)));
+      }
+      work.alloc(static_cast<size_t>(work_elems * es));
+    }
+    cudaStream_t stream = 0;
+    Events ev(5);
+    const int saved_ctas = gd->grid_ctas;
+    const bool saved_staged = gd->force_staged;
+
+    for (auto& p : grids) {
+      if (!gridUsable(gd, p, o->allow_uneven_decompositions)) continue;
+      valid = true;
+      setGeometry(gd, p);
+      if (gd->mbox.valid()) gd->mbox.reset(*h->comm);
+
+      for (int backend : backends) {
+        gd->config.transpose_comm_backend = static_cast<cudecompTransposeCommBackend_t>(backend);
+        gd->force_staged = backendIsStaged(backend);
+        // CTA counts to try: everything resident, and one / two CTAs per SM
+        std::vector<int> cta_list = {0};
+        if (tune_backend && h->sm_count > 0) {
+          cta_list.push_back(2 * h->sm_count);
+          cta_list.push_back(h->sm_count);
+        }
+        for (int ctas : cta_list) {
+          gd->grid_ctas = ctas;
+          auto runOp = [&](int op) {
+            void* in = data.p;
+            void* out = o->transpose_use_inplace_buffers[op] ? data.p : data2.p;
+            runTranspose(h, gd, kOps[op][0], kOps[op][1], in, out, work.p, o->dtype,
+                         o->transpose_input_halo_extents[op], o->transpose_output_halo_extents[op],
+                         o->transpose_input_padding[op], o->transpose_output_padding[op], stream);
+          };
+          for (int w = 0; w < o->n_warmup_trials; ++w)
+            for (int op = 0; op < 4; ++op)
+              if (o->transpose_op_weights[op] != 0.0) runOp(op);
+          CHECK_CUDA(cudaStreamSynchronize(stream));
+
+          std::vector<double> total, total_w;
+          std::vector<double> per_op[4];
+          bool skipped = false;
+          for (int t = 0; t < o->n_trials; ++t) {
+            CHECK_CUDA(cudaEventRecord(ev.ev[0], stream));
+            for (int op = 0; op < 4; ++op) {
+              if (o->transpose_op_weights[op] != 0.0) runOp(op);
+              CHECK_CUDA(cudaEventRecord(ev.ev[op + 1], stream));
+            }
+            CHECK_CUDA(cudaStreamSynchronize(stream));
+            double tt = 0, tw = 0;
+            for (int op = 0; op < 4; ++op) {
+              float ms = 0;
+              CHECK_CUDA(cudaEventElapsedTime(&ms, ev.ev[op], ev.ev[op + 1]));
+              per_op[op].push_back(ms);
+              tt += ms;
+              tw += ms * o->transpose_op_weights[op];
+            }
+            total.push_back(tt);
+            total_w.push_back(tw);
+            if (t == 0 && o->skip_threshold > 0.0) {
+              // agree across ranks whether this configuration is hopeless (reference src/autotune.cc:578-602)
+              double first = tw;
+              allreduceF64(*h->comm, &first, 1, ReduceOp::SUM);
+              first /= h->nranks;
+              if (o->skip_threshold * first > t_best) {
+                skipped = true;
+                break;
+              }
+            }
+          }
+          if (skipped) {
+            if (h->rank == 0)
+              std::printf("CUDECOMP:\tgrid: %d x %d, backend: %s, CTAs: %d \nCUDECOMP:\t(skipped) \n", p[0], p[1],
+                          cudecompTransposeCommBackendToString(gd->config.transpose_comm_backend), ctas);
+            continue;
+          }
+          Stats st = reduceTimes(h, total), sw = reduceTimes(h, total_w);
+          Stats so[4];
+          for (int op = 0; op < 4; ++op) so[op] = reduceTimes(h, per_op[op]);
+          if (h->rank == 0) {
+            std::printf("CUDECOMP:\tgrid: %d x %d, backend: %s, CTAs: %d \n"
+                        "CUDECOMP:\tTotal time min/max/avg/std [ms]: %f/%f/%f/%f\n"
+                        "CUDECOMP:\t           min/max/avg/std [ms]: %f/%f/%f/%f (weighted)\n",
+                        p[0], p[1], cudecompTransposeCommBackendToString(gd->config.transpose_comm_backend), ctas,
+                        st.min, st.max, st.avg, st.std, sw.min, sw.max, sw.avg, sw.std);
+            const char* names[4] = {"XY", "YZ", "ZY", "YX"};
+            for (int op = 0; op < 4; ++op)
+              std::printf("CUDECOMP:\tTranspose%s time min/max/avg/std [ms]: %f/%f/%f/%f%s\n", names[op], so[op].min,
+                          so[op].max, so[op].avg, so[op].std,
+                          o->transpose_op_weights[op] == 0.0 ? " (skipped)" : "");
+          }
+          if (sw.avg < t_best) {
+            t_best = sw.avg;
+            best_grid = p;
+            best_backend = backend;
+            best_ctas = ctas;
+          }
+        }
+      }
+    }
+    gd->grid_ctas = saved_ctas;
+    gd->force_staged = saved_staged;
+    CHECK_CUDA(cudaDeviceSynchronize());
+    // our device buffers are about to be freed: every peer drops its imports of them first
+    h->peers.clear();
+    barrier(*h->comm);
+  }
+
+  if (!valid) THROW_NOT_SUPPORTED("No valid decomposition found during autotuning with provided arguments.");
+
+  gd->config.pdims[0] = best_grid[0];
+  gd->config.pdims[1] = best_grid[1];
+  gd->config.transpose_comm_backend = static_cast<cudecompTransposeCommBackend_t>(best_backend);
+  if (tune_backend) gd->grid_ctas = best_ctas;
+  gd->force_staged = false;
+  if (h->rank == 0)
+    std::printf("CUDECOMP: SELECTED: grid: %d x %d, backend: %s, Avg. time (weighted) [ms]: %f\n", best_grid[0],
+                best_grid[1], cudecompTransposeCommBackendToString(gd->config.transpose_comm_backend),
+                h->have_device ? t_best : 0.0);
+  barrier(*h->comm);
+  if (h->rank == 0) std::printf("CUDECOMP: transpose autotuning time [s]: %f\n", MPI_Wtime() - t_start);
+}
+
+void autotuneHalos(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecompGridDescAutotuneOptions_t* o,
+                   bool tune_pdims, bool tune_backend) {
+  const double t_start = MPI_Wtime();
+  if (h->rank == 0) std::printf("CUDECOMP: Running halo autotuning...\n");
+  if (o->halo_axis < 0 || o->halo_axis > 2) THROW_INVALID_USAGE("halo_axis out of range");
+
+  std::vector<std::array<int32_t, 2>> grids;
+  if (tune_pdims)
+    grids = autotunePdims(h, gd);
+  else
+    grids.push_back({gd->config.pdims[0], gd->config.pdims[1]});
+
+  // all halo backend values run the same peer-store schedule; keep the caller's value unless it asked to tune
+  int backend = gd->config.halo_comm_backend;
+  if (tune_backend) {
+    if (!o->disable_nccl_backends)
+      backend = CUDECOMP_HALO_COMM_NCCL;
+    else if (!o->disable_mpi_backends)
+      backend = CUDECOMP_HALO_COMM_MPI;
+    else if (!o->disable_nvshmem_backends)
+      backend = CUDECOMP_HALO_COMM_NVSHMEM;
+    else
+      THROW_INVALID_USAGE("Halo backend autotuning has no usable candidates");
+  }
+  const int64_t es = dtypeSize(o->dtype);
+  const int ax = o->halo_axis;
+
+  int64_t data_elems = 0, work_elems = 0;
+  for (auto& p : grids) {
+    if (!gridUsable(gd, p, o->allow_uneven_decompositions)) continue;
+    setGeometry(gd, p);
+    data_elems = std::max(data_elems, pencilInfo(gd->geom, gd->pidx, ax, o->halo_extents, o->halo_padding).size);
+    work_elems = std::max(work_elems, haloWorkspaceSize(gd->geom, gd->pidx, ax, o->halo_extents));
+  }
+  // the workspace size depends on the rank's slab; peers only need each rank's own size to be sufficient
+
+  double t_best = std::numeric_limits<double>::max();
+  std::array<int32_t, 2> best_grid{0, 0};
+  bool valid = false;
+
+  if (!h->have_device) {
+    for (auto& p : grids) {
+      if (!gridUsable(gd, p, o->allow_uneven_decompositions)) continue;
+      best_grid = p;
+      valid = true;
+      break;
+    }
+    if (h->rank == 0) std::printf("CUDECOMP:WARN: no CUDA device, autotuning skipped (first usable grid selected)\n");
+  } else {
+    DeviceBuffer data, work;
+    if (data_elems > 0) {
+      data.alloc(static_cast<size_t>(data_elems * es));
+      CHECK_CUDA(cudaMemset(data.p, 0, static_cast<size_t>(data_elems * es)));
+      work.alloc(static_cast<size_t>(std::max<int64_t>(work_elems, 64) * es));
+    }
+    cudaStream_t stream = 0;
+    Events ev(4);
+    for (auto& p : grids) {
+      if (!gridUsable(gd, p, o->allow_uneven_decompositions)) continue;
+      setGeometry(gd, p);
+      if (gd->mbox.valid()) gd->mbox.reset(*h->comm);
+      // a halo wider than some rank's slab cannot be exchanged on this grid
+      bool too_wide = false;
+      for (int dim = 0; dim < 3 && !too_wide; ++dim) {
+        if (dim == ax || o->halo_extents[dim] == 0) continue;
+        const int P = gd->geom.pdims[haloCommAxis(ax, dim)];
+        if (P == 1) continue;
+        auto splits = getSplits(gd->geom.gdims_dist[dim], P, gd->geom.gdims[dim] - gd->geom.gdims_dist[dim]);
+        if (o->halo_extents[dim] > *std::min_element(splits.begin(), splits.end())) too_wide = true;
+      }
+      if (too_wide) continue;
+      valid = true;
+      auto runAll = [&]() {
+        for (int dim = 0; dim < 3; ++dim)
+          runHalo(h, gd, ax, data.p, work.p, o->dtype, o->halo_extents, o->halo_periods, dim, o->halo_padding, stream);
+      };
+      for (int w = 0; w < o->n_warmup_trials; ++w) runAll();
+      CHECK_CUDA(cudaStreamSynchronize(stream));
+      std::vector<double> total;
+      for (int t = 0; t < o->n_trials; ++t) {
+        CHECK_CUDA(cudaEventRecord(ev.ev[0], stream));
+        runAll();
+        CHECK_CUDA(cudaEventRecord(ev.ev[1], stream));
+        CHECK_CUDA(cudaStreamSynchronize(stream));
+        float ms = 0;
+        CHECK_CUDA(cudaEventElapsedTime(&ms, ev.ev[0], ev.ev[1]));
+        total.push_back(ms);
+      }
+      Stats st = reduceTimes(h, total);
+      if (h->rank == 0)
+        std::printf("CUDECOMP:\tgrid: %d x %d, halo backend: %s \n"
+                    "CUDECOMP:\tTotal time min/max/avg/std [ms]: %f/%f/%f/%f\n",
+                    p[0], p[1], cudecompHaloCommBackendToString(static_cast<cudecompHaloCommBackend_t>(backend)),
+                    st.min, st.max, st.avg, st.std);
+      if (st.avg < t_best) {
+        t_best = st.avg;
+        best_grid = p;
+      }
+    }
+    CHECK_CUDA(cudaDeviceSynchronize());
+    h->peers.clear();
+    barrier(*h->comm);
+  }
+  if (!valid) THROW_NOT_SUPPORTED("No valid decomposition found during autotuning with provided arguments.");
+  gd->config.pdims[0] = best_grid[0];
+  gd->config.pdims[1] = best_grid[1];
+  gd->config.halo_comm_backend = static_cast<cudecompHaloCommBackend_t>(backend);
+  if (h->rank == 0)
+    std::printf("CUDECOMP: SELECTED: grid: %d x %d, halo backend: %s, Avg. time [ms]: %f\n", best_grid[0], best_grid[1],
+                cudecompHaloCommBackendToString(gd->config.halo_comm_backend), h->have_device ? t_best : 0.0);
+  barrier(*h->comm);
+  if (h->rank == 0) std::printf("CUDECOMP: halo autotuning time [s]: %f\n", MPI_Wtime() - t_start);
+}
+
+} // namespace
+
+void autotune(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecompGridDescAutotuneOptions_t* o) {
+  if (!o) THROW_INVALID_USAGE("options argument cannot be null if autotuning");
+  const bool tune_pdims = (gd->config.pdims[0] == 0 && gd->config.pdims[1] == 0);
+  const bool tune_t = o->autotune_transpose_backend;
+  const bool tune_h = o->autotune_halo_backend;
+  if (o->n_trials < 1 || o->n_warmup_trials < 0) THROW_INVALID_USAGE("invalid number of autotuning trials");
+  // the grid is chosen by the first pass; the second pass (if any) tunes its backend on that grid
+  // (reference src/cudecomp.cc:1201-1211)
+  if (o->grid_mode == CUDECOMP_AUTOTUNE_GRID_TRANSPOSE) {
+    if (tune_t || tune_pdims) autotuneTransposes(h, gd, o, tune_pdims, tune_t);
+    if (tune_h) autotuneHalos(h, gd, o, false, true);
+  } else if (o->grid_mode == CUDECOMP_AUTOTUNE_GRID_HALO) {
+    if (tune_h || tune_pdims) autotuneHalos(h, gd, o, tune_pdims, tune_h);
+    if (tune_t) autotuneTransposes(h, gd, o, false, true);
+  } else {
+    THROW_INVALID_USAGE("unknown value of autotune_grid_mode encountered.");
+  }
+  std::fflush(stdout);
+}
+
+} // namespace cdb

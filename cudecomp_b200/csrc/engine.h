@@ -1,0 +1,81 @@
+// Internal state behind the two opaque handles of the C ABI and the execution of one transpose / halo
+// call (the orchestration layer the reference keeps in include/internal/transpose.h and halo.h).
+#ifndef CUDECOMP_B200_ENGINE_H
+#define CUDECOMP_B200_ENGINE_H
+
+#include <array>
+#include <cstdint>
+#include <set>
+
+#include "bootstrap.h"
+#include "cudecomp.h"
+#include "geometry.h"
+#include "kernels.h"
+#include "peer.h"
+#include "plan.h"
+
+// Which way the last operation on a grid descriptor moved its data (cudecompB200GetLastPath).
+enum {
+  CUDECOMP_B200_PATH_NONE = 0,   // nothing to do (no-op transpose, zero halo, no neighbour)
+  CUDECOMP_B200_PATH_LOCAL = 1,  // single-rank communicator: one local kernel
+  CUDECOMP_B200_PATH_DIRECT = 2, // peer stores straight into the destination buffers, one kernel
+  CUDECOMP_B200_PATH_STAGED = 3  // peer stores into the peers' workspace + local unpack kernel
+};
+
+struct cudecompHandle {
+  bool initialized = false;
+  cdb::CommPtr comm;
+  int rank = 0;
+  int nranks = 1;
+  bool have_device = false;
+  int device = -1;
+  int sm_count = 0;
+  bool env_col_major = false;
+  bool allow_direct = true;      // CUDECOMP_B200_DIRECT=0 forces staging through the workspace
+  uint64_t spin_timeout_ns = 0;  // device-side wait limit
+  uint64_t token = 0;            // names shared-memory segments
+  int next_instance = 0;
+  int live_grid_descs = 0;
+  cdb::PeerCache peers;          // imported peer allocations, shared by all grid descriptors
+};
+
+struct cudecompGridDesc {
+  bool initialized = false;
+  cudecompHandle_t handle = nullptr;
+  cudecompGridDescConfig_t config{}; // normalised, orders and gdims_dist resolved
+  bool gdims_dist_set = false;
+  bool transpose_mem_order_set = false;
+  cdb::GridGeom geom;
+  std::array<int, 2> pidx{0, 0};
+  cdb::SignalPads pads;
+  cdb::Mailbox mbox;
+  uint64_t epoch = 0;
+  std::set<void*> allocations; // from cudecompMalloc
+  // tuning knobs (autotuner / cudecompB200SetTuning)
+  int grid_ctas = 0;       // 0: all resident CTAs
+  bool force_staged = false;
+  int last_path = CUDECOMP_B200_PATH_NONE;
+};
+
+namespace cdb {
+
+void setGeometry(cudecompGridDesc_t gd, const std::array<int32_t, 2>& pdims);
+
+int64_t dtypeSize(cudecompDataType_t dtype);
+
+void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, void* input, void* output, void* work,
+                  cudecompDataType_t dtype, const int32_t in_halo[], const int32_t out_halo[], const int32_t in_pad[],
+                  const int32_t out_pad[], cudaStream_t stream);
+
+void runHalo(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, void* input, void* work, cudecompDataType_t dtype,
+             const int32_t halo[], const bool periods[], int dim, const int32_t pad[], cudaStream_t stream);
+
+// Raises INTERNAL_ERROR if a device-side wait of an earlier operation timed out.
+void checkDeviceError(cudecompGridDesc_t gd);
+
+// grid-descriptor autotuning (autotune.cc)
+void autotune(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecompGridDescAutotuneOptions_t* options);
+
+} // namespace cdb
+
+#endif

@@ -1,0 +1,260 @@
+// Box-copy kernels for sm_100a. See kernels.h.
+//
+// Data path per box: coalesced 16-byte loads from the local pencil (LDG.128, streaming), 16-byte stores
+// to the destination (STG.128) which is either local HBM or a peer GPU's memory mapped over NVLink.
+// The kernels are persistent: a fixed grid of CTAs walks the tile list, and consecutive tiles belong
+// to different peers so every peer's ingress is fed evenly for the whole duration of the launch.
+//
+// Cross-GPU ordering lives in the same launch (no host synchronisation, no second kernel):
+//   entry : CTA 0 stores the operation's epoch into slot [me] of each peer's signal pad; every CTA then
+//           waits until the local pad shows that epoch for each peer. A peer's kernel only starts after
+//           that peer's earlier stream work, so from here on its buffers may be overwritten.
+//   exit  : each CTA fences its stores (fence.sys) and bumps a local counter; the last CTA publishes
+//           "done" to every peer and waits for every peer's "done". Kernel completion therefore means
+//           both "my data has landed everywhere" and "everyone's data has landed here".
+#include "kernels.h"
+
+#include <atomic>
+
+namespace cdb {
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+
+__device__ __forceinline__ uint64_t ldAcquireSys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void stReleaseSys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ uint64_t globalTimerNs() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Spin until *flag >= epoch. Gives up after timeout_ns and records the failure for the host: a peer that
+// never arrives (crashed rank, mismatched call sequence) must not wedge the GPU.
+__device__ __noinline__ void waitFlag(const uint64_t* flag, const SyncParams& s, uint32_t code) {
+  if (ldAcquireSys(flag) >= s.epoch) return;
+  const uint64_t t0 = globalTimerNs();
+  uint32_t spins = 0;
+  while (ldAcquireSys(flag) < s.epoch) {
+    ++spins;
+    if (spins > 32) __nanosleep(spins > 4096 ? 1000 : 50);
+    if ((spins & 255u) == 0 && globalTimerNs() - t0 > s.timeout_ns) {
+      if (s.error_word) {
+        *reinterpret_cast<volatile uint32_t*>(s.error_word) = code;
+        __threadfence_system();
+      }
+      return;
+    }
+  }
+}
+
+__device__ __forceinline__ void syncEntry(const SyncParams& s) {
+  if (s.my_pad == nullptr || s.npeers == 0 || !s.do_entry) return;
+  const int t = threadIdx.x;
+  if (t < s.npeers) {
+    if (blockIdx.x == 0) stReleaseSys(s.peer_pad[t] + kPadEntry + s.my_world, s.epoch);
+    waitFlag(s.my_pad + kPadEntry + s.peer_world[t], s, 1u);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void syncExit(const SyncParams& s) {
+  if (s.my_pad == nullptr || s.npeers == 0 || !s.do_exit) return;
+  __shared__ uint32_t is_last;
+  __threadfence_system(); // my stores (local and peer) are performed before anything that follows
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* ctr = reinterpret_cast<unsigned long long*>(s.my_pad + kPadCounter);
+    const unsigned long long old = atomicAdd(ctr, 1ull);
+    is_last = (old == static_cast<unsigned long long>(gridDim.x) - 1ull) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence_system(); // order the other CTAs' (already fenced) stores before the flags below
+  const int t = threadIdx.x;
+  if (t < s.npeers) {
+    stReleaseSys(s.peer_pad[t] + kPadExit + s.my_world, s.epoch);
+    waitFlag(s.my_pad + kPadExit + s.peer_world[t], s, 2u);
+  }
+  if (t == 0) *reinterpret_cast<volatile unsigned long long*>(s.my_pad + kPadCounter) = 0ull;
+}
+
+template <typename V> __device__ __forceinline__ V loadStream(const V* p) { return __ldcs(p); }
+template <typename V> __device__ __forceinline__ void storeStream(V* p, const V& v) { __stcs(p, v); }
+
+// ---------------------------------------------------------------------------------------------
+// ROWCOPY: every box is a grid of rows that are contiguous on both sides. V is the widest vector all
+// addresses and strides of the launch are aligned to (16, 8 or 4 bytes).
+// A tile is rows_per_tile rows x seg_vecs vectors (about 32 KiB); inside a tile each warp takes
+// 128-vector pieces (4 independent loads per lane in flight, then 4 stores).
+// ---------------------------------------------------------------------------------------------
+template <typename V> __global__ void __launch_bounds__(256) rowCopyKernel(const __grid_constant__ CopyParams p) {
+  syncEntry(p.sync);
+
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t nwarps = blockDim.x >> 5;
+  const uint32_t total = p.nboxes * p.max_tiles;
+  constexpr uint32_t kUnroll = 4;
+  constexpr uint32_t kPiece = 32 * kUnroll;
+
+  for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const uint32_t b = t % p.nboxes;
+    const uint32_t j = t / p.nboxes;
+    const KBox& bx = p.box[b];
+    if (j >= bx.tiles) continue;
+    const uint32_t seg = j % bx.segs_per_row;
+    const uint32_t row_tile = j / bx.segs_per_row;
+    const int64_t row0 = static_cast<int64_t>(row_tile) * bx.rows_per_tile;
+    const int64_t nrows = bx.n[1] * bx.n[2];
+    const uint32_t c0 = seg * bx.seg_vecs;
+    const uint32_t nvec = min(bx.seg_vecs, bx.row_vecs - c0);
+    const uint32_t pieces_per_row = (nvec + kPiece - 1) / kPiece;
+    const uint32_t rows_here = static_cast<uint32_t>(min(static_cast<int64_t>(bx.rows_per_tile), nrows - row0));
+    const uint32_t npieces = rows_here * pieces_per_row;
+    const int64_t esz = p.elem_size;
+
+    for (uint32_t pc = warp; pc < npieces; pc += nwarps) {
+      const uint32_t r = pc / pieces_per_row;
+      const uint32_t q = pc - r * pieces_per_row;
+      const int64_t row = row0 + r;
+      const int64_t i1 = row % bx.n[1];
+      const int64_t i2 = row / bx.n[1];
+      const V* s = reinterpret_cast<const V*>(bx.src + (i1 * bx.ss[1] + i2 * bx.ss[2]) * esz) + c0;
+      V* d = reinterpret_cast<V*>(bx.dst + (i1 * bx.ds[1] + i2 * bx.ds[2]) * esz) + c0;
+      const uint32_t base = q * kPiece + lane;
+      V v[kUnroll];
+#pragma unroll
+      for (uint32_t k = 0; k < kUnroll; ++k) {
+        const uint32_t idx = base + 32u * k;
+        if (idx < nvec) v[k] = loadStream(s + idx);
+      }
+#pragma unroll
+      for (uint32_t k = 0; k < kUnroll; ++k) {
+        const uint32_t idx = base + 32u * k;
+        if (idx < nvec) storeStream(d + idx, v[k]);
+      }
+    }
+  }
+
+  syncExit(p.sync);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TRANSPOSE: source is contiguous along axis 0, destination along axis 1 (memory orders differ, e.g.
+// axis-contiguous layouts). 32x32 element tiles through shared memory: coalesced on both sides.
+// T is the element itself (4, 8 or 16 bytes).
+// ---------------------------------------------------------------------------------------------
+template <typename T> __global__ void __launch_bounds__(256) transposeKernel(const __grid_constant__ CopyParams p) {
+  __shared__ T tile[32][33];
+  syncEntry(p.sync);
+
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t wrow = threadIdx.x >> 5; // 0..7
+  const uint32_t total = p.nboxes * p.max_tiles;
+
+  for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const uint32_t b = t % p.nboxes;
+    const uint32_t j = t / p.nboxes;
+    const KBox& bx = p.box[b];
+    if (j < bx.tiles) { // uniform per CTA
+      const uint32_t j0 = j % bx.tiles0;
+      const uint32_t j1 = (j / bx.tiles0) % bx.tiles1;
+      const int64_t i2 = j / (bx.tiles0 * bx.tiles1);
+      const T* s = reinterpret_cast<const T*>(bx.src) + i2 * bx.ss[2];
+      T* d = reinterpret_cast<T*>(bx.dst) + i2 * bx.ds[2];
+      {
+        const int64_t i0 = static_cast<int64_t>(j0) * 32 + lane;
+#pragma unroll
+        for (uint32_t r = 0; r < 32; r += 8) {
+          const int64_t i1 = static_cast<int64_t>(j1) * 32 + r + wrow;
+          if (i0 < bx.n[0] && i1 < bx.n[1]) tile[r + wrow][lane] = s[i0 * bx.ss[0] + i1 * bx.ss[1]];
+        }
+      }
+      __syncthreads();
+      {
+        const int64_t i1 = static_cast<int64_t>(j1) * 32 + lane;
+#pragma unroll
+        for (uint32_t r = 0; r < 32; r += 8) {
+          const int64_t i0 = static_cast<int64_t>(j0) * 32 + r + wrow;
+          if (i0 < bx.n[0] && i1 < bx.n[1]) d[i0 * bx.ds[0] + i1 * bx.ds[1]] = tile[lane][r + wrow];
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  syncExit(p.sync);
+}
+
+using KernelFn = void (*)(const CopyParams);
+
+KernelFn pickKernel(KernelKind kind, int size) {
+  if (kind == KernelKind::ROWCOPY) {
+    switch (size) {
+    case 16: return rowCopyKernel<uint4>;
+    case 8: return rowCopyKernel<uint2>;
+    case 4: return rowCopyKernel<uint32_t>;
+    }
+  } else {
+    switch (size) {
+    case 16: return transposeKernel<uint4>;
+    case 8: return transposeKernel<uint2>;
+    case 4: return transposeKernel<uint32_t>;
+    }
+  }
+  return nullptr;
+}
+
+} // namespace
+
+int maxResidentCtas(KernelKind kind, int size, int threads) {
+  static int cache[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  static int cache_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev != cache_dev) {
+    for (auto& row : cache)
+      for (int& v : row) v = 0;
+    cache_dev = dev;
+  }
+  const int ki = (kind == KernelKind::ROWCOPY) ? 0 : 1;
+  const int si = (size == 16) ? 2 : (size == 8 ? 1 : 0);
+  if (threads == 256 && cache[ki][si] > 0) return cache[ki][si];
+  KernelFn fn = pickKernel(kind, size);
+  int per_sm = 0, sms = 0;
+  if (!fn || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  const int total = per_sm * sms;
+  if (threads == 256) cache[ki][si] = total;
+  return total;
+}
+
+cudaError_t launchCopy(KernelKind kind, const CopyParams& p, const LaunchConfig& cfg, cudaStream_t stream) {
+  const int size = (kind == KernelKind::ROWCOPY) ? static_cast<int>(p.vec_size) : static_cast<int>(p.elem_size);
+  KernelFn fn = pickKernel(kind, size);
+  if (!fn) return cudaErrorInvalidValue;
+  const uint64_t total = static_cast<uint64_t>(p.nboxes) * p.max_tiles;
+  int grid = cfg.grid;
+  const int resident = maxResidentCtas(kind, size, cfg.threads);
+  if (resident <= 0) return cudaErrorInvalidDevice;
+  if (grid <= 0 || grid > resident) grid = resident;
+  if (static_cast<uint64_t>(grid) > total) grid = static_cast<int>(total);
+  if (grid < 1) grid = 1; // still runs the handshake when this rank has nothing to move
+  fn<<<grid, cfg.threads, 0, stream>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+uint64_t launchCount() { return g_launches.load(std::memory_order_relaxed); }
+
+} // namespace cdb

@@ -1,0 +1,354 @@
+// See peer.h.
+#include "peer.h"
+
+#include <cuda.h>
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "errors.h"
+#include "kernels.h"
+
+namespace cdb {
+
+namespace {
+
+// Driver entry points are fetched through the runtime so the library has no link-time dependency on
+// libcuda.so and still loads on a machine without a GPU.
+using PfnGetAddressRange = CUresult (*)(CUdeviceptr*, size_t*, CUdeviceptr);
+using PfnPointerGetAttribute = CUresult (*)(void*, CUpointer_attribute, CUdeviceptr);
+
+struct DriverApi {
+  PfnGetAddressRange getAddressRange = nullptr;
+  PfnPointerGetAttribute pointerGetAttribute = nullptr;
+  bool ok = false;
+};
+
+const DriverApi& driverApi() {
+  static DriverApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      api.getAddressRange = reinterpret_cast<PfnGetAddressRange>(fn);
+    fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      api.pointerGetAttribute = reinterpret_cast<PfnPointerGetAttribute>(fn);
+    (void)cudaGetLastError();
+    api.ok = api.getAddressRange && api.pointerGetAttribute;
+  });
+  return api;
+}
+
+struct ExportEntry {
+  uint64_t buffer_id;
+  uint64_t size;
+  cudaIpcMemHandle_t handle;
+  bool exportable;
+};
+std::map<uint64_t, ExportEntry> g_exports; // by allocation base
+
+double nowSeconds() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+void describeBuffer(const void* ptr, BufDesc* d) {
+  std::memset(d, 0, sizeof(*d));
+  if (!ptr) return;
+  static const bool disabled = [] {
+    const char* v = std::getenv("CUDECOMP_B200_DISABLE_IPC");
+    return v && *v && std::strcmp(v, "0") != 0;
+  }();
+  if (disabled) return;
+  const DriverApi& api = driverApi();
+  if (!api.ok) return;
+
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+    (void)cudaGetLastError();
+    return;
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (api.getAddressRange(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS) return;
+  unsigned long long buffer_id = 0;
+  if (api.pointerGetAttribute(&buffer_id, CU_POINTER_ATTRIBUTE_BUFFER_ID, reinterpret_cast<CUdeviceptr>(ptr)) !=
+      CUDA_SUCCESS)
+    return;
+
+  auto it = g_exports.find(static_cast<uint64_t>(base));
+  if (it == g_exports.end() || it->second.buffer_id != buffer_id) {
+    ExportEntry e{};
+    e.buffer_id = buffer_id;
+    e.size = size;
+    e.exportable = (cudaIpcGetMemHandle(&e.handle, reinterpret_cast<void*>(base)) == cudaSuccess);
+    if (!e.exportable) (void)cudaGetLastError();
+    g_exports[static_cast<uint64_t>(base)] = e;
+    it = g_exports.find(static_cast<uint64_t>(base));
+  }
+  const ExportEntry& e = it->second;
+  d->handle = e.handle;
+  d->offset = reinterpret_cast<uint64_t>(ptr) - static_cast<uint64_t>(base);
+  d->alloc_size = e.size;
+  d->buffer_id = e.buffer_id;
+  d->exportable = e.exportable ? 1u : 0u;
+}
+
+// ------------------------------------------------------------------------------------------ PeerCache
+
+PeerCache::~PeerCache() { clear(); }
+
+void* PeerCache::resolve(int owner, const BufDesc& d) {
+  if (!d.exportable) THROW_INTERNAL_ERROR("peer buffer is not exportable");
+  Key k{owner, d.buffer_id, std::string(reinterpret_cast<const char*>(&d.handle), sizeof(d.handle))};
+  auto it = map_.find(k);
+  if (it == map_.end()) {
+    evictIfNeeded();
+    void* base = nullptr;
+    cudaError_t err = cudaIpcOpenMemHandle(&base, d.handle, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+      (void)cudaGetLastError();
+      THROW_CUDA_ERROR(std::string("cudaIpcOpenMemHandle failed for a buffer of rank ") + std::to_string(owner) +
+                       ": " + cudaGetErrorString(err) +
+                       " (peer-to-peer access between the ranks' GPUs is required)");
+    }
+    it = map_.emplace(k, Entry{base, 0}).first;
+  }
+  it->second.last_use = ++tick_;
+  return static_cast<char*>(it->second.base) + d.offset;
+}
+
+void PeerCache::forget(int owner, const BufDesc& d) {
+  Key k{owner, d.buffer_id, std::string(reinterpret_cast<const char*>(&d.handle), sizeof(d.handle))};
+  auto it = map_.find(k);
+  if (it == map_.end()) return;
+  cudaIpcCloseMemHandle(it->second.base);
+  (void)cudaGetLastError();
+  map_.erase(it);
+}
+
+void PeerCache::evictIfNeeded() {
+  constexpr size_t kMaxEntries = 256;
+  if (map_.size() < kMaxEntries) return;
+  // an import may still be the target of a running kernel: drain the device before unmapping
+  cudaDeviceSynchronize();
+  while (map_.size() >= kMaxEntries / 2) {
+    auto victim = map_.begin();
+    for (auto it = map_.begin(); it != map_.end(); ++it)
+      if (it->second.last_use < victim->second.last_use) victim = it;
+    cudaIpcCloseMemHandle(victim->second.base);
+    map_.erase(victim);
+  }
+  (void)cudaGetLastError();
+}
+
+void PeerCache::clear() {
+  if (map_.empty()) return;
+  cudaDeviceSynchronize();
+  for (auto& kv : map_) cudaIpcCloseMemHandle(kv.second.base);
+  (void)cudaGetLastError();
+  map_.clear();
+}
+
+// -------------------------------------------------------------------------------------------- Mailbox
+
+Mailbox::~Mailbox() {
+  if (base_) munmap(base_, bytes_);
+}
+
+Mailbox::Slot* Mailbox::slot(int rank, int channel, int parity) {
+  constexpr size_t kSlotBytes = 256;
+  static_assert(sizeof(Slot) <= kSlotBytes, "mailbox slot too small");
+  char* p = static_cast<char*>(base_) + (static_cast<size_t>(rank) * 4 + channel * 2 + parity) * kSlotBytes;
+  return reinterpret_cast<Slot*>(p);
+}
+
+void Mailbox::create(Comm& comm, uint64_t token, int instance) {
+  nranks_ = comm.size();
+  me_ = comm.rank();
+  bytes_ = static_cast<size_t>(nranks_) * 4 * 256;
+  if (const char* v = std::getenv("CUDECOMP_B200_HOST_TIMEOUT")) timeout_s_ = std::atof(v);
+  char name[96];
+  std::snprintf(name, sizeof(name), "/cudecomp_b200_%016llx_%d", static_cast<unsigned long long>(token), instance);
+  name_ = name;
+
+  int32_t ok = 1;
+  if (me_ == 0) {
+    int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, static_cast<off_t>(bytes_)) != 0) ok = 0;
+    if (ok) {
+      base_ = mmap(nullptr, bytes_, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+      if (base_ == MAP_FAILED) {
+        base_ = nullptr;
+        ok = 0;
+      } else {
+        std::memset(base_, 0, bytes_);
+      }
+    }
+    if (fd >= 0) close(fd);
+  }
+  bcast(comm, &ok, sizeof(ok), 0);
+  if (ok && me_ != 0) {
+    int fd = shm_open(name, O_RDWR, 0600);
+    if (fd >= 0) {
+      base_ = mmap(nullptr, bytes_, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+      if (base_ == MAP_FAILED) base_ = nullptr;
+      close(fd);
+    }
+  }
+  int64_t all_ok = (ok && base_) ? 1 : 0;
+  allreduceI64(comm, &all_ok, 1, ReduceOp::MIN);
+  if (me_ == 0) shm_unlink(name); // the mappings keep the segment alive; nothing is left behind on a crash
+  if (!all_ok) {
+    if (base_) munmap(base_, bytes_);
+    base_ = nullptr;
+    THROW_INTERNAL_ERROR("cannot create the shared-memory mailbox (is /dev/shm available to all ranks of the node?)");
+  }
+  seq_[0] = seq_[1] = 0;
+}
+
+void Mailbox::destroy() {
+  if (base_) munmap(base_, bytes_);
+  base_ = nullptr;
+}
+
+void Mailbox::reset(Comm& comm) {
+  if (!base_) return;
+  barrier(comm);
+  for (int ch = 0; ch < 2; ++ch) {
+    for (int par = 0; par < 2; ++par) slot(me_, ch, par)->seq.store(0, std::memory_order_release);
+    seq_[ch] = 0;
+  }
+  barrier(comm);
+}
+
+void Mailbox::exchange(int channel, const std::vector<int>& members, int my_index, const CallMsg& mine,
+                       std::vector<CallMsg>& out) {
+  if (!base_) THROW_INTERNAL_ERROR("mailbox not initialised");
+  const uint64_t n = ++seq_[channel];
+  const int par = static_cast<int>(n & 1);
+  Slot* s = slot(me_, channel, par);
+  s->msg = mine;
+  s->seq.store(n, std::memory_order_release);
+
+  out.resize(members.size());
+  for (size_t i = 0; i < members.size(); ++i) {
+    if (static_cast<int>(i) == my_index) {
+      out[i] = mine;
+      continue;
+    }
+    Slot* ps = slot(members[i], channel, par);
+    double t0 = 0;
+    uint32_t spins = 0;
+    for (;;) {
+      const uint64_t v = ps->seq.load(std::memory_order_acquire);
+      if (v == n) break;
+      if (v > n) THROW_INTERNAL_ERROR("mailbox sequence overrun: ranks issued collective calls in different orders");
+      if (++spins > 2000) {
+        sched_yield();
+        if ((spins & 1023) == 0) {
+          if (t0 == 0) t0 = nowSeconds();
+          if (nowSeconds() - t0 > timeout_s_)
+            THROW_INTERNAL_ERROR("timed out waiting for rank " + std::to_string(members[i]) +
+                                 " to enter the same collective call");
+        }
+      }
+    }
+    out[i] = ps->msg;
+    if (out[i].opcode != mine.opcode)
+      THROW_INVALID_USAGE("ranks of one communicator entered different cuDecomp operations");
+  }
+}
+
+// ----------------------------------------------------------------------------------------- SignalPads
+
+SignalPads::~SignalPads() {
+  // process teardown without GridDescDestroy: leave the memory to the driver
+}
+
+void SignalPads::create(Comm& comm) {
+  const int n = comm.size();
+  if (n > kPadMaxRanks) THROW_NOT_SUPPORTED("more ranks than the signal pad supports");
+  const size_t bytes = 4096;
+  static_assert(kPadWords * sizeof(uint64_t) <= 4096, "signal pad larger than its page");
+  void* p = nullptr;
+  CHECK_CUDA(cudaMalloc(&p, bytes));
+  mine_ = static_cast<uint64_t*>(p);
+  CHECK_CUDA(cudaMemset(mine_, 0, bytes));
+  CHECK_CUDA(cudaDeviceSynchronize());
+  void* eh = nullptr;
+  CHECK_CUDA(cudaHostAlloc(&eh, 64, cudaHostAllocMapped));
+  err_host_ = static_cast<uint32_t*>(eh);
+  std::memset(eh, 0, 64);
+  void* ed = nullptr;
+  CHECK_CUDA(cudaHostGetDevicePointer(&ed, eh, 0));
+  err_dev_ = static_cast<uint32_t*>(ed);
+
+  pads_.assign(n, nullptr);
+  imported_.assign(n, false);
+  pads_[comm.rank()] = mine_;
+  if (n == 1) return;
+
+  struct Msg {
+    cudaIpcMemHandle_t h;
+    int32_t ok;
+  } mine{};
+  mine.ok = (cudaIpcGetMemHandle(&mine.h, mine_) == cudaSuccess) ? 1 : 0;
+  if (!mine.ok) (void)cudaGetLastError();
+  std::vector<Msg> all(n);
+  allgather(comm, &mine, sizeof(Msg), all.data());
+  std::string failure;
+  for (int r = 0; r < n && failure.empty(); ++r) {
+    if (r == comm.rank()) continue;
+    if (!all[r].ok) {
+      failure = "rank " + std::to_string(r) + " cannot export device memory with CUDA IPC";
+      break;
+    }
+    void* q = nullptr;
+    cudaError_t err = cudaIpcOpenMemHandle(&q, all[r].h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+      (void)cudaGetLastError();
+      failure = std::string("cannot map the signal pad of rank ") + std::to_string(r) + ": " + cudaGetErrorString(err);
+      break;
+    }
+    pads_[r] = static_cast<uint64_t*>(q);
+    imported_[r] = true;
+  }
+  int64_t bad = failure.empty() ? 0 : 1;
+  allreduceI64(comm, &bad, 1, ReduceOp::MAX);
+  if (bad) {
+    if (failure.empty()) failure = "another rank failed to map the signal pads";
+    THROW_CUDA_ERROR(failure + " (all ranks must be on GPUs of one node with peer-to-peer access)");
+  }
+}
+
+void SignalPads::destroy(Comm* comm) {
+  if (!mine_) return;
+  cudaDeviceSynchronize();
+  for (size_t r = 0; r < pads_.size(); ++r)
+    if (imported_[r] && pads_[r]) cudaIpcCloseMemHandle(pads_[r]);
+  pads_.clear();
+  imported_.clear();
+  if (comm && comm->size() > 1) barrier(*comm);
+  cudaFree(mine_);
+  mine_ = nullptr;
+  if (err_host_) cudaFreeHost(err_host_);
+  err_host_ = nullptr;
+  err_dev_ = nullptr;
+  (void)cudaGetLastError();
+}
+
+} // namespace cdb

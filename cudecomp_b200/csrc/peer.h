@@ -1,0 +1,140 @@
+// Cross-process peer memory: how a rank obtains a pointer it can store through into another rank's
+// buffer. Ranks are separate processes on one NVSwitch domain.
+//
+// Replaces the reference's transport setup (NCCL communicators src/cudecomp.cc:59-72,1152-1182; NVSHMEM
+// symmetric heap :1470-1496; cuMem fabric handles :1508-1602).  Design:
+//   * every buffer a peer must write (workspace, and the user's output / halo buffer when it is plain
+//     device memory) is exported lazily with CUDA IPC and imported once per peer (PeerCache);
+//   * per collective call the members of the row/column communicator swap one small descriptor through a
+//     shared-memory mailbox (Mailbox) -- which buffer + offset each rank is using in THIS call and
+//     whether it could be exported -- so all members take the same direct/staged decision without a
+//     socket round trip;
+//   * a 4 KiB signal pad per grid descriptor carries the device-side entry/exit flags (SignalPads).
+#ifndef CUDECOMP_B200_PEER_H
+#define CUDECOMP_B200_PEER_H
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "bootstrap.h"
+
+namespace cdb {
+
+// What a rank tells its peers about one buffer argument of the current call.
+struct BufDesc {
+  cudaIpcMemHandle_t handle; // of the allocation containing the pointer
+  uint64_t offset;           // pointer - allocation base
+  uint64_t alloc_size;
+  uint64_t buffer_id;        // CU_POINTER_ATTRIBUTE_BUFFER_ID: unique per allocation, guards handle reuse
+  uint32_t exportable;       // 0: cannot be mapped by peers (managed, host, pool memory, ...)
+  uint32_t pad_;
+};
+
+struct CallMsg {
+  uint32_t opcode; // must match on all members (catches mismatched collective calls)
+  uint32_t flags;
+  BufDesc data;    // transpose: output buffer; halo: the pencil buffer
+  BufDesc work;    // workspace
+};
+
+// Fills `d` for a local device pointer. Never throws: failure means exportable = 0.
+void describeBuffer(const void* ptr, BufDesc* d);
+
+// Imported peer allocations, keyed by (rank, buffer id, handle bytes).
+class PeerCache {
+public:
+  ~PeerCache();
+  // Pointer in MY address space for `d` owned by world rank `owner`. Throws CUDA_ERROR if the import fails.
+  void* resolve(int owner, const BufDesc& d);
+  // Drop every import that refers to one of these buffers (owner frees it next).
+  void forget(int owner, const BufDesc& d);
+  void clear();
+
+private:
+  struct Key {
+    int owner;
+    uint64_t buffer_id;
+    std::string handle;
+    bool operator<(const Key& o) const {
+      if (owner != o.owner) return owner < o.owner;
+      if (buffer_id != o.buffer_id) return buffer_id < o.buffer_id;
+      return handle < o.handle;
+    }
+  };
+  struct Entry {
+    void* base;
+    uint64_t last_use;
+  };
+  std::map<Key, Entry> map_;
+  uint64_t tick_ = 0;
+  void evictIfNeeded();
+};
+
+// Shared-memory mailbox: a host-side all-gather of CallMsg among the members of one communicator,
+// a few hundred nanoseconds when everybody is already there. One segment per grid descriptor.
+class Mailbox {
+public:
+  Mailbox() = default;
+  ~Mailbox();
+  Mailbox(const Mailbox&) = delete;
+  Mailbox& operator=(const Mailbox&) = delete;
+
+  // Collective over `comm` (creates and maps the segment).
+  void create(Comm& comm, uint64_t token, int instance);
+  void destroy();
+  bool valid() const { return base_ != nullptr; }
+
+  // Exchange on channel 0 (column groups) or 1 (row groups). `members` are indices into the creating
+  // communicator; out[i] receives member i's message. Every member of the group must call this for every
+  // operation on that channel, in the same order.
+  void exchange(int channel, const std::vector<int>& members, int my_index, const CallMsg& mine,
+                std::vector<CallMsg>& out);
+  // forget all sequence numbers (collective; used when the process grid changes during autotuning)
+  void reset(Comm& comm);
+
+private:
+  struct Slot {
+    std::atomic<uint64_t> seq;
+    CallMsg msg;
+  };
+  Slot* slot(int rank, int channel, int parity);
+  void* base_ = nullptr;
+  size_t bytes_ = 0;
+  int nranks_ = 0;
+  int me_ = 0;
+  uint64_t seq_[2] = {0, 0};
+  std::string name_;
+  double timeout_s_ = 120.0;
+};
+
+// Device-side flag pages (see kernels.h) of all ranks of a grid descriptor.
+class SignalPads {
+public:
+  ~SignalPads();
+  void create(Comm& comm); // collective: allocate, zero, export, import everybody's
+  void destroy(Comm* comm); // collective when comm != nullptr: nobody frees before everybody unmapped
+  bool valid() const { return mine_ != nullptr; }
+  uint64_t* mine() const { return mine_; }
+  uint64_t* of(int rank) const { return pads_[rank]; }
+  uint32_t* errorWordDevice() const { return err_dev_; }
+  uint32_t errorWordHost() const { return err_host_ ? *reinterpret_cast<volatile uint32_t*>(err_host_) : 0u; }
+  void clearError() {
+    if (err_host_) *reinterpret_cast<volatile uint32_t*>(err_host_) = 0u;
+  }
+
+private:
+  uint64_t* mine_ = nullptr;
+  std::vector<uint64_t*> pads_;
+  std::vector<bool> imported_;
+  uint32_t* err_host_ = nullptr; // pinned, mapped
+  uint32_t* err_dev_ = nullptr;
+};
+
+} // namespace cdb
+
+#endif

@@ -1,0 +1,277 @@
+// See plan.h.
+#include "plan.h"
+
+#include <algorithm>
+
+#include "errors.h"
+
+namespace cdb {
+
+static bool same3(const int32_t* a, const int32_t* b) {
+  for (int i = 0; i < 3; ++i)
+    if ((a ? a[i] : 0) != (b ? b[i] : 0)) return false;
+  return true;
+}
+
+static int64_t dot3(const std::array<int64_t, 3>& a, const std::array<int64_t, 3>& b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+
+TransposePlan buildTransposePlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dir,
+                                 const int32_t in_halo[3], const int32_t out_halo[3], const int32_t in_pad[3],
+                                 const int32_t out_pad[3], DstKind kind, bool inplace) {
+  TransposePlan plan;
+  plan.axes = transposeAxes(ax, dir);
+  const int a = plan.axes.a, b = plan.axes.b, c = plan.axes.c;
+  const int ci = plan.axes.comm; // pdims/pidx slot of the communicator
+
+  // geometry first, so bad halo/padding arguments are reported before anything else (reference order,
+  // transpose.h:248-259)
+  const Pencil pa = pencilInfo(g, pidx, a, nullptr, nullptr);
+  const Pencil pa_h = pencilInfo(g, pidx, a, in_halo, in_pad);
+  const Pencil pb = pencilInfo(g, pidx, b, nullptr, nullptr);
+  const Pencil pb_h = pencilInfo(g, pidx, b, out_halo, out_pad);
+  if (hasEmptyPencils(g, a) || hasEmptyPencils(g, b))
+    THROW_NOT_SUPPORTED("transposes on configurations with empty pencils not supported");
+
+  const int P = g.pdims[ci];
+  const int me = pidx[ci];
+  plan.comm_size = P;
+  plan.me = me;
+  for (int i = 0; i < P; ++i) {
+    auto pp = pidx;
+    pp[ci] = i;
+    plan.group_world.push_back(rankOfPidx(g, pp));
+  }
+
+  const auto splits_a = getSplits(g.gdims_dist[a], P, g.gdims[a] - g.gdims_dist[a]);
+  const auto splits_b = getSplits(g.gdims_dist[b], P, g.gdims[b] - g.gdims_dist[b]);
+  const auto off_a = prefixOffsets(splits_a);
+  const auto off_b = prefixOffsets(splits_b);
+
+  const bool orders_equal = (pa.order == pb.order);
+  const bool halos_equal = same3(in_halo, out_halo) && same3(in_pad, out_pad);
+  if (P == 1 && inplace && orders_equal && halos_equal) {
+    plan.noop = true; // reference transpose.h:326-341
+    return plan;
+  }
+
+  const auto shape_a = pa.shapeG();
+  if (shape_a[b] != splits_b[me]) THROW_INTERNAL_ERROR("pencil/split mismatch");
+  const auto sstr = pa_h.strideG();
+  plan.src_elems = pa.size;
+
+  for (int i = 0; i < P; ++i) {
+    auto pp = pidx;
+    pp[ci] = i;
+    BoxDesc bx;
+    bx.peer = i;
+    bx.peer_world = plan.group_world[i];
+    bx.ext[a] = splits_a[i];
+    bx.ext[b] = shape_a[b];
+    bx.ext[c] = shape_a[c];
+    std::array<int64_t, 3> s0{}, d0{};
+    s0[a] = off_a[i] + pa_h.halo[a];
+    s0[b] = pa_h.halo[b];
+    s0[c] = pa_h.halo[c];
+    bx.sstr = sstr;
+    bx.src_off = dot3(s0, sstr);
+    if (kind == DstKind::FINAL) {
+      const Pencil q = pencilInfo(g, pp, b, out_halo, out_pad);
+      bx.dstr = q.strideG();
+      d0[a] = q.halo[a];
+      d0[b] = off_b[me] + q.halo[b];
+      d0[c] = q.halo[c];
+    } else {
+      const Pencil q = pencilInfo(g, pp, b, nullptr, nullptr);
+      bx.dstr = q.strideG();
+      d0[b] = off_b[me];
+    }
+    bx.dst_off = dot3(d0, bx.dstr);
+    if (i != me) plan.wire_elems += bx.count();
+    plan.push.push_back(bx);
+  }
+
+  if (kind == DstKind::STAGE) {
+    BoxDesc u;
+    u.peer = me;
+    u.peer_world = plan.group_world[me];
+    auto sb = pb.shapeG();
+    for (int k = 0; k < 3; ++k) u.ext[k] = sb[k];
+    u.sstr = pb.strideG();
+    u.dstr = pb_h.strideG();
+    std::array<int64_t, 3> d0{pb_h.halo[0], pb_h.halo[1], pb_h.halo[2]};
+    u.dst_off = dot3(d0, u.dstr);
+    plan.unpack.push_back(u);
+  }
+  return plan;
+}
+
+HaloPlan buildHaloPlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dim, const int32_t halo[3],
+                       const bool periods[3], const int32_t pad[3], DstKind kind) {
+  HaloPlan plan;
+  const Pencil ph = pencilInfo(g, pidx, ax, halo, nullptr);
+  const Pencil php = pencilInfo(g, pidx, ax, halo, pad);
+  if (hasEmptyPencils(g, ax)) THROW_NOT_SUPPORTED("halo operations on configurations with empty pencils not supported");
+
+  const bool periodic = periods ? periods[dim] : false;
+  const int hw = ph.halo[dim];
+  const int my_world = rankOfPidx(g, pidx);
+
+  if (dim == ax) {
+    plan.comm_size = 1;
+    plan.me = 0;
+    plan.group_world = {my_world};
+    plan.neighbor = periodic ? std::array<int, 2>{0, 0} : std::array<int, 2>{-1, -1};
+  } else {
+    plan.comm = haloCommAxis(ax, dim);
+    const int P = g.pdims[plan.comm];
+    plan.comm_size = P;
+    plan.me = pidx[plan.comm];
+    for (int i = 0; i < P; ++i) {
+      auto pp = pidx;
+      pp[plan.comm] = i;
+      plan.group_world.push_back(rankOfPidx(g, pp));
+    }
+    int l = plan.me - 1, r = plan.me + 1;
+    if (periodic) {
+      l = (l + P) % P;
+      r = r % P;
+    } else {
+      if (l < 0) l = -1;
+      if (r >= P) r = -1;
+    }
+    plan.neighbor = {l, r};
+  }
+
+  if (hw == 0) { // reference halo.h:70-71
+    plan.nothing = true;
+    return plan;
+  }
+  if (plan.neighbor[0] == -1 && plan.neighbor[1] == -1) {
+    plan.nothing = true;
+    return plan;
+  }
+  const bool self_only = (plan.neighbor[0] == plan.me && plan.neighbor[1] == plan.me);
+  if (!self_only) {
+    // the face must come from the nearest neighbour alone (reference halo.h:120-145)
+    const auto splits = getSplits(g.gdims_dist[dim], plan.comm_size, g.gdims[dim] - g.gdims_dist[dim]);
+    for (int nb : plan.neighbor) {
+      if (nb < 0) continue;
+      if (hw > splits[nb] || hw > splits[plan.me])
+        THROW_INVALID_USAGE(
+            "halo includes ranks other than nearest neighbor processes, this is not currently supported.");
+    }
+  }
+
+  const auto shape_h = ph.shapeG();   // halo-inclusive, padding-exclusive
+  const auto shape_hp = php.shapeG(); // what the buffer really is
+  const auto sstr = php.strideG();
+  std::array<int64_t, 3> ext{};
+  for (int k = 0; k < 3; ++k) ext[k] = (k == dim) ? hw : shape_h[k];
+  plan.face_elems = ext[0] * ext[1] * ext[2];
+  const int64_t slot = alignCount(plan.face_elems);
+
+  // dense strides of a face in the pencil's memory order
+  std::array<int64_t, 3> dense{};
+  {
+    int64_t acc = 1;
+    for (int k = 0; k < 3; ++k) {
+      dense[php.order[k]] = acc;
+      acc *= ext[php.order[k]];
+    }
+  }
+
+  for (int side = 0; side < 2; ++side) {
+    const int nb = plan.neighbor[side];
+    if (nb < 0) continue;
+    auto pp = pidx;
+    if (dim != ax) pp[plan.comm] = nb;
+    const Pencil q = pencilInfo(g, pp, ax, halo, pad);
+    const auto qshape = q.shapeG();
+
+    BoxDesc bx;
+    bx.peer = nb;
+    bx.peer_world = plan.group_world[nb];
+    bx.ext = ext;
+    bx.sstr = sstr;
+    std::array<int64_t, 3> s0{}, d0{};
+    // side 0: my first interior layers go to the left neighbour's right halo;
+    // side 1: my last interior layers go to the right neighbour's left halo
+    s0[dim] = (side == 0) ? hw : shape_hp[dim] - 2 * hw - php.pad[dim];
+    bx.src_off = dot3(s0, sstr);
+    if (kind == DstKind::FINAL) {
+      bx.dstr = q.strideG();
+      d0[dim] = (side == 0) ? qshape[dim] - hw - q.pad[dim] : 0;
+      bx.dst_off = dot3(d0, bx.dstr);
+    } else {
+      bx.dstr = dense;
+      bx.dst_off = (side == 0) ? slot : 0; // receiver slot 0 = its left halo, slot 1 = its right halo
+    }
+    plan.push.push_back(bx);
+  }
+
+  if (kind == DstKind::STAGE) {
+    for (int side = 0; side < 2; ++side) {
+      if (plan.neighbor[side] < 0) continue;
+      BoxDesc u;
+      u.peer = plan.me;
+      u.peer_world = my_world;
+      u.ext = ext;
+      u.sstr = dense;
+      u.src_off = (side == 0) ? 0 : slot;
+      u.dstr = sstr;
+      std::array<int64_t, 3> d0{};
+      d0[dim] = (side == 0) ? 0 : shape_hp[dim] - hw - php.pad[dim];
+      u.dst_off = dot3(d0, sstr);
+      plan.unpack.push_back(u);
+    }
+  }
+  return plan;
+}
+
+CanonBox canonicalize(const BoxDesc& b, bool merge) {
+  struct Ax {
+    int64_t n, ss, ds;
+  };
+  std::vector<Ax> axes;
+  for (int k = 0; k < 3; ++k)
+    if (b.ext[k] > 1) axes.push_back({b.ext[k], b.sstr[k], b.dstr[k]});
+  std::sort(axes.begin(), axes.end(), [](const Ax& x, const Ax& y) { return x.ss != y.ss ? x.ss < y.ss : x.ds < y.ds; });
+  if (merge) {
+    for (size_t k = 0; k + 1 < axes.size();) {
+      if (axes[k + 1].ss == axes[k].n * axes[k].ss && axes[k + 1].ds == axes[k].n * axes[k].ds) {
+        axes[k].n *= axes[k + 1].n;
+        axes.erase(axes.begin() + k + 1);
+      } else {
+        ++k;
+      }
+    }
+  }
+  // a box whose unit-stride axis has extent 1 still needs a (trivial) row axis
+  const bool has_row = !axes.empty() && axes[0].ss == 1 && axes[0].ds == 1;
+  bool transposable = false;
+  if (!axes.empty() && axes[0].ss == 1)
+    for (size_t k = 1; k < axes.size(); ++k)
+      if (axes[k].ds == 1) transposable = true;
+  if (!has_row && !transposable && axes.size() < 3) axes.insert(axes.begin(), Ax{1, 1, 1});
+  if (b.count() == 0) axes.assign(1, Ax{0, 1, 1});
+  if (axes.empty()) axes.push_back({1, 1, 1});
+
+  CanonBox c;
+  c.nd = static_cast<int>(axes.size());
+  for (int k = 0; k < 3; ++k) {
+    if (k < c.nd) {
+      c.n[k] = axes[k].n;
+      c.ss[k] = axes[k].ss;
+      c.ds[k] = axes[k].ds;
+    } else {
+      c.n[k] = 1;
+      c.ss[k] = 0;
+      c.ds[k] = 0;
+    }
+  }
+  return c;
+}
+
+} // namespace cdb

@@ -1,0 +1,91 @@
+// Transfer plans: which 3-D sub-block ("box") of my pencil goes where.
+//
+// The reference runs every transpose as pack -> all-to-all -> unpack through two staging regions
+// (reference include/internal/transpose.h:196-905). Here a transpose is described once as P boxes,
+// one per rank of the row/column communicator: the part of my source pencil whose `a` coordinate
+// belongs to peer i, addressed with my strides on the source side and with PEER i's strides on the
+// destination side. A single kernel then gathers each box from local HBM and stores it straight into
+// the peer's memory in its final layout, so pack, exchange and unpack are one pass.
+//
+// Halo exchange (reference include/internal/halo.h:40-315) uses the same representation with at most
+// two boxes (the faces for the left and right neighbour).
+#ifndef CUDECOMP_B200_PLAN_H
+#define CUDECOMP_B200_PLAN_H
+
+#include <array>
+#include <cstdint>
+#include <vector>
+
+#include "geometry.h"
+
+namespace cdb {
+
+// One box in element units; extents and strides are indexed by GLOBAL axis.
+struct BoxDesc {
+  int peer = 0;        // index of the destination rank inside the communicator
+  int peer_world = 0;  // its global rank
+  int64_t src_off = 0; // element offset of the first element in the source buffer
+  int64_t dst_off = 0; // element offset of the first element in the destination buffer
+  std::array<int64_t, 3> ext{};
+  std::array<int64_t, 3> sstr{};
+  std::array<int64_t, 3> dstr{};
+  int64_t count() const { return ext[0] * ext[1] * ext[2]; }
+};
+
+enum class DstKind {
+  FINAL, // the peer's user buffer (output pencil / halo region), final layout incl. halos and padding
+  STAGE  // the peer's workspace: dense destination pencil (transpose) or dense face slots (halo)
+};
+
+struct TransposePlan {
+  TransposeAxes axes{};
+  int comm_size = 1;
+  int me = 0;                   // my index in the communicator
+  std::vector<int> group_world; // global rank of each communicator member
+  bool noop = false;            // single rank, in place, identical layouts: nothing to do
+  std::vector<BoxDesc> push;    // one per peer (self included), source = input
+  std::vector<BoxDesc> unpack;  // STAGE only: dense pencil in my workspace -> output
+  int64_t src_elems = 0;        // elements of my source pencil interior (= what this rank sends, self included)
+  int64_t wire_elems = 0;       // elements that leave this GPU
+};
+
+// Builds the sender-side plan of transpose (ax, dir) for the rank at `pidx`.
+// Throws NOT_SUPPORTED for decompositions with empty pencils (reference transpose.h:257-259).
+TransposePlan buildTransposePlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dir,
+                                 const int32_t in_halo[3], const int32_t out_halo[3], const int32_t in_pad[3],
+                                 const int32_t out_pad[3], DstKind kind, bool inplace);
+
+struct HaloPlan {
+  bool nothing = false; // zero halo width, or no neighbour in this dimension
+  CommAxis comm = COMM_COL;
+  int comm_size = 1;
+  int me = 0;
+  std::vector<int> group_world;
+  std::array<int, 2> neighbor{-1, -1}; // communicator index of the left / right neighbour (-1: none)
+  std::vector<BoxDesc> push;           // faces I send; peer may be myself (periodic, single rank)
+  std::vector<BoxDesc> unpack;         // STAGE only: face slots in my workspace -> my halo cells
+  int64_t face_elems = 0;
+};
+
+HaloPlan buildHaloPlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dim, const int32_t halo[3],
+                       const bool periods[3], const int32_t pad[3], DstKind kind);
+
+// A box reduced to what a kernel needs: axes sorted by source stride, unit axes dropped, adjacent
+// axes merged when both sides allow it.
+struct CanonBox {
+  int nd = 1;                  // 1..3
+  std::array<int64_t, 3> n{1, 1, 1};
+  std::array<int64_t, 3> ss{1, 0, 0};
+  std::array<int64_t, 3> ds{1, 0, 0};
+  bool rowCopy() const { return ss[0] == 1 && ds[0] == 1; } // contiguous runs on both sides
+  int dstUnitAxis() const {                                 // axis with unit destination stride, -1 if none
+    for (int k = 0; k < nd; ++k)
+      if (ds[k] == 1) return k;
+    return -1;
+  }
+};
+CanonBox canonicalize(const BoxDesc& b, bool merge);
+
+} // namespace cdb
+
+#endif

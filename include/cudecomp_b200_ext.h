@@ -1,0 +1,54 @@
+/*
+ * cudecomp_b200_ext.h -- entry points of libcudecomp.so that have no counterpart in the reference ABI.
+ * Nothing here is needed by a drop-in caller; they exist for tests, benchmarks and tuning.
+ */
+#ifndef CUDECOMP_B200_EXT_H
+#define CUDECOMP_B200_EXT_H
+
+#include "cudecomp.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One transfer box of a plan, in elements; extents and strides are indexed by global axis (x, y, z). */
+typedef struct {
+  int32_t peer_rank;  /* global rank that owns the destination */
+  int32_t is_unpack;  /* 1: local workspace -> destination buffer copy of the staged path */
+  int64_t src_offset; /* first element in the source buffer */
+  int64_t dst_offset; /* first element in the destination buffer (of peer_rank) */
+  int64_t extent[3];
+  int64_t src_stride[3];
+  int64_t dst_stride[3];
+} cudecompB200Box_t;
+
+/* Number of copy kernels this process has launched so far. */
+cudecompResult_t cudecompB200GetLaunchCount(uint64_t* count);
+
+/* Path of the last transpose/halo call on the descriptor: 0 none, 1 local, 2 direct peer stores, 3 staged. */
+cudecompResult_t cudecompB200GetLastPath(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t* path);
+
+/* grid_ctas: CTAs per launch (0 = all resident CTAs); force_staged != 0 routes every exchange through the workspace. */
+cudecompResult_t cudecompB200SetTuning(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t grid_ctas,
+                                       int32_t force_staged);
+
+/* Reports (and clears) a device-side handshake timeout of an earlier operation. */
+cudecompResult_t cudecompB200CheckErrors(cudecompHandle_t handle, cudecompGridDesc_t grid_desc);
+
+/* The sender-side plan of a transpose (ax, dir) / halo update as this rank would execute it; needs no GPU.
+ * Returns the number of boxes (writes at most max_boxes), or -1 on error. staged != 0 describes the
+ * workspace-staged variant (push boxes followed by the unpack boxes). */
+int32_t cudecompB200DescribeTransposeBoxes(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t ax,
+                                           int32_t dir, const int32_t input_halo_extents[],
+                                           const int32_t output_halo_extents[], const int32_t input_padding[],
+                                           const int32_t output_padding[], int32_t staged, cudecompB200Box_t* boxes,
+                                           int32_t max_boxes);
+int32_t cudecompB200DescribeHaloBoxes(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t ax, int32_t dim,
+                                      const int32_t halo_extents[], const bool halo_periods[], const int32_t padding[],
+                                      int32_t staged, cudecompB200Box_t* boxes, int32_t max_boxes);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

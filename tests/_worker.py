@@ -1,0 +1,369 @@
+"""One rank of a multi-rank test run (started by tests/_launcher.py).
+
+mode 'gpu'  : runs each case through the C ABI of libcudecomp.so on this rank's GPU and checks the result against
+              (a) the analytic global-index pattern of the reference's tests and (b) the CPU oracle fed with the
+              same seeded inputs. Ranks share a GPU when there are fewer GPUs than ranks (the reference's tests do
+              the same under MPS, tests/README.md:69-82).
+mode 'plan' : host only. Dumps the rank's pencil infos and transfer plans so the parent can execute the plans with
+              numpy and compare with the oracle (covers the N>1 planning logic without a GPU).
+"""
+import ctypes
+import json
+import os
+import sys
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from cudecomp_b200 import capi as cd  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+DTYPES = {"float": (cd.CUDECOMP_FLOAT, np.float32), "double": (cd.CUDECOMP_DOUBLE, np.float64),
+          "float_complex": (cd.CUDECOMP_FLOAT_COMPLEX, np.complex64),
+          "double_complex": (cd.CUDECOMP_DOUBLE_COMPLEX, np.complex128)}
+OPS = ["XY", "YZ", "ZY", "YX"]
+
+
+def make_config(case):
+    c = cd.cudecompGridDescConfig_t()
+    cd.check(cd.cudecompGridDescConfigSetDefaults(c))
+    c.gdims[:] = case["gdims"]
+    c.pdims[:] = case["pdims"]
+    if case.get("gdims_dist"):
+        c.gdims_dist[:] = case["gdims_dist"]
+    c.rank_order = case.get("rank_order", 0)
+    c.transpose_comm_backend = case.get("backend", cd.CUDECOMP_TRANSPOSE_COMM_NCCL)
+    c.halo_comm_backend = case.get("halo_backend", cd.CUDECOMP_HALO_COMM_NCCL)
+    ac = case.get("axis_contiguous") or [False] * 3
+    for i in range(3):
+        c.transpose_axis_contiguous[i] = bool(ac[i])
+    mo = case.get("mem_order")
+    if mo:
+        for i in range(3):
+            for j in range(3):
+                c.transpose_mem_order[i][j] = mo[i][j]
+    return c
+
+
+def make_oracle(case, pdims=None):
+    return orc.Oracle(case["gdims"], pdims or case["pdims"], case.get("axis_contiguous") or (False,) * 3,
+                      case.get("mem_order"), case.get("gdims_dist"), case.get("rank_order", 0) == 2)
+
+
+def pinfo_to_py(p):
+    return orc.PencilInfo(p.shape, p.lo, p.hi, p.order, p.halo_extents, p.padding, p.size)
+
+
+def seeded(n, np_dtype, seed):
+    """Random bit patterns (finite values) -- the engine never computes on the payload."""
+    rng = np.random.default_rng(seed)
+    if np.issubdtype(np_dtype, np.complexfloating):
+        base = np.float32 if np_dtype == np.complex64 else np.float64
+        return (rng.standard_normal(n).astype(base) + 1j * rng.standard_normal(n).astype(base)).astype(np_dtype)
+    return rng.standard_normal(n).astype(np_dtype)
+
+
+# ------------------------------------------------------------------------------------------------- gpu mode
+class Gpu:
+    def __init__(self):
+        import torch
+        self.torch = torch
+        ndev = torch.cuda.device_count()
+        if ndev == 0:
+            raise RuntimeError("no CUDA device")
+        self.dev = int(os.environ.get("LOCAL_RANK", "0")) % ndev
+        torch.cuda.set_device(self.dev)
+
+    def upload(self, arr):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).copy())
+        return t.cuda(self.dev)
+
+    def download(self, t, np_dtype):
+        self.torch.cuda.synchronize()
+        return t.cpu().numpy().view(np_dtype).copy()
+
+    def empty(self, nbytes):
+        return self.torch.zeros(max(int(nbytes), 16), dtype=self.torch.uint8, device="cuda:%d" % self.dev)
+
+
+def transpose_case(gpu, handle, rank, case):
+    """Single op or a chain of ops; every step is checked."""
+    dt_enum, np_dtype = DTYPES[case.get("dtype", "float")]
+    es = np.dtype(np_dtype).itemsize
+    cfg = make_config(case)
+    res, gd = cd.cudecompGridDescCreate(handle, cfg)
+    if res != case.get("expect_create", 0):
+        return dict(ok=False, msg="GridDescCreate returned %d" % res)
+    if res != 0:
+        return dict(ok=True, msg="create failed as expected")
+    out = dict(ok=True, msg="", paths=[])
+    work_ptr = 0
+    try:
+        o = make_oracle(case)
+        nranks = o.nranks
+        ops = case.get("ops") or [case["op"]]
+        halos = case.get("halos") or {}  # axis -> halo extents of that pencil
+        pads = case.get("pads") or {}
+        inplace = not case.get("out_of_place", False)
+        if case.get("force_staged"):
+            cd.check(cd.set_tuning(handle, gd, 0, True))
+        if case.get("grid_ctas"):
+            cd.check(cd.set_tuning(handle, gd, case["grid_ctas"], bool(case.get("force_staged"))))
+
+        def h(ax):
+            return halos.get(str(ax))
+
+        def pd(ax):
+            return pads.get(str(ax))
+
+        # pencil infos from the library must agree with the oracle's
+        infos = {}
+        for ax in range(3):
+            r_, p = cd.cudecompGetPencilInfo(handle, gd, ax, h(ax), pd(ax))
+            cd.check(r_, "cudecompGetPencilInfo")
+            mine = pinfo_to_py(p)
+            ref = o.pencil_info(rank, ax, h(ax), pd(ax))
+            if mine.as_tuple() != ref.as_tuple():
+                return dict(ok=False, msg="pencil info mismatch axis %d: %r vs oracle %r" % (ax, mine, ref))
+            infos[ax] = mine
+        res, wsize = cd.cudecompGetTransposeWorkspaceSize(handle, gd)
+        cd.check(res)
+        if wsize != o.transpose_workspace_size():
+            return dict(ok=False, msg="workspace size mismatch %d vs %d" % (wsize, o.transpose_workspace_size()))
+        if case.get("work_alloc", "cudecomp") == "cudecomp":
+            res, work_ptr = cd.cudecompMalloc(handle, gd, wsize * es)
+            cd.check(res, "cudecompMalloc")
+            work = work_ptr
+        else:
+            work_t = gpu.empty(wsize * es)
+            work = work_t.data_ptr()
+        data_elems = max(infos[ax].size for ax in range(3))
+
+        for fill in case.get("fills", ["pattern", "random"]):
+            a0 = orc.transpose_axes(ops[0])[0]
+            # all ranks' inputs (the oracle runs every rank in this process)
+            cur = []
+            for r in range(nranks):
+                pa = o.pencil_info(r, a0, h(a0), pd(a0))
+                buf = np.full(max(o.pencil_info(r, ax, h(ax), pd(ax)).size for ax in range(3)), -7, dtype=np_dtype)
+                if fill == "pattern":
+                    buf[:pa.size] = orc.pattern_pencil(pa, case["gdims"], np_dtype)
+                else:
+                    buf[:pa.size] = seeded(pa.size, np_dtype, 1000 * r + 17)
+                cur.append(buf)
+            other = [np.full(c.size, -3, dtype=np_dtype) for c in cur]  # host mirror of the second device buffer
+            d_in = gpu.upload(cur[rank])
+            d_out = d_in if inplace else gpu.upload(other[rank])
+            for op in ops:
+                a, b = orc.transpose_axes(op)
+                # oracle step on the host mirrors: same inputs, same pre-existing output contents as on the device
+                o.transpose(op, cur, cur if inplace else other, h(a), h(b), pd(a), pd(b))
+                exp = (cur if inplace else other)[rank]
+                res = cd.TRANSPOSES[op](handle, gd, d_in, d_out, work, dt_enum, h(a), h(b), pd(a), pd(b), None)
+                if res != case.get("expect", 0):
+                    return dict(ok=False, msg="%s returned %d, expected %d" % (op, res, case.get("expect", 0)))
+                if res != 0:
+                    return dict(ok=True, msg="failed as expected")
+                out["paths"].append(cd.last_path(handle, gd))
+                got = gpu.download(d_out, np_dtype)
+                pb = infos[b]
+                if fill == "pattern":
+                    want = orc.pattern_pencil(pb, case["gdims"], np_dtype)
+                    if not orc.interior_equal(pb, want, got[:pb.size]):
+                        return dict(ok=False, msg="%s %s: interior differs from the analytic pattern" % (op, fill))
+                # the whole buffer (interior, untouched halo/padding cells, tail) must equal the oracle's
+                if exp.size != got.size or not np.array_equal(exp.view(np.uint8), got.view(np.uint8)):
+                    bad = np.flatnonzero(exp != got[:exp.size])
+                    return dict(ok=False, msg="%s %s: differs from oracle at %d cells, first %d (want %r got %r)" %
+                                (op, fill, bad.size, bad[0] if bad.size else -1, exp[bad[0]] if bad.size else None,
+                                 got[bad[0]] if bad.size else None))
+                if cd.check_errors(handle, gd) != 0:
+                    return dict(ok=False, msg="%s: device-side handshake error" % op)
+                if not inplace:
+                    # the reference's legacy chain swaps the buffers (tests/cc/transpose_test.cc:523-545)
+                    d_in, d_out = d_out, d_in
+                    cur, other = other, cur
+    finally:
+        if work_ptr:
+            cd.cudecompFree(handle, gd, work_ptr)
+        cd.cudecompGridDescDestroy(handle, gd)
+    return out
+
+
+def halo_case(gpu, handle, rank, case):
+    dt_enum, np_dtype = DTYPES[case.get("dtype", "float")]
+    es = np.dtype(np_dtype).itemsize
+    cfg = make_config(case)
+    res, gd = cd.cudecompGridDescCreate(handle, cfg)
+    cd.check(res, "cudecompGridDescCreate")
+    out = dict(ok=True, msg="", paths=[])
+    work_ptr = 0
+    try:
+        o = make_oracle(case)
+        ax = case["axis"]
+        halo = case["halo"]
+        periods = case.get("periods") or [False] * 3
+        pad = case.get("padding")
+        if case.get("force_staged"):
+            cd.check(cd.set_tuning(handle, gd, 0, True))
+        r_, p = cd.cudecompGetPencilInfo(handle, gd, ax, halo, pad)
+        cd.check(r_)
+        pinfo = pinfo_to_py(p)
+        if pinfo.as_tuple() != o.pencil_info(rank, ax, halo, pad).as_tuple():
+            return dict(ok=False, msg="pencil info mismatch")
+        res, wsize = cd.cudecompGetHaloWorkspaceSize(handle, gd, ax, halo)
+        cd.check(res)
+        if wsize != o.halo_workspace_size(rank, ax, halo):
+            return dict(ok=False, msg="halo workspace size mismatch %d vs %d" % (wsize, o.halo_workspace_size(rank, ax, halo)))
+        res, work_ptr = cd.cudecompMalloc(handle, gd, max(wsize, 64) * es)
+        cd.check(res)
+        for fill in case.get("fills", ["pattern", "random"]):
+            hosts = []
+            for r in range(o.nranks):
+                pr = o.pencil_info(r, ax, halo, pad)
+                hosts.append(orc.pattern_pencil(pr, case["gdims"], np_dtype) if fill == "pattern" else
+                             seeded(pr.size, np_dtype, 77 + r))
+            d = gpu.upload(hosts[rank])
+            for dim in case.get("dims", [0, 1, 2]):
+                o.halo(ax, dim, hosts, halo, periods, pad)
+                res = cd.UPDATE_HALOS[ax](handle, gd, d, work_ptr, dt_enum, halo, periods, dim, pad, None)
+                if res != case.get("expect", 0):
+                    return dict(ok=False, msg="UpdateHalos dim %d returned %d" % (dim, res))
+                if res != 0:
+                    return dict(ok=True, msg="failed as expected")
+                out["paths"].append(cd.last_path(handle, gd))
+            got = gpu.download(d, np_dtype)[:pinfo.size]
+            if fill == "pattern" and case.get("dims", [0, 1, 2]) == [0, 1, 2]:
+                want = orc.halo_reference(pinfo, case["gdims"], np_dtype, periods)
+                if not np.array_equal(want, got):
+                    bad = np.flatnonzero(want != got)
+                    return dict(ok=False, msg="halo: differs from analytic reference at %d cells (first %d)" %
+                                (bad.size, bad[0]))
+            if not np.array_equal(hosts[rank].view(np.uint8), got.view(np.uint8)):
+                bad = np.flatnonzero(hosts[rank] != got)
+                return dict(ok=False, msg="halo %s: differs from oracle at %d cells (first %d)" % (fill, bad.size, bad[0]))
+            if cd.check_errors(handle, gd) != 0:
+                return dict(ok=False, msg="device-side handshake error")
+    finally:
+        if work_ptr:
+            cd.cudecompFree(handle, gd, work_ptr)
+        cd.cudecompGridDescDestroy(handle, gd)
+    return out
+
+
+def autotune_case(gpu, handle, rank, case):
+    cfg = make_config(case)
+    cfg.pdims[:] = [0, 0]
+    opt = cd.cudecompGridDescAutotuneOptions_t()
+    cd.check(cd.cudecompGridDescAutotuneOptionsSetDefaults(opt))
+    opt.dtype = DTYPES[case.get("dtype", "double")][0]
+    opt.n_warmup_trials = case.get("n_warmup", 1)
+    opt.n_trials = case.get("n_trials", 2)
+    opt.autotune_transpose_backend = bool(case.get("autotune_backend", False))
+    opt.grid_mode = case.get("grid_mode", 0)
+    if case.get("halo"):
+        opt.halo_extents[:] = case["halo"]
+        opt.autotune_halo_backend = bool(case.get("autotune_halo_backend", False))
+        for i in range(3):
+            opt.halo_periods[i] = True
+    res, gd = cd.cudecompGridDescCreate(handle, cfg, opt)
+    if res != 0:
+        return dict(ok=False, msg="autotuned GridDescCreate returned %d" % res)
+    try:
+        nranks = cd.MPI_Comm_size()
+        ok = cfg.pdims[0] * cfg.pdims[1] == nranks and 1 <= cfg.transpose_comm_backend <= 8
+        # the chosen grid must work
+        sub = dict(case)
+        sub["pdims"] = [cfg.pdims[0], cfg.pdims[1]]
+        return dict(ok=ok, msg="selected %dx%d backend %d" % (cfg.pdims[0], cfg.pdims[1], cfg.transpose_comm_backend),
+                    pdims=[cfg.pdims[0], cfg.pdims[1]], backend=int(cfg.transpose_comm_backend))
+    finally:
+        cd.cudecompGridDescDestroy(handle, gd)
+
+
+# ------------------------------------------------------------------------------------------------ plan mode
+def plan_case(handle, rank, case):
+    cfg = make_config(case)
+    res, gd = cd.cudecompGridDescCreate(handle, cfg)
+    cd.check(res, "cudecompGridDescCreate")
+    try:
+        out = dict(ok=True, pencils={}, transposes={}, halos={}, shifted=[], config_pdims=list(cfg.pdims))
+        halos = case.get("halos") or {}
+        pads = case.get("pads") or {}
+        for ax in range(3):
+            r_, p = cd.cudecompGetPencilInfo(handle, gd, ax, halos.get(str(ax)), pads.get(str(ax)))
+            cd.check(r_)
+            out["pencils"][str(ax)] = [list(p.shape), list(p.lo), list(p.hi), list(p.order), list(p.halo_extents),
+                                       list(p.padding), p.size]
+        out["workspace"] = cd.cudecompGetTransposeWorkspaceSize(handle, gd)[1]
+        for op in OPS:
+            ax, d = orc.TRANSPOSE_OPS[op]
+            a, b = orc.transpose_axes(op)
+            for staged in (False, True):
+                out["transposes"]["%s/%d" % (op, staged)] = cd.describe_transpose_boxes(
+                    handle, gd, ax, d, halos.get(str(a)), halos.get(str(b)), pads.get(str(a)), pads.get(str(b)), staged)
+        if case.get("halo"):
+            for ax in range(3):
+                for dim in range(3):
+                    for staged in (False, True):
+                        out["halos"]["%d/%d/%d" % (ax, dim, staged)] = cd.describe_halo_boxes(
+                            handle, gd, ax, dim, case["halo"], case.get("periods"), case.get("padding"), staged)
+        for q in case.get("shifted", []):
+            res, v = cd.cudecompGetShiftedRank(handle, gd, q["axis"], q["dim"], q["displacement"], q["periodic"])
+            out["shifted"].append(v)
+        return out
+    finally:
+        cd.cudecompGridDescDestroy(handle, gd)
+
+
+def main():
+    payload_path, out_dir = sys.argv[1], sys.argv[2]
+    with open(payload_path) as f:
+        payload = json.load(f)
+    rank = int(os.environ.get("RANK", "0"))
+    results = []
+    gpu = Gpu() if payload["mode"] == "gpu" else None
+    assert cd.MPI_Init() == 0
+    res, handle = cd.cudecompInit(cd.MPI_COMM_WORLD)
+    cd.check(res, "cudecompInit")
+    fatal = False
+    for case in payload["cases"]:
+        if fatal:
+            results.append(dict(ok=False, msg="skipped after an earlier failure that may have desynchronised the ranks"))
+            continue
+        try:
+            if payload["mode"] == "plan":
+                results.append(plan_case(handle, rank, case))
+            elif case["kind"] == "halo":
+                results.append(halo_case(gpu, handle, rank, case))
+            elif case["kind"] == "autotune":
+                results.append(autotune_case(gpu, handle, rank, case))
+            else:
+                results.append(transpose_case(gpu, handle, rank, case))
+        except Exception as e:  # noqa: BLE001
+            results.append(dict(ok=False, msg="exception: %s\n%s" % (e, traceback.format_exc())))
+            fatal = True
+        # keep ranks in lock step between cases (a failing rank must not leave the others mid-collective)
+        cd.MPI_Barrier()
+    if os.environ.get("CDB_TEST_GLOO") == "1":
+        # N>1 host path cross-checked over torch.distributed (gloo): every rank sees every rank's plans
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=int(os.environ["WORLD_SIZE"]))
+        results = json.loads(json.dumps(results))  # tuples -> lists, as the parent will read them
+        gathered = [None] * dist.get_world_size()
+        dist.all_gather_object(gathered, results)
+        assert gathered[rank] == results
+        results = dict(mine=results, gathered=gathered)
+        dist.barrier()
+        dist.destroy_process_group()
+    with open(os.path.join(out_dir, "rank%d.json" % rank), "w") as f:
+        json.dump(results, f)
+    cd.cudecompFinalize(handle)
+    cd.MPI_Finalize()
+
+
+if __name__ == "__main__":
+    main()

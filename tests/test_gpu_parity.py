@@ -1,0 +1,129 @@
+"""Parity of the CUDA path with the oracle, through the C ABI, on real GPUs (pytest -m gpu).
+
+The case matrix is the reference's own (tests/ctest/transpose_tests.cc:163-273, halo_tests.cc:103-146,
+tests/test_runner.py:80-90). Every case runs on N ranks = N processes; with fewer GPUs than ranks the ranks share
+a GPU. Each rank checks its result (a) against the analytic global-index pattern -- the reference's own pass/fail
+criterion -- and (b) byte for byte against the CPU oracle run on the same seeded inputs, including the cells the
+operation must leave untouched (output halos, padding).
+"""
+import pytest
+
+from tests import cases as C
+from tests._launcher import run_ranks
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(nranks, cases, timeout=1500):
+    results, logs = run_ranks(nranks, "gpu", cases, timeout=timeout)
+    return results, logs
+
+
+def _assert_case(results, i, case):
+    msgs = ["rank %d: %s" % (r, results[r][i].get("msg")) for r in range(len(results)) if not results[r][i]["ok"]]
+    assert not msgs, "%s\n%s" % (case["name"], "\n".join(msgs))
+
+
+# ------------------------------------------------------------------------------------------- single rank (1x1)
+SINGLE = C.transpose_single_rank() + C.halo_baseline((1, 1)) + C.legacy_mem_order_chain((1, 1), stride=4) + \
+    C.legacy_mem_order_chain((1, 1), dtype="double_complex", out_of_place=True, stride=7)
+
+
+@pytest.fixture(scope="module")
+def single_results():
+    return _run(1, SINGLE)[0]
+
+
+@pytest.mark.parametrize("i", range(len(SINGLE)), ids=[c["name"] for c in SINGLE])
+def test_single_rank(single_results, i):
+    _assert_case(single_results, i, SINGLE[i])
+
+
+# ------------------------------------------------------------------------------------------------- 4 ranks, 2x2
+FOUR = C.transpose_baseline((2, 2)) + C.transpose_coverage_2x2() + C.halo_baseline((2, 2)) + C.halo_coverage() + \
+    C.legacy_mem_order_chain((2, 2), stride=3) + \
+    C.legacy_mem_order_chain((2, 2), dtype="double_complex", out_of_place=True, stride=5) + [
+        dict(kind="transpose", name="Slab4x1_chain", gdims=[16, 12, 20], pdims=[4, 1], dtype="double",
+             ops=["XY", "YZ", "ZY", "YX"], out_of_place=True),
+        dict(kind="transpose", name="Slab1x4_chain_inplace", gdims=[16, 12, 20], pdims=[1, 4], dtype="float_complex",
+             ops=["XY", "YZ", "ZY", "YX"]),
+        dict(kind="transpose", name="NativeAlltoAllPath_YZ_1x4", gdims=[8, 8, 8], pdims=[1, 4], dtype="float",
+             op="YZ", out_of_place=True),
+        dict(kind="transpose", name="EmptyPencils_NotSupported", gdims=[2, 2, 2], pdims=[4, 1], dtype="float", op="XY",
+             expect=2, fills=["pattern"]),
+        dict(kind="halo", name="HaloTooWide_InvalidUsage", gdims=C.GDIMS, pdims=[2, 2], dtype="float", axis=0,
+             halo=[0, 6, 0], periods=[True] * 3, expect=1, fills=["pattern"], dims=[1]),
+        dict(kind="transpose", name="FewCtas_XY", gdims=[40, 36, 44], pdims=[2, 2], dtype="double", op="XY",
+             out_of_place=True, grid_ctas=3),
+        dict(kind="autotune", name="AutotuneTransposeGrid", gdims=[24, 20, 28], dtype="double", n_trials=2),
+        dict(kind="autotune", name="AutotuneTransposeBackend", gdims=[24, 20, 28], dtype="float_complex",
+             autotune_backend=True, n_trials=1),
+        dict(kind="autotune", name="AutotuneHaloGrid", gdims=[24, 20, 28], dtype="float", grid_mode=1,
+             halo=[1, 1, 1], n_trials=1),
+    ]
+
+
+@pytest.fixture(scope="module")
+def four_results():
+    return _run(4, FOUR)[0]
+
+
+@pytest.mark.parametrize("i", range(len(FOUR)), ids=[c["name"] for c in FOUR])
+def test_four_ranks(four_results, i):
+    _assert_case(four_results, i, FOUR[i])
+
+
+def test_direct_and_staged_paths_are_both_exercised(four_results):
+    """Out-of-place exchanges with exportable buffers take the one-kernel direct path (2); in-place ones and the
+    NVSHMEM backend values stage through the workspace (3)."""
+    by_name = {c["name"]: four_results[0][i] for i, c in enumerate(FOUR)}
+    assert set(by_name["BaselineDefaultLayout_XY_float_P2x2_OutOfPlace"]["paths"]) == {2}
+    assert set(by_name["BaselineDefaultLayout_XY_float_P2x2_InPlace"]["paths"]) == {3}
+    assert set(by_name["StagedBackend_XY"]["paths"]) == {3}
+    assert set(by_name["ForceStaged_YZ_AxisContiguous"]["paths"]) == {3}
+    assert 2 in set(by_name["BaselineDefaultLayoutPeriodic_Axis0_float_P2x2"]["paths"])
+    assert set(by_name["StagedBackend"]["paths"]) <= {1, 3}
+
+
+# ------------------------------------------------------------------------------------- 3 ranks (non power of two)
+THREE = C.transpose_coverage_3x1() + C.halo_3x1()
+
+
+@pytest.fixture(scope="module")
+def three_results():
+    return _run(3, THREE)[0]
+
+
+@pytest.mark.parametrize("i", range(len(THREE)), ids=[c["name"] for c in THREE])
+def test_three_ranks(three_results, i):
+    _assert_case(three_results, i, THREE[i])
+
+
+# ---------------------------------------------------------------- 2 ranks: BASELINE.json config 1 (128^3 double)
+TWO = [
+    dict(kind="transpose", name="Config1_128cubed_double_1x2_%s" % ("oop" if oop else "inplace"), gdims=[128] * 3,
+         pdims=[1, 2], dtype="double", ops=["XY", "YZ", "ZY", "YX"], out_of_place=oop)
+    for oop in (False, True)
+] + [
+    dict(kind="transpose", name="Config1_128cubed_double_2x1_%s" % ("oop" if oop else "inplace"), gdims=[128] * 3,
+         pdims=[2, 1], dtype="double", ops=["XY", "YZ", "ZY", "YX"], out_of_place=oop)
+    for oop in (False, True)
+] + [
+    dict(kind="transpose", name="Uneven_130x126x134_c128_2x1_axis_contiguous", gdims=[130, 126, 134], pdims=[2, 1],
+         dtype="double_complex", ops=["XY", "YZ", "ZY", "YX"], out_of_place=True, axis_contiguous=[True] * 3,
+         fills=["random"]),
+    dict(kind="halo", name="Halo_128x132x124_1x2_axis0", gdims=[128, 132, 124], pdims=[1, 2], dtype="float", axis=0,
+         halo=[2, 2, 2], periods=[True] * 3, fills=["random"]),
+    dict(kind="halo", name="Halo_128x132x124_2x1_axis2_nonperiodic", gdims=[128, 132, 124], pdims=[2, 1],
+         dtype="double_complex", axis=2, halo=[1, 2, 1], periods=[False] * 3, fills=["random"]),
+]
+
+
+@pytest.fixture(scope="module")
+def two_results():
+    return _run(2, TWO)[0]
+
+
+@pytest.mark.parametrize("i", range(len(TWO)), ids=[c["name"] for c in TWO])
+def test_two_ranks(two_results, i):
+    _assert_case(two_results, i, TWO[i])
