@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline benchmark for the pencil-transpose hot path on B200.
+
+Workload (BASELINE.json metric): 1024^3 complex128 grid, X->Y->Z->Y->X transpose round trip (the autotuner's trial
+body, reference src/autotune.cc:541-576), default memory layout, out-of-place buffers (the autotuner's default,
+transpose_use_inplace_buffers = false), process grid 1x1 / 1x2 / 2x2 / 2x4 at 1 / 2 / 4 / 8 GPUs.
+A step is one round trip (4 transposes) over this rank's pencil. The global grid is fixed, so scaling is strong.
+
+metric  = effective transpose GB/s, the reference's own accounting (include/internal/transpose.h:316,
+          src/performance.cc:391): pencil bytes S per transpose / time. value = whole-job aggregate = N * 4S / t_step.
+e2e     = same metric with the pencil starting and ending in pinned HOST memory: H2D of the input pencil, the round
+          trip through the C ABI, D2H of the result pencil, all inside the timed region.
+roofline= dominant kernel (cdb::rowCopyKernel<uint4>) against the measured HBM copy bandwidth: algorithmic bytes
+          2S per launch (read the pencil once, write it once) / average launch duration from CUDA events.
+nvlink  = bytes that leave this GPU per second against the measured 770 GB/s peer-copy rate (N > 1).
+
+`--impl reference` times the CPU restatement of the reference's path (oracle/, OpenMP over all host cores) on a
+bounded z-slab sample of the same workload; the reference itself cannot be built here.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRID_BY_N = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
+OPS = ["XY", "YZ", "ZY", "YX"]
+NVLINK_PEAK_GBS = 770.0  # measured peer-copy rate per direction (B200_PROFILING.md), 900 nominal
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--n", type=int, default=1024, help="grid edge (default 1024, the metric's configuration)")
+    ap.add_argument("--dtype", default="double_complex")
+    ap.add_argument("--inplace", action="store_true", help="in-place buffers (the reference benchmark's default)")
+    ap.add_argument("--axis-contiguous", action="store_true")
+    ap.add_argument("--pdims", default=None, help="override process grid, e.g. 2x4")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--staged", action="store_true", help="force the workspace-staged schedule")
+    ap.add_argument("--ctas", type=int, default=0)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([v.strip() for v in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if r[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """CPU restatement of the reference path on the host cores, bounded sample: a z-slab of the same grid."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import oracle as orc
+    import torch  # noqa: F401  (only for parity of the environment; not used by the timed code)
+
+    n = args.n
+    nz = max(1, min(n, 32))  # 1024 x 1024 x 32 complex128 = 0.54 GB: ~1/32 of the workload per step
+    pd = GRID_BY_N.get(args.gpus, (1, args.gpus))
+    if args.pdims:
+        pd = tuple(int(v) for v in args.pdims.split("x"))
+    # the sample keeps the full x-y extent (what the X<->Y exchange moves) and thins z
+    nz = max(nz, pd[1] * 4)
+    gd = [n, n, nz]
+    o = orc.Oracle(gd, pd, (args.axis_contiguous,) * 3)
+    cores = o.max_threads()
+    dt = orc.NP_DTYPES[args.dtype]
+    es = np.dtype(dt).itemsize
+    bufs_a = [np.ones(max(o.pencil_info(r, ax).size for ax in range(3)), dt) for r in range(o.nranks)]
+    bufs_b = [np.zeros_like(b) for b in bufs_a]
+    S_total = float(n) * n * nz * es
+
+    def step():
+        cur, other = bufs_a, bufs_b
+        for op in OPS:
+            o.transpose(op, cur, cur if args.inplace else other)
+            if not args.inplace:
+                cur, other = other, cur
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt_s = (time.perf_counter() - t0) / args.steps
+    value = 4.0 * S_total / dt_s / 1e9
+    sample = "z-slab %dx%dx%d of the %d^3 %s grid, %s, pdims %dx%d as %d in-process ranks" % (
+        n, n, nz, n, args.dtype, "in-place" if args.inplace else "out-of-place", pd[0], pd[1], o.nranks)
+    line = {
+        "impl": "reference", "metric": "effective transpose GB/s (4*S/t round trip, whole job)", "value": value,
+        "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_s * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128" if es == 16 else args.dtype,
+        "data": "synthetic",
+        "config": workload_config(args, pd, sample=sample),
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, pd, sample=None):
+    c = {"workload": "%d^3 %s X->Y->Z->Y->X transpose round trip, %s, %s layout, pdims %dx%d" % (
+        args.n, args.dtype, "in-place" if args.inplace else "out-of-place",
+        "axis-contiguous" if args.axis_contiguous else "default", pd[0], pd[1]),
+        "l2": "inputs larger than L2 (no flush needed)", "grid": [args.n] * 3, "pdims": list(pd)}
+    if sample:
+        c["sample"] = sample
+    return c
+
+
+# -------------------------------------------------------------------------------------------------- native arm
+def run_native(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cudecomp_b200 import capi as cd
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pd = GRID_BY_N.get(world, (1, world))
+    if args.pdims:
+        pd = tuple(int(v) for v in args.pdims.split("x"))
+    assert pd[0] * pd[1] == world, "pdims do not match the number of ranks"
+    dt_enum = {"float": cd.CUDECOMP_FLOAT, "double": cd.CUDECOMP_DOUBLE, "float_complex": cd.CUDECOMP_FLOAT_COMPLEX,
+               "double_complex": cd.CUDECOMP_DOUBLE_COMPLEX}[args.dtype]
+    es = cd.DTYPE_SIZES[dt_enum]
+
+    assert cd.MPI_Init() == 0
+    res, handle = cd.cudecompInit(cd.MPI_COMM_WORLD)
+    cd.check(res, "cudecompInit")
+    cfg = cd.cudecompGridDescConfig_t()
+    cd.check(cd.cudecompGridDescConfigSetDefaults(cfg))
+    cfg.gdims[:] = [args.n] * 3
+    cfg.pdims[:] = pd
+    cfg.transpose_comm_backend = cd.CUDECOMP_TRANSPOSE_COMM_NCCL
+    for i in range(3):
+        cfg.transpose_axis_contiguous[i] = args.axis_contiguous
+    res, gd = cd.cudecompGridDescCreate(handle, cfg)
+    cd.check(res, "cudecompGridDescCreate")
+    if args.staged or args.ctas:
+        cd.check(cd.set_tuning(handle, gd, args.ctas, args.staged))
+
+    sizes = [cd.cudecompGetPencilInfo(handle, gd, ax)[1].size for ax in range(3)]
+    S = sizes[0] * es  # bytes of this rank's pencil (equal for the three orientations on even grids)
+    nbytes = max(sizes) * es
+    res, wsize = cd.cudecompGetTransposeWorkspaceSize(handle, gd)
+    res, work = cd.cudecompMalloc(handle, gd, wsize * es)
+    cd.check(res, "cudecompMalloc")
+
+    # synthetic pencil: uniform [0,1) reals like the reference benchmark (benchmark/benchmark.cu:472-485)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    a = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
+    a.uniform_(0.0, 1.0, generator=gen)
+    b = a if args.inplace else torch.zeros_like(a)
+    stream = torch.cuda.current_stream()
+
+    def round_trip(src, dst, events=None):
+        cur, other = src, dst
+        for k, op in enumerate(OPS):
+            cd.check(cd.TRANSPOSES[op](handle, gd, cur, cur if args.inplace else other, work, dt_enum, None, None,
+                                       None, None, stream), op)
+            if events is not None:
+                events[k + 1].record(stream)
+            if not args.inplace:
+                cur, other = other, cur
+        return cur
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        round_trip(a, b)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    launches0 = cd.launch_count()
+    barrier()
+    for s in range(args.steps):
+        evs[s][0].record(stream)
+        round_trip(a, b, evs[s])
+    torch.cuda.synchronize()
+    barrier()
+    launches = cd.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    cd.check(cd.check_errors(handle, gd), "device-side handshake")
+    total_ms = sum(evs[s][0].elapsed_time(evs[s][4]) for s in range(args.steps))
+    op_ms = [sum(evs[s][k].elapsed_time(evs[s][k + 1]) for s in range(args.steps)) / args.steps for k in range(4)]
+    ms_step = max_over_ranks(total_ms / args.steps)
+    op_ms = [max_over_ranks(v) for v in op_ms]
+    value = world * 4.0 * S / (ms_step * 1e-3) / 1e9
+
+    # ---- end to end: pinned host pencil -> device -> round trip -> pinned host
+    e2e = None
+    if not args.no_e2e:
+        h_in = torch.empty(S // 8, dtype=torch.float64, pin_memory=True)
+        h_in.copy_(a[:S // 8])
+        h_out = torch.empty(S // 8, dtype=torch.float64, pin_memory=True)
+
+        def e2e_step():
+            a[:S // 8].copy_(h_in, non_blocking=True)
+            out = round_trip(a, b)
+            h_out.copy_(out[:S // 8], non_blocking=True)
+
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        e2e = {"value": world * 4.0 * S / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(S),
+               "d2h_bytes_per_step": int(S), "ms_per_step": e2e_ms}
+        del h_in, h_out
+
+    hbm_peak, peak_src = peaks()
+    # dominant kernel: one copy launch per transpose; algorithmic traffic 2S (read once, write once)
+    slowest = max(range(4), key=lambda k: op_ms[k])
+    kern_ms = sum(op_ms) / 4.0
+    achieved = 2.0 * S / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": TRAFFIC_BYTES.get((world, args.n, args.dtype, args.inplace)),
+                "kernel": "cdb::transposeKernel<uint4>" if args.axis_contiguous else "cdb::rowCopyKernel<uint4>",
+                "peak_source": peak_src,
+                "per_op_ms": dict(zip(OPS, op_ms)), "algorithmic_bytes_per_launch": 2.0 * S,
+                "slowest_op": OPS[slowest]}
+    nvlink = None
+    if world > 1:
+        comm = {"XY": pd[0], "YX": pd[0], "YZ": pd[1], "ZY": pd[1]}
+        wire = sum(S * (1.0 - 1.0 / comm[op]) for op in OPS)
+        t_wire = sum(op_ms[k] for k, op in enumerate(OPS) if comm[op] > 1) * 1e-3
+        nvlink = {"wire_bytes_per_step": wire, "achieved": wire / t_wire / 1e9 if t_wire > 0 else None,
+                  "peak": NVLINK_PEAK_GBS, "unit": "GB/s",
+                  "frac": (wire / t_wire / 1e9) / NVLINK_PEAK_GBS if t_wire > 0 else None,
+                  "roofline_ms_per_step": wire / (NVLINK_PEAK_GBS * 1e9) * 1e3 +
+                  sum(2.0 * S / (hbm_peak * 1e9) * 1e3 for op in OPS if comm[op] == 1)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args, pd)
+
+    if rank == 0:
+        line = {"metric": "effective transpose GB/s (4*S/t round trip, whole job)", "value": value, "unit": "GB/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "c128" if es == 16 else args.dtype, "data": "synthetic",
+                "config": workload_config(args, pd), "per_gpu_value": value / world,
+                "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
+                "path": {0: "none", 1: "local", 2: "direct", 3: "staged"}[cd.last_path(handle, gd)]}
+        if nvlink:
+            line["nvlink"] = nvlink
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+
+    barrier()
+    cd.cudecompFree(handle, gd, work)
+    cd.cudecompGridDescDestroy(handle, gd)
+    cd.cudecompFinalize(handle)
+    cd.MPI_Finalize()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu capture
+# (profiles/), keyed by (n_gpus, grid edge, dtype, inplace). Filled in when a capture of that configuration exists.
+TRAFFIC_BYTES = {
+    # profiles/r1_n1_rowcopy_full.txt: 17.180 GB read + 17.135 GB written per launch (algorithmic 2S = 34.360 GB)
+    (1, 1024, "double_complex", False): 34.315e9,
+}
+
+
+def cpu_baseline(args, pd):
+    """The oracle on this box's host cores, bounded sample of the same workload (see run_reference)."""
+    import numpy as np
+    from oracle import oracle as orc
+    n, nz = args.n, 32
+    o = orc.Oracle([n, n, nz], pd, (args.axis_contiguous,) * 3)
+    dt = orc.NP_DTYPES[args.dtype]
+    es = np.dtype(dt).itemsize
+    A = [np.ones(o.pencil_info(0, 0).size, dt)]
+    B = [np.zeros_like(A[0])]
+
+    def step():
+        cur, other = A, B
+        for op in OPS:
+            o.transpose(op, cur, cur if args.inplace else other)
+            if not args.inplace:
+                cur, other = other, cur
+    step()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    t = (time.perf_counter() - t0) / reps
+    return {"value": 4.0 * n * n * nz * es / t / 1e9, "unit": "GB/s", "cores": o.max_threads(), "kind": "port",
+            "sample": "z-slab %dx%dx%d of the %d^3 %s grid, %d timed round trips" % (n, n, nz, n, args.dtype, reps)}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d --master-addr "
+                     "127.0.0.1 --master-port P bench.py --gpus %d ..." % (args.gpus, args.gpus))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

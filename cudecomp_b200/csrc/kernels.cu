@@ -88,6 +88,8 @@ __device__ __forceinline__ void syncExit(const SyncParams& s) {
   if (t == 0) *reinterpret_cast<volatile unsigned long long*>(s.my_pad + kPadCounter) = 0ull;
 }
 
+} // namespace
+
 template <typename V> __device__ __forceinline__ V loadStream(const V* p) { return __ldcs(p); }
 template <typename V> __device__ __forceinline__ void storeStream(V* p, const V& v) { __stcs(p, v); }
 
@@ -195,6 +197,8 @@ template <typename T> __global__ void __launch_bounds__(256) transposeKernel(con
 
   syncExit(p.sync);
 }
+
+namespace {
 
 using KernelFn = void (*)(const CopyParams);
 

@@ -46,6 +46,31 @@ typedef struct {
 
 static int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 
+/* Staging regions persist between calls, like the reference's workspace does (the caller allocates `work` once,
+ * include/cudecomp.h:433-448): a timed run must not pay for fresh page faults on every transpose. */
+#define ORACLE_MAX_STAGE 1024
+static char* g_stage[ORACLE_MAX_STAGE];
+static size_t g_stage_bytes[ORACLE_MAX_STAGE];
+
+static char* stage_buffer(int slot, size_t bytes) {
+  if (slot < 0 || slot >= ORACLE_MAX_STAGE) return NULL;
+  if (g_stage_bytes[slot] < bytes) {
+    free(g_stage[slot]);
+    g_stage[slot] = (char*)malloc(bytes ? bytes : 1);
+    g_stage_bytes[slot] = g_stage[slot] ? bytes : 0;
+    if (g_stage[slot]) memset(g_stage[slot], 0, bytes); /* touch the pages once */
+  }
+  return g_stage[slot];
+}
+
+void oracle_release(void) {
+  for (int i = 0; i < ORACLE_MAX_STAGE; ++i) {
+    free(g_stage[i]);
+    g_stage[i] = NULL;
+    g_stage_bytes[i] = 0;
+  }
+}
+
 /* reference include/internal/common.h:318-331 */
 static void pidx_of_rank(const oracle_grid_t* g, int rank, int pidx[2]) {
   if (g->col_major) {
@@ -256,8 +281,12 @@ int oracle_transpose(const oracle_grid_t* g, int ax, int dir, int es, void* cons
   for (int r = 0; r < nranks && !rc; ++r) {
     oracle_pencil_t pa, pb;
     if (oracle_pencil_info(g, r, a, NULL, NULL, &pa) || oracle_pencil_info(g, r, b, NULL, NULL, &pb)) rc = 1;
-    sendb[r] = (char*)malloc((size_t)(pa.size > 0 ? pa.size : 1) * es);
-    recvb[r] = (char*)malloc((size_t)(pb.size > 0 ? pb.size : 1) * es);
+    if (2 * nranks > ORACLE_MAX_STAGE) {
+      rc = 3;
+      break;
+    }
+    sendb[r] = stage_buffer(2 * r, (size_t)(pa.size > 0 ? pa.size : 1) * es);
+    recvb[r] = stage_buffer(2 * r + 1, (size_t)(pb.size > 0 ? pb.size : 1) * es);
     if (!sendb[r] || !recvb[r]) rc = 3;
   }
 
@@ -310,7 +339,15 @@ int oracle_transpose(const oracle_grid_t* g, int ax, int dir, int es, void* cons
       const int64_t send_offset = off_a[i] * sga[b] * sga[c];
       const int64_t send_count = splits_a[i] * sga[b] * sga[c];
       const int64_t recv_offset = off_b[me] * sgb[a] * sgb[c];
-      memcpy(recvb[dst] + recv_offset * es, sendb[r] + send_offset * es, (size_t)(send_count * es));
+      /* split large messages over the host threads */
+      const int64_t bytes = send_count * es;
+      const int64_t chunk = 1 << 22;
+      const int64_t nchunks = (bytes + chunk - 1) / chunk;
+#pragma omp parallel for schedule(static) if (nchunks > 1)
+      for (int64_t k = 0; k < nchunks; ++k) {
+        const int64_t lo = k * chunk, len = (lo + chunk <= bytes) ? chunk : bytes - lo;
+        memcpy(recvb[dst] + recv_offset * es + lo, sendb[r] + send_offset * es + lo, (size_t)len);
+      }
     }
   }
 
@@ -350,10 +387,6 @@ int oracle_transpose(const oracle_grid_t* g, int ax, int dir, int es, void* cons
     }
   }
 
-  for (int r = 0; r < nranks; ++r) {
-    free(sendb[r]);
-    free(recvb[r]);
-  }
   free(sendb);
   free(splits_a);
   return rc;

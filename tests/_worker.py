@@ -142,6 +142,14 @@ def transpose_case(gpu, handle, rank, case):
             work = work_t.data_ptr()
         data_elems = max(infos[ax].size for ax in range(3))
 
+        if case.get("expect", 0) != 0:
+            # error path: the call must fail before touching the buffers (reference api_tests.cc:1493-1505)
+            a, b = orc.transpose_axes(ops[0])
+            res = cd.TRANSPOSES[ops[0]](handle, gd, 4096, 8192 if not inplace else 4096, work, dt_enum, h(a), h(b),
+                                        pd(a), pd(b), None)
+            ok = res == case["expect"]
+            return dict(ok=ok, msg="returned %d, expected %d" % (res, case["expect"]), paths=[])
+
         for fill in case.get("fills", ["pattern", "random"]):
             a0 = orc.transpose_axes(ops[0])[0]
             # all ranks' inputs (the oracle runs every rank in this process)
@@ -220,6 +228,15 @@ def halo_case(gpu, handle, rank, case):
             return dict(ok=False, msg="halo workspace size mismatch %d vs %d" % (wsize, o.halo_workspace_size(rank, ax, halo)))
         res, work_ptr = cd.cudecompMalloc(handle, gd, max(wsize, 64) * es)
         cd.check(res)
+        if case.get("expect", 0) != 0:
+            d = gpu.empty(pinfo.size * es)
+            res = 0
+            for dim in case.get("dims", [0, 1, 2]):
+                res = cd.UPDATE_HALOS[ax](handle, gd, d, work_ptr, dt_enum, halo, periods, dim, pad, None)
+                if res != 0:
+                    break
+            return dict(ok=(res == case["expect"]), msg="returned %d, expected %d" % (res, case["expect"]), paths=[])
+
         for fill in case.get("fills", ["pattern", "random"]):
             hosts = []
             for r in range(o.nranks):
