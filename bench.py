@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--n", type=int, default=1024, help="grid edge (default 1024, the metric's configuration)")
+    ap.add_argument("--grid", dest="n", type=int, default=1024, help="grid edge (default 1024, the metric's configuration)")
     ap.add_argument("--dtype", default="double_complex")
     ap.add_argument("--inplace", action="store_true", help="in-place buffers (the reference benchmark's default)")
     ap.add_argument("--axis-contiguous", action="store_true")
