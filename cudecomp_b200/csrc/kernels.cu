@@ -251,7 +251,16 @@ cudaError_t launchCopy(KernelKind kind, const CopyParams& p, const LaunchConfig&
   int grid = cfg.grid;
   const int resident = maxResidentCtas(kind, size, cfg.threads);
   if (resident <= 0) return cudaErrorInvalidDevice;
-  if (grid <= 0 || grid > resident) grid = resident;
+  if (grid <= 0) {
+    // Measured on B200 (profiles/r1_n1_cta_sweep.txt): HBM streams best with a moderate number of CTAs in flight;
+    // filling every resident slot costs 6-8 % of copy bandwidth. 2.5 CTAs/SM for the row copy, 4/SM for the
+    // shared-memory transpose. NVLink-bound launches are insensitive to the count (profiles/r1_n2_sweep.txt).
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    grid = (kind == KernelKind::ROWCOPY) ? (5 * sms) / 2 : 4 * sms;
+  }
+  if (grid > resident) grid = resident;
   if (static_cast<uint64_t>(grid) > total) grid = static_cast<int>(total);
   if (grid < 1) grid = 1; // still runs the handshake when this rank has nothing to move
   fn<<<grid, cfg.threads, 0, stream>>>(p);
