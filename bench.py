@@ -258,9 +258,11 @@ def run_native(args, rank, world, local_rank):
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     launches0 = cd.launch_count()
     barrier()
+    t_host0 = time.perf_counter()
     for s in range(args.steps):
         evs[s][0].record(stream)
         round_trip(a, b, evs[s])
+    host_us_per_op = (time.perf_counter() - t_host0) / (4 * args.steps) * 1e6  # enqueue cost incl. Python
     torch.cuda.synchronize()
     barrier()
     launches = cd.launch_count() - launches0
@@ -332,6 +334,7 @@ def run_native(args, rank, world, local_rank):
                 "dtype": "c128" if es == 16 else args.dtype, "data": "synthetic",
                 "config": workload_config(args, pd), "per_gpu_value": value / world,
                 "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
+                "host_enqueue_us_per_op": host_us_per_op,
                 "path": {0: "none", 1: "local", 2: "direct", 3: "staged"}[cd.last_path(handle, gd)]}
         if nvlink:
             line["nvlink"] = nvlink

@@ -495,21 +495,21 @@ cudecompResult_t cudecompFree(cudecompHandle_t handle, cudecompGridDesc_t grid_d
   API_TRY
   checkHandle(handle);
   checkGridDesc(handle, grid_desc);
-  if (handle->have_device) {
-    // Collective: every rank drops its import of every buffer being freed before any owner releases it.
+  if (handle->have_device && buffer) {
+    // Not collective: the reference's own test drivers free and re-allocate workspaces on the ranks that need a
+    // larger one only (tests/cc/halo_test.cc workspace reuse). The release is announced to the peers with the next
+    // operation's descriptor exchange, where they drop their imports of this allocation (peer.h, CallMsg).
     CHECK_CUDA(cudaDeviceSynchronize());
-    if (handle->nranks > 1) {
-      BufDesc mine;
-      describeBuffer(buffer, &mine);
-      std::vector<BufDesc> all(handle->nranks);
-      allgather(*handle->comm, &mine, sizeof(BufDesc), all.data());
-      for (int r = 0; r < handle->nranks; ++r)
-        if (r != handle->rank && all[r].exportable) handle->peers.forget(r, all[r]);
-      barrier(*handle->comm);
+    BufDesc d;
+    describeBuffer(buffer, &d);
+    if (d.exportable && d.offset == 0) {
+      for (int k = kReleaseSlots - 1; k > 0; --k) handle->released[k] = handle->released[k - 1];
+      handle->released[0] = d.buffer_id;
+      handle->release_count++;
     }
-    if (buffer) CHECK_CUDA(cudaFree(buffer));
+    CHECK_CUDA(cudaFree(buffer));
   }
-  for (cudecompGridDesc_t gd : {grid_desc}) gd->allocations.erase(buffer);
+  grid_desc->allocations.erase(buffer);
   API_CATCH()
 }
 

@@ -186,6 +186,16 @@ void requireDevice(cudecompHandle_t h) {
     CDB_THROW(CUDECOMP_RESULT_CUDA_ERROR, "CUDA error.", "no CUDA device is available to this process");
 }
 
+void fillReleases(cudecompHandle_t h, CallMsg* m) {
+  m->release_count = h->release_count;
+  for (int k = 0; k < kReleaseSlots; ++k) m->released[k] = h->released[k];
+}
+
+void processReleases(cudecompHandle_t h, const std::vector<int>& group_world, int me, const std::vector<CallMsg>& msgs) {
+  for (size_t i = 0; i < msgs.size(); ++i)
+    if (static_cast<int>(i) != me) h->peers.noteReleases(group_world[i], msgs[i].release_count, msgs[i].released);
+}
+
 uint32_t transposeOpcode(int ax, int dir) { return 0x100u + static_cast<uint32_t>(ax) * 4u + (dir > 0 ? 1u : 0u); }
 uint32_t haloOpcode(int ax, int dim) { return 0x200u + static_cast<uint32_t>(ax) * 4u + static_cast<uint32_t>(dim); }
 
@@ -237,8 +247,10 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
   mine.flags = inplace ? 1u : 0u;
   describeBuffer(output, &mine.data);
   describeBuffer(work, &mine.work);
+  fillReleases(h, &mine);
   std::vector<CallMsg> msgs;
   gd->mbox.exchange(probe.axes.comm == COMM_COL ? 0 : 1, probe.group_world, probe.me, mine, msgs);
+  processReleases(h, probe.group_world, probe.me, msgs);
 
   bool direct = h->allow_direct && !gd->force_staged &&
                 gd->config.transpose_comm_backend < CUDECOMP_TRANSPOSE_COMM_NVSHMEM; // NVSHMEM* values = staged schedule
@@ -325,8 +337,10 @@ void runHalo(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, void* input, voi
   mine.opcode = haloOpcode(ax, dim);
   describeBuffer(input, &mine.data);
   describeBuffer(work, &mine.work);
+  fillReleases(h, &mine);
   std::vector<CallMsg> msgs;
   gd->mbox.exchange(probe.comm == COMM_COL ? 0 : 1, probe.group_world, probe.me, mine, msgs);
+  processReleases(h, probe.group_world, probe.me, msgs);
 
   bool direct = h->allow_direct && !gd->force_staged && gd->config.halo_comm_backend < CUDECOMP_HALO_COMM_NVSHMEM;
   bool work_ok = true;

@@ -37,6 +37,8 @@ struct cudecompHandle {
   int next_instance = 0;
   int live_grid_descs = 0;
   cdb::PeerCache peers;          // imported peer allocations, shared by all grid descriptors
+  uint64_t release_count = 0;    // buffers freed through cudecompFree so far
+  uint64_t released[cdb::kReleaseSlots] = {0}; // ids of the most recent ones, newest first
 };
 
 struct cudecompGridDesc {

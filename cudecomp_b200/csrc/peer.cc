@@ -131,13 +131,43 @@ void* PeerCache::resolve(int owner, const BufDesc& d) {
   return static_cast<char*>(it->second.base) + d.offset;
 }
 
-void PeerCache::forget(int owner, const BufDesc& d) {
-  Key k{owner, d.buffer_id, std::string(reinterpret_cast<const char*>(&d.handle), sizeof(d.handle))};
-  auto it = map_.find(k);
-  if (it == map_.end()) return;
-  cudaIpcCloseMemHandle(it->second.base);
+void PeerCache::forgetBuffer(int owner, uint64_t buffer_id) {
+  for (auto it = map_.begin(); it != map_.end();) {
+    if (it->first.owner == owner && it->first.buffer_id == buffer_id) {
+      cudaIpcCloseMemHandle(it->second.base);
+      it = map_.erase(it);
+    } else {
+      ++it;
+    }
+  }
   (void)cudaGetLastError();
-  map_.erase(it);
+}
+
+void PeerCache::forgetOwner(int owner) {
+  for (auto it = map_.begin(); it != map_.end();) {
+    if (it->first.owner == owner) {
+      cudaIpcCloseMemHandle(it->second.base);
+      it = map_.erase(it);
+    } else {
+      ++it;
+    }
+  }
+  (void)cudaGetLastError();
+}
+
+// No in-flight kernel of this process can still target a released buffer: its owner only frees it after every
+// operation that used it has completed there, and the owner's kernel completes only after it has received this
+// rank's "all my stores have landed" flag.
+void PeerCache::noteReleases(int owner, uint64_t release_count, const uint64_t* recent_ids) {
+  uint64_t& seen = releases_seen_[owner];
+  if (release_count <= seen) return;
+  const uint64_t fresh = release_count - seen;
+  if (fresh > static_cast<uint64_t>(kReleaseSlots)) {
+    forgetOwner(owner); // missed some announcements: drop everything, imports are re-created on demand
+  } else {
+    for (uint64_t k = 0; k < fresh; ++k) forgetBuffer(owner, recent_ids[k]);
+  }
+  seen = release_count;
 }
 
 void PeerCache::evictIfNeeded() {
@@ -170,7 +200,7 @@ Mailbox::~Mailbox() {
 }
 
 Mailbox::Slot* Mailbox::slot(int rank, int channel, int parity) {
-  constexpr size_t kSlotBytes = 256;
+  constexpr size_t kSlotBytes = 384;
   static_assert(sizeof(Slot) <= kSlotBytes, "mailbox slot too small");
   char* p = static_cast<char*>(base_) + (static_cast<size_t>(rank) * 4 + channel * 2 + parity) * kSlotBytes;
   return reinterpret_cast<Slot*>(p);
@@ -179,7 +209,7 @@ Mailbox::Slot* Mailbox::slot(int rank, int channel, int parity) {
 void Mailbox::create(Comm& comm, uint64_t token, int instance) {
   nranks_ = comm.size();
   me_ = comm.rank();
-  bytes_ = static_cast<size_t>(nranks_) * 4 * 256;
+  bytes_ = static_cast<size_t>(nranks_) * 4 * 384;
   if (const char* v = std::getenv("CUDECOMP_B200_HOST_TIMEOUT")) timeout_s_ = std::atof(v);
   char name[96];
   std::snprintf(name, sizeof(name), "/cudecomp_b200_%016llx_%d", static_cast<unsigned long long>(token), instance);

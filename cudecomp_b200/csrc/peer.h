@@ -35,11 +35,18 @@ struct BufDesc {
   uint32_t pad_;
 };
 
+constexpr int kReleaseSlots = 6;
+
 struct CallMsg {
   uint32_t opcode; // must match on all members (catches mismatched collective calls)
   uint32_t flags;
   BufDesc data;    // transpose: output buffer; halo: the pencil buffer
   BufDesc work;    // workspace
+  // cudecompFree is not collective in practice (the reference's own tests free workspaces on a subset of the
+  // ranks), so releases are announced here: how many buffers this rank has freed so far and the ids of the most
+  // recent ones. Readers drop their imports of those buffers (all imports of the rank if they missed some).
+  uint64_t release_count;
+  uint64_t released[kReleaseSlots];
 };
 
 // Fills `d` for a local device pointer. Never throws: failure means exportable = 0.
@@ -51,8 +58,10 @@ public:
   ~PeerCache();
   // Pointer in MY address space for `d` owned by world rank `owner`. Throws CUDA_ERROR if the import fails.
   void* resolve(int owner, const BufDesc& d);
-  // Drop every import that refers to one of these buffers (owner frees it next).
-  void forget(int owner, const BufDesc& d);
+  // Drop the imports of buffers the owner has released (see CallMsg::release_count).
+  void noteReleases(int owner, uint64_t release_count, const uint64_t* recent_ids);
+  void forgetBuffer(int owner, uint64_t buffer_id);
+  void forgetOwner(int owner);
   void clear();
 
 private:
@@ -71,6 +80,7 @@ private:
     uint64_t last_use;
   };
   std::map<Key, Entry> map_;
+  std::map<int, uint64_t> releases_seen_; // per owner
   uint64_t tick_ = 0;
   void evictIfNeeded();
 };

@@ -1,0 +1,62 @@
+"""Runs the REFERENCE's own legacy test executables (tests/cc/transpose_test.cc, tests/cc/halo_test.cc) against this
+library. The binaries are built UNMODIFIED from the reference sources by oracle/ref_tests.mk into oracle/_ref/
+(they travel to the GPU box with the snapshot); the case lists are what the reference's tests/test_runner.py
+generates from its tests/test_config.yaml (oracle/make_ref_testfiles.py -> tests/golden/ref_cases/). Each executable
+carries the reference's own known-answer generator and comparator, so "Passed all tests." is the reference's verdict.
+"""
+import json
+import os
+import signal
+import subprocess
+
+import pytest
+
+from tests._launcher import free_port
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref")
+# default: the small committed sample; CUDECOMP_REF_CASES points at a larger set from oracle/make_ref_testfiles.py
+CASES = os.environ.get("CUDECOMP_REF_CASES") or os.path.join(ROOT, "tests", "golden", "ref_cases")
+with open(os.path.join(CASES, "index.n4.json")) as f:
+    INDEX = json.load(f)
+
+# (config, dtype) pairs: every configuration with its first dtype, plus all four dtypes of the two base sweeps
+RUNS = [(name, dt) for name, info in sorted(INDEX.items()) for dt in info["dtypes"]]
+
+
+def run_mpi(nranks, argv, timeout):
+    port = free_port()
+    procs = []
+    for r in range(nranks):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(nranks), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen(argv, env=env, stdout=subprocess.PIPE if r == 0 else subprocess.DEVNULL,
+                                      stderr=subprocess.STDOUT, text=True, start_new_session=True))
+    try:
+        out, _ = procs[0].communicate(timeout=timeout)
+        codes = [procs[0].returncode] + [p.wait(timeout=60) for p in procs[1:]]
+    except subprocess.TimeoutExpired:
+        out, codes = "TIMEOUT", [-1]
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                try:
+                    os.killpg(p.pid, signal.SIGKILL)
+                except ProcessLookupError:
+                    pass
+                p.wait()
+    return out, codes
+
+
+@pytest.mark.parametrize("config,dtype", RUNS, ids=["%s-%s" % r for r in RUNS])
+def test_reference_executable(config, dtype):
+    info = INDEX[config]
+    exe = os.path.join(REF_BIN, "%s_%s" % (info["executable"], dtype))
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref binaries not built (make -f oracle/ref_tests.mk needs /root/reference)")
+    out, codes = run_mpi(info["nranks"], [exe, "--testfile", os.path.join(CASES, info["file"])], timeout=1500)
+    tail = "\n".join(out.splitlines()[-15:])
+    assert all(c == 0 for c in codes), "%s\n%s" % (codes, tail)
+    assert "Passed all tests." in out, tail
+    assert "Running %d tests" % info["kept"] in out
