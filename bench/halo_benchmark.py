@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Halo-exchange benchmark: BASELINE.json config 4 (2048 x 2048 x 1024 float, slab 1 x N decomposition, halo width 2,
+cudecompUpdateHalosX/Y/Z over all three dimensions). Reports microseconds per call and the bytes each GPU sends per
+second; these calls are latency-dominated (<= 67 MB per GPU per call), so both are shown.
+
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 bench/halo_benchmark.py
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grid", type=int, nargs=3, default=[2048, 2048, 1024])
+    ap.add_argument("--pdims", default=None)
+    ap.add_argument("--halo", type=int, nargs=3, default=[2, 2, 2])
+    ap.add_argument("--dtype", default="float", choices=["float", "double", "float_complex", "double_complex"])
+    ap.add_argument("--nonperiodic", action="store_true")
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--staged", action="store_true")
+    args = ap.parse_args()
+
+    import torch
+    from cudecomp_b200 import capi as cd
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", str(rank))) % torch.cuda.device_count())
+    dev = torch.device("cuda", torch.cuda.current_device())
+    pd = [int(v) for v in args.pdims.split("x")] if args.pdims else [1, world]
+    dt_enum = {"float": cd.CUDECOMP_FLOAT, "double": cd.CUDECOMP_DOUBLE, "float_complex": cd.CUDECOMP_FLOAT_COMPLEX,
+               "double_complex": cd.CUDECOMP_DOUBLE_COMPLEX}[args.dtype]
+    es = cd.DTYPE_SIZES[dt_enum]
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    assert cd.MPI_Init() == 0
+    res, handle = cd.cudecompInit(cd.MPI_COMM_WORLD)
+    cd.check(res)
+    cfg = cd.cudecompGridDescConfig_t()
+    cd.check(cd.cudecompGridDescConfigSetDefaults(cfg))
+    cfg.gdims[:] = args.grid
+    cfg.pdims[:] = pd
+    cfg.halo_comm_backend = cd.CUDECOMP_HALO_COMM_NVSHMEM if args.staged else cd.CUDECOMP_HALO_COMM_NCCL
+    res, gd = cd.cudecompGridDescCreate(handle, cfg)
+    cd.check(res, "cudecompGridDescCreate")
+    periods = [not args.nonperiodic] * 3
+    stream = torch.cuda.current_stream()
+    rows = []
+    for ax in range(3):
+        res, p = cd.cudecompGetPencilInfo(handle, gd, ax, args.halo)
+        cd.check(res)
+        res, wsize = cd.cudecompGetHaloWorkspaceSize(handle, gd, ax, args.halo)
+        res, work = cd.cudecompMalloc(handle, gd, max(wsize, 64) * es)
+        cd.check(res)
+        data = torch.zeros(p.size * es // 4, dtype=torch.float32, device=dev)
+        shape_g = {p.order[i]: p.shape[i] for i in range(3)}
+        for dim in range(3):
+            face = args.halo[dim] * shape_g[(dim + 1) % 3] * shape_g[(dim + 2) % 3]
+            call = lambda: cd.check(cd.UPDATE_HALOS[ax](handle, gd, data, work, dt_enum, args.halo, periods, dim,  # noqa: E731
+                                                        None, stream))
+            for _ in range(args.warmup):
+                call()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.steps):
+                call()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            path = cd.last_path(handle, gd)
+            sent = 2 * face * es if path in (2, 3) else 0
+            rows.append(dict(pencil="XYZ"[ax], dim=dim, us=t.item() * 1e3, path=["none", "local", "direct", "staged"][path],
+                             bytes_sent_per_gpu=sent, moved_bytes=2 * face * es,
+                             gbs=(2 * face * es / (t.item() * 1e-3) / 1e9) if t.item() > 0 else None))
+        cd.check(cd.cudecompFree(handle, gd, work))
+    if rank == 0:
+        print(json.dumps({"benchmark": "halo update", "grid": args.grid, "pdims": pd, "halo": args.halo, "dtype": args.dtype,
+                          "periodic": not args.nonperiodic, "n_gpus": world, "calls": rows}), flush=True)
+    cd.cudecompGridDescDestroy(handle, gd)
+    cd.cudecompFinalize(handle)
+    cd.MPI_Finalize()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -179,7 +179,13 @@ cudecompResult_t report(const std::exception& e, bool bootstrap) {
 void destroyGridDescResources(cudecompGridDesc_t gd, bool collective) {
   if (!gd) return;
   cudecompHandle_t h = gd->handle;
-  if (gd->pads.valid()) gd->pads.destroy(collective ? h->comm.get() : nullptr);
+  if (gd->pad_slot >= 0) {
+    // all ranks are past their last operation on this descriptor before anybody recycles the slot
+    if (collective && h->nranks > 1) barrier(*h->comm);
+    h->arena.zeroSlot(gd->pad_slot);
+    h->free_slots.push_back(gd->pad_slot);
+    gd->pad_slot = -1;
+  }
   gd->mbox.destroy();
 }
 
@@ -248,6 +254,7 @@ cudecompResult_t cudecompFinalize(cudecompHandle_t handle) {
   API_TRY
   checkHandle(handle);
   handle->peers.clear();
+  if (handle->arena.valid()) handle->arena.destroy(handle->comm.get());
   handle->initialized = false;
   delete handle;
   API_CATCH()
@@ -306,11 +313,16 @@ cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudeco
     for (int i = 0; i < 3; ++i) gd->config.gdims_dist[i] = gd->config.gdims[i];
 
   // Device-side plumbing shared by every operation on this descriptor (collective).
-  if (handle->have_device && handle->nranks > 1) {
-    gd->pads.create(*handle->comm);
-    gd->mbox.create(*handle->comm, handle->token, handle->next_instance);
-  } else if (handle->have_device) {
-    gd->pads.create(*handle->comm);
+  if (handle->have_device) {
+    if (!handle->arena.valid()) handle->arena.create(*handle->comm);
+    if (!handle->free_slots.empty()) {
+      gd->pad_slot = handle->free_slots.back();
+      handle->free_slots.pop_back();
+    } else {
+      if (handle->next_slot >= SignalArena::kSlots) THROW_NOT_SUPPORTED("too many live grid descriptors");
+      gd->pad_slot = handle->next_slot++;
+    }
+    if (handle->nranks > 1) gd->mbox.create(*handle->comm, handle->token, handle->next_instance);
   }
   handle->next_instance++;
 
@@ -484,8 +496,12 @@ cudecompResult_t cudecompMalloc(cudecompHandle_t handle, cudecompGridDesc_t grid
     CDB_THROW(CUDECOMP_RESULT_CUDA_ERROR, "CUDA error.", "no CUDA device is available to this process");
   // Plain device memory: peers import it with CUDA IPC the first time an operation names it, so no
   // symmetric-size agreement is needed (the reference's NVSHMEM arm MAX-reduces the size, src/cudecomp.cc:1474).
+  // Rounded up to whole 2 MiB pages: small cudaMalloc requests share a driver block (and with it one IPC handle),
+  // which peers cannot import twice.
+  const size_t kPage = size_t(2) << 20;
+  const size_t rounded = (buffer_size_bytes + kPage - 1) / kPage * kPage;
   void* p = nullptr;
-  CHECK_CUDA(cudaMalloc(&p, buffer_size_bytes));
+  CHECK_CUDA(cudaMalloc(&p, rounded));
   grid_desc->allocations.insert(p);
   *buffer = p;
   API_CATCH()

@@ -33,10 +33,11 @@ void setGeometry(cudecompGridDesc_t gd, const std::array<int32_t, 2>& pdims) {
 }
 
 void checkDeviceError(cudecompGridDesc_t gd) {
-  if (!gd->pads.valid()) return;
-  const uint32_t e = gd->pads.errorWordHost();
+  SignalArena& arena = gd->handle->arena;
+  if (!arena.valid()) return;
+  const uint32_t e = arena.errorWordHost();
   if (e == 0) return;
-  gd->pads.clearError();
+  arena.clearError();
   THROW_INTERNAL_ERROR(std::string("a device-side wait for a peer rank timed out during an earlier operation (") +
                        (e == 1 ? "entry" : "exit") +
                        " handshake); a rank of the communicator did not enter the same operation");
@@ -57,20 +58,21 @@ SyncParams makeSync(cudecompGridDesc_t gd, const std::vector<int>& peers) {
   SyncParams s;
   std::memset(&s, 0, sizeof(s));
   if (peers.empty()) return s;
-  if (!gd->pads.valid()) THROW_INTERNAL_ERROR("signal pads are not initialised");
+  SignalArena& arena = gd->handle->arena;
+  if (!arena.valid() || gd->pad_slot < 0) THROW_INTERNAL_ERROR("signal pads are not initialised");
   if (peers.size() > static_cast<size_t>(kMaxPeers))
     THROW_NOT_SUPPORTED("communicators with more than 17 ranks are not supported yet");
-  s.my_pad = gd->pads.mine();
+  s.my_pad = arena.mine(gd->pad_slot);
   s.npeers = static_cast<int32_t>(peers.size());
   for (size_t i = 0; i < peers.size(); ++i) {
-    s.peer_pad[i] = gd->pads.of(peers[i]);
+    s.peer_pad[i] = arena.of(peers[i], gd->pad_slot);
     s.peer_world[i] = peers[i];
   }
   s.my_world = gd->handle->rank;
   s.epoch = gd->epoch;
   s.do_entry = 1;
   s.do_exit = 1;
-  s.error_word = gd->pads.errorWordDevice();
+  s.error_word = arena.errorWordDevice();
   s.timeout_ns = gd->handle->spin_timeout_ns;
   return s;
 }

@@ -6,6 +6,7 @@
 #include <array>
 #include <cstdint>
 #include <set>
+#include <vector>
 
 #include "bootstrap.h"
 #include "cudecomp.h"
@@ -37,6 +38,9 @@ struct cudecompHandle {
   int next_instance = 0;
   int live_grid_descs = 0;
   cdb::PeerCache peers;          // imported peer allocations, shared by all grid descriptors
+  cdb::SignalArena arena;        // device flag pages, one slot per grid descriptor (created with the first one)
+  std::vector<int> free_slots;   // recycled slots (create/destroy are collective, so all ranks agree)
+  int next_slot = 0;
   uint64_t release_count = 0;    // buffers freed through cudecompFree so far
   uint64_t released[cdb::kReleaseSlots] = {0}; // ids of the most recent ones, newest first
 };
@@ -49,7 +53,7 @@ struct cudecompGridDesc {
   bool transpose_mem_order_set = false;
   cdb::GridGeom geom;
   std::array<int, 2> pidx{0, 0};
-  cdb::SignalPads pads;
+  int pad_slot = -1; // slot of handle->arena
   cdb::Mailbox mbox;
   uint64_t epoch = 0;
   std::set<void*> allocations; // from cudecompMalloc

@@ -94,8 +94,13 @@ void describeBuffer(const void* ptr, BufDesc* d) {
     ExportEntry e{};
     e.buffer_id = buffer_id;
     e.size = size;
-    e.exportable = (cudaIpcGetMemHandle(&e.handle, reinterpret_cast<void*>(base)) == cudaSuccess);
-    if (!e.exportable) (void)cudaGetLastError();
+    // Allocations below 2 MiB may be carved out of a shared driver block: all of them would present the same IPC
+    // handle, which a peer can import only once. They are treated as not exportable (staged path instead).
+    e.exportable = false;
+    if (size >= (size_t(2) << 20)) {
+      e.exportable = (cudaIpcGetMemHandle(&e.handle, reinterpret_cast<void*>(base)) == cudaSuccess);
+      if (!e.exportable) (void)cudaGetLastError();
+    }
     g_exports[static_cast<uint64_t>(base)] = e;
     it = g_exports.find(static_cast<uint64_t>(base));
   }
@@ -303,20 +308,20 @@ void Mailbox::exchange(int channel, const std::vector<int>& members, int my_inde
   }
 }
 
-// ----------------------------------------------------------------------------------------- SignalPads
+// ---------------------------------------------------------------------------------------- SignalArena
 
-SignalPads::~SignalPads() {
-  // process teardown without GridDescDestroy: leave the memory to the driver
+SignalArena::~SignalArena() {
+  // process teardown without cudecompFinalize: leave the memory to the driver
 }
 
-void SignalPads::create(Comm& comm) {
+void SignalArena::create(Comm& comm) {
   const int n = comm.size();
   if (n > kPadMaxRanks) THROW_NOT_SUPPORTED("more ranks than the signal pad supports");
-  const size_t bytes = 4096;
-  static_assert(kPadWords * sizeof(uint64_t) <= 4096, "signal pad larger than its page");
+  static_assert(kPadWords * sizeof(uint64_t) <= kSlotBytes, "signal pad larger than its slot");
+  const size_t bytes = kSlotBytes * kSlots;
   void* p = nullptr;
   CHECK_CUDA(cudaMalloc(&p, bytes));
-  mine_ = static_cast<uint64_t*>(p);
+  mine_ = static_cast<char*>(p);
   CHECK_CUDA(cudaMemset(mine_, 0, bytes));
   CHECK_CUDA(cudaDeviceSynchronize());
   void* eh = nullptr;
@@ -327,9 +332,9 @@ void SignalPads::create(Comm& comm) {
   CHECK_CUDA(cudaHostGetDevicePointer(&ed, eh, 0));
   err_dev_ = static_cast<uint32_t*>(ed);
 
-  pads_.assign(n, nullptr);
+  bases_.assign(n, nullptr);
   imported_.assign(n, false);
-  pads_[comm.rank()] = mine_;
+  bases_[comm.rank()] = mine_;
   if (n == 1) return;
 
   struct Msg {
@@ -351,26 +356,33 @@ void SignalPads::create(Comm& comm) {
     cudaError_t err = cudaIpcOpenMemHandle(&q, all[r].h, cudaIpcMemLazyEnablePeerAccess);
     if (err != cudaSuccess) {
       (void)cudaGetLastError();
-      failure = std::string("cannot map the signal pad of rank ") + std::to_string(r) + ": " + cudaGetErrorString(err);
+      failure = std::string("cannot map the signal arena of rank ") + std::to_string(r) + ": " + cudaGetErrorString(err);
       break;
     }
-    pads_[r] = static_cast<uint64_t*>(q);
+    bases_[r] = static_cast<char*>(q);
     imported_[r] = true;
   }
   int64_t bad = failure.empty() ? 0 : 1;
   allreduceI64(comm, &bad, 1, ReduceOp::MAX);
   if (bad) {
-    if (failure.empty()) failure = "another rank failed to map the signal pads";
+    if (failure.empty()) failure = "another rank failed to map the signal arenas";
     THROW_CUDA_ERROR(failure + " (all ranks must be on GPUs of one node with peer-to-peer access)");
   }
 }
 
-void SignalPads::destroy(Comm* comm) {
+void SignalArena::zeroSlot(int slot) {
+  if (!mine_) return;
+  cudaMemset(mine_ + static_cast<size_t>(slot) * kSlotBytes, 0, kSlotBytes);
+  cudaDeviceSynchronize();
+  (void)cudaGetLastError();
+}
+
+void SignalArena::destroy(Comm* comm) {
   if (!mine_) return;
   cudaDeviceSynchronize();
-  for (size_t r = 0; r < pads_.size(); ++r)
-    if (imported_[r] && pads_[r]) cudaIpcCloseMemHandle(pads_[r]);
-  pads_.clear();
+  for (size_t r = 0; r < bases_.size(); ++r)
+    if (imported_[r] && bases_[r]) cudaIpcCloseMemHandle(bases_[r]);
+  bases_.clear();
   imported_.clear();
   if (comm && comm->size() > 1) barrier(*comm);
   cudaFree(mine_);

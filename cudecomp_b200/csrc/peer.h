@@ -122,15 +122,22 @@ private:
   double timeout_s_ = 120.0;
 };
 
-// Device-side flag pages (see kernels.h) of all ranks of a grid descriptor.
-class SignalPads {
+// Device-side flag pages (see kernels.h). One arena per handle, exported/imported ONCE: CUDA IPC hands out one
+// handle per underlying driver allocation, and small cudaMalloc'ed buffers share a driver block, so per-descriptor
+// 4 KiB allocations cannot be imported twice ("resource already mapped"). Every grid descriptor gets one 4 KiB slot.
+class SignalArena {
 public:
-  ~SignalPads();
+  static constexpr size_t kSlotBytes = 4096;
+  static constexpr int kSlots = 512; // 2 MiB arena: a dedicated driver block
+  ~SignalArena();
   void create(Comm& comm); // collective: allocate, zero, export, import everybody's
   void destroy(Comm* comm); // collective when comm != nullptr: nobody frees before everybody unmapped
   bool valid() const { return mine_ != nullptr; }
-  uint64_t* mine() const { return mine_; }
-  uint64_t* of(int rank) const { return pads_[rank]; }
+  uint64_t* mine(int slot) const { return reinterpret_cast<uint64_t*>(mine_ + static_cast<size_t>(slot) * kSlotBytes); }
+  uint64_t* of(int rank, int slot) const {
+    return reinterpret_cast<uint64_t*>(bases_[rank] + static_cast<size_t>(slot) * kSlotBytes);
+  }
+  void zeroSlot(int slot);
   uint32_t* errorWordDevice() const { return err_dev_; }
   uint32_t errorWordHost() const { return err_host_ ? *reinterpret_cast<volatile uint32_t*>(err_host_) : 0u; }
   void clearError() {
@@ -138,8 +145,8 @@ public:
   }
 
 private:
-  uint64_t* mine_ = nullptr;
-  std::vector<uint64_t*> pads_;
+  char* mine_ = nullptr;
+  std::vector<char*> bases_;
   std::vector<bool> imported_;
   uint32_t* err_host_ = nullptr; // pinned, mapped
   uint32_t* err_dev_ = nullptr;

@@ -31,7 +31,13 @@ def run_mpi(nranks, argv, timeout):
     procs = []
     for r in range(nranks):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(nranks), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-        procs.append(subprocess.Popen(argv, env=env, stdout=subprocess.PIPE if r == 0 else subprocess.DEVNULL,
+        # rank 0 reports; the other ranks' output is kept for debugging when CUDECOMP_REF_LOG_DIR is set
+        log_dir = os.environ.get("CUDECOMP_REF_LOG_DIR")
+        sink = subprocess.DEVNULL
+        if r > 0 and log_dir:
+            os.makedirs(log_dir, exist_ok=True)
+            sink = open(os.path.join(log_dir, "%s.rank%d.log" % (os.path.basename(argv[0]), r)), "a")
+        procs.append(subprocess.Popen(argv, env=env, stdout=subprocess.PIPE if r == 0 else sink,
                                       stderr=subprocess.STDOUT, text=True, start_new_session=True))
     try:
         out, _ = procs[0].communicate(timeout=timeout)
@@ -56,7 +62,13 @@ def test_reference_executable(config, dtype):
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref binaries not built (make -f oracle/ref_tests.mk needs /root/reference)")
     out, codes = run_mpi(info["nranks"], [exe, "--testfile", os.path.join(CASES, info["file"])], timeout=1500)
-    tail = "\n".join(out.splitlines()[-15:])
+    log_dir = os.environ.get("CUDECOMP_REF_LOG_DIR")
+    if log_dir:
+        os.makedirs(log_dir, exist_ok=True)
+        with open(os.path.join(log_dir, "%s-%s.rank0.log" % (config, dtype)), "w") as f:
+            f.write(out)
+    errors = [l for l in out.splitlines() if "CUDECOMP:ERROR" in l or "FAILED" in l][:8]
+    tail = "\n".join(errors + out.splitlines()[-6:])
     assert all(c == 0 for c in codes), "%s\n%s" % (codes, tail)
     assert "Passed all tests." in out, tail
     assert "Running %d tests" % info["kept"] in out
