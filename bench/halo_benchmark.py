@@ -37,10 +37,6 @@ def main():
     dt_enum = {"float": cd.CUDECOMP_FLOAT, "double": cd.CUDECOMP_DOUBLE, "float_complex": cd.CUDECOMP_FLOAT_COMPLEX,
                "double_complex": cd.CUDECOMP_DOUBLE_COMPLEX}[args.dtype]
     es = cd.DTYPE_SIZES[dt_enum]
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-
     assert cd.MPI_Init() == 0
     res, handle = cd.cudecompInit(cd.MPI_COMM_WORLD)
     cd.check(res)
@@ -69,22 +65,19 @@ def main():
             for _ in range(args.warmup):
                 call()
             torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
+            cd.MPI_Barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for _ in range(args.steps):
                 call()
             e1.record(stream)
             torch.cuda.synchronize()
-            t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = cd.MPI_Allreduce_max(e0.elapsed_time(e1) / args.steps)
             path = cd.last_path(handle, gd)
             sent = 2 * face * es if path in (2, 3) else 0
-            rows.append(dict(pencil="XYZ"[ax], dim=dim, us=t.item() * 1e3, path=["none", "local", "direct", "staged"][path],
+            rows.append(dict(pencil="XYZ"[ax], dim=dim, us=ms * 1e3, path=["none", "local", "direct", "staged"][path],
                              bytes_sent_per_gpu=sent, moved_bytes=2 * face * es,
-                             gbs=(2 * face * es / (t.item() * 1e-3) / 1e9) if t.item() > 0 else None))
+                             gbs=(2 * face * es / (ms * 1e-3) / 1e9) if ms > 0 else None))
         cd.check(cd.cudecompFree(handle, gd, work))
     if rank == 0:
         print(json.dumps({"benchmark": "halo update", "grid": args.grid, "pdims": pd, "halo": args.halo, "dtype": args.dtype,
@@ -92,8 +85,6 @@ def main():
     cd.cudecompGridDescDestroy(handle, gd)
     cd.cudecompFinalize(handle)
     cd.MPI_Finalize()
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -277,6 +277,13 @@ def MPI_Barrier(comm=MPI_COMM_WORLD):
     return lib.MPI_Barrier(comm)
 
 
+def MPI_Allreduce_max(value, comm=MPI_COMM_WORLD):
+    """max over the ranks of one double (MPI_DOUBLE = (3 << 8) | 8, MPI_MAX = 2 in include/mpi_shim/mpi.h)."""
+    v = ctypes.c_double(float(value))
+    lib.MPI_Allreduce(ctypes.c_void_p(-1), ctypes.byref(v), 1, (3 << 8) | 8, 2, comm)  # MPI_IN_PLACE
+    return v.value
+
+
 def MPI_Comm_split(comm, color, key):
     out = ctypes.c_int(0)
     lib.MPI_Comm_split(comm, color, key, ctypes.byref(out))

@@ -31,7 +31,7 @@ def make_config(case):
     c = cd.cudecompGridDescConfig_t()
     cd.check(cd.cudecompGridDescConfigSetDefaults(c))
     c.gdims[:] = case["gdims"]
-    c.pdims[:] = case["pdims"]
+    c.pdims[:] = case.get("pdims", [0, 0])
     if case.get("gdims_dist"):
         c.gdims_dist[:] = case["gdims_dist"]
     c.rank_order = case.get("rank_order", 0)

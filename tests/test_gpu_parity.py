@@ -127,3 +127,44 @@ def two_results():
 @pytest.mark.parametrize("i", range(len(TWO)), ids=[c["name"] for c in TWO])
 def test_two_ranks(two_results, i):
     _assert_case(two_results, i, TWO[i])
+
+
+# ------------------------------------------------------------------------- the transposes inside their caller
+def _run_script(nranks, argv, timeout=600):
+    import os
+    import signal
+    import subprocess
+    import sys
+    from tests._launcher import ROOT, free_port
+    port = free_port()
+    procs = []
+    for r in range(nranks):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(nranks), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), PYTHONPATH=ROOT)
+        procs.append(subprocess.Popen([sys.executable] + argv, env=env, cwd=ROOT,
+                                      stdout=subprocess.PIPE if r == 0 else subprocess.DEVNULL,
+                                      stderr=subprocess.STDOUT, text=True, start_new_session=True))
+    try:
+        out, _ = procs[0].communicate(timeout=timeout)
+        codes = [procs[0].returncode] + [p.wait(timeout=60) for p in procs[1:]]
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                try:
+                    os.killpg(p.pid, signal.SIGKILL)
+                except ProcessLookupError:
+                    pass
+                p.wait()
+    return out, codes
+
+
+@pytest.mark.parametrize("layout", [[], ["--axis-contiguous"]], ids=["default", "axis_contiguous"])
+def test_distributed_fft_matches_numpy_fftn(layout):
+    """benchmark/benchmark.cu's sequence (FFT per pencil + 4 transposes) on 4 ranks: forward transform equals
+    numpy.fft.fftn of the whole field, forward + backward reproduces the input (tolerance 1e-10, benchmark.cu:21-27)."""
+    import json
+    out, codes = _run_script(4, ["bench/fft_benchmark.py", "--grid", "48", "40", "36", "--check-global", "--steps", "1",
+                                 "--warmup", "1"] + layout)
+    assert all(c == 0 for c in codes), out[-3000:]
+    line = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert line["passed"] and line["max_roundtrip_error"] <= 1e-10 and line["global_fftn_rel_error"] < 1e-12
