@@ -98,7 +98,11 @@ struct DeviceBuffer {
   ~DeviceBuffer() {
     if (p) cudaFree(p);
   }
-  void alloc(size_t bytes) { CHECK_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 256))); }
+  // whole 2 MiB pages, like cudecompMalloc: peers must be able to import the buffer (see peer.cc describeBuffer)
+  void alloc(size_t bytes) {
+    const size_t page = size_t(2) << 20;
+    CHECK_CUDA(cudaMalloc(&p, (std::max<size_t>(bytes, 1) + page - 1) / page * page));
+  }
 };
 
 struct Events {
