@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #define CK(x)                                                                                                          \
@@ -20,7 +21,8 @@
 
 using namespace cdb;
 
-int main() {
+int main(int argc, char** argv) {
+  const bool profile_remote = argc > 1 && std::string(argv[1]) == "--profile-remote";
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (ndev < 2) {
@@ -31,7 +33,7 @@ int main() {
   char *src[2], *dst[2];
   cudaStream_t st[2];
   cudaEvent_t e0[2], e1[2];
-  const size_t bytes = 64ull << 20;
+  const size_t bytes = profile_remote ? (1024ull << 20) : (64ull << 20);
   for (int d = 0; d < 2; ++d) {
     CK(cudaSetDevice(d));
     CK(cudaDeviceEnablePeerAccess(1 - d, 0));
@@ -106,6 +108,13 @@ int main() {
       if (rep == 1) printf("%-60s %8.2f us per launch\n", name, worst * 1e3 / iters);
     }
   };
+  if (profile_remote) {
+    // for ncu (single process, no handshake so that kernel replay is safe): cdb::rowCopyKernel<uint4> storing 1 GiB
+    // into the peer GPU, then the same box locally
+    run("remote copy 32768 tiles (1 GiB), no handshake, default grid", 32768, false, true, 0, 3);
+    run("local copy 32768 tiles (1 GiB), no handshake, default grid", 32768, false, false, 0, 3);
+    return 0;
+  }
   const int it = 300;
   run("empty kernel, no handshake, 1 CTA", 0, false, false, 1, it);
   run("handshake only, 1 CTA", 0, true, false, 1, it);
