@@ -125,6 +125,34 @@ template <typename V> __global__ void __launch_bounds__(256) rowCopyKernel(const
     const uint32_t npieces = rows_here * pieces_per_row;
     const int64_t esz = p.elem_size;
 
+    if (bx.row_vecs <= 32u) {
+      // Short rows (e.g. the 2-element faces of a halo along the contiguous axis): a warp per row would leave most
+      // lanes idle, so lanes take (row, vector) pairs of the tile instead.
+      const uint32_t total_vecs = rows_here * nvec;
+      for (uint32_t e0 = threadIdx.x; e0 < total_vecs; e0 += blockDim.x * kUnroll) {
+        V v[kUnroll];
+        V* dptr[kUnroll];
+#pragma unroll
+        for (uint32_t k = 0; k < kUnroll; ++k) {
+          const uint32_t e = e0 + k * blockDim.x;
+          dptr[k] = nullptr;
+          if (e < total_vecs) {
+            const uint32_t r = e / nvec;
+            const uint32_t c = e - r * nvec;
+            const int64_t row = row0 + r;
+            const int64_t i1 = row % bx.n[1];
+            const int64_t i2 = row / bx.n[1];
+            v[k] = loadStream(reinterpret_cast<const V*>(bx.src + (i1 * bx.ss[1] + i2 * bx.ss[2]) * esz) + c0 + c);
+            dptr[k] = reinterpret_cast<V*>(bx.dst + (i1 * bx.ds[1] + i2 * bx.ds[2]) * esz) + c0 + c;
+          }
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < kUnroll; ++k)
+          if (dptr[k]) storeStream(dptr[k], v[k]);
+      }
+      continue;
+    }
+
     for (uint32_t pc = warp; pc < npieces; pc += nwarps) {
       const uint32_t r = pc / pieces_per_row;
       const uint32_t q = pc - r * pieces_per_row;

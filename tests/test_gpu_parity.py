@@ -168,3 +168,36 @@ def test_distributed_fft_matches_numpy_fftn(layout):
     assert all(c == 0 for c in codes), out[-3000:]
     line = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
     assert line["passed"] and line["max_roundtrip_error"] <= 1e-10 and line["global_fftn_rel_error"] < 1e-12
+
+
+# ------------------------------------------------------------------ 8 ranks: the 2x4 grid of the headline benchmark
+EIGHT = [
+    dict(kind="transpose", name="Grid2x4_chain_c128_oop", gdims=[32, 40, 48], pdims=[2, 4], dtype="double_complex",
+         ops=["XY", "YZ", "ZY", "YX"], out_of_place=True),
+    dict(kind="transpose", name="Grid2x4_chain_c64_inplace", gdims=[32, 40, 48], pdims=[2, 4], dtype="float_complex",
+         ops=["XY", "YZ", "ZY", "YX"]),
+    dict(kind="transpose", name="Grid2x4_uneven_axis_contiguous", gdims=[30, 29, 35], pdims=[2, 4], dtype="double",
+         ops=["XY", "YZ", "ZY", "YX"], out_of_place=True, axis_contiguous=[True] * 3),
+    dict(kind="transpose", name="Grid4x2_halo_padding_float", gdims=[30, 29, 35], pdims=[4, 2], dtype="float",
+         ops=["XY", "YZ", "ZY", "YX"], out_of_place=True,
+         halos={"0": [1, 1, 1], "1": [1, 2, 1], "2": [2, 1, 1]}, pads={"0": [1, 0, 0], "1": [0, 1, 0], "2": [0, 0, 2]}),
+    dict(kind="transpose", name="Slab1x8_chain", gdims=[24, 32, 40], pdims=[1, 8], dtype="double", out_of_place=True,
+         ops=["XY", "YZ", "ZY", "YX"]),
+    dict(kind="transpose", name="Slab8x1_chain_inplace", gdims=[24, 32, 40], pdims=[8, 1], dtype="float_complex",
+         ops=["XY", "YZ", "ZY", "YX"]),
+    dict(kind="halo", name="Halo2x4_axis0_periodic", gdims=[32, 40, 48], pdims=[2, 4], dtype="float", axis=0,
+         halo=[2, 2, 2], periods=[True] * 3),
+    dict(kind="halo", name="Halo1x8_axis2_nonperiodic_c128", gdims=[32, 40, 48], pdims=[1, 8], dtype="double_complex",
+         axis=2, halo=[1, 2, 1], periods=[False] * 3),
+    dict(kind="autotune", name="Autotune8", gdims=[32, 40, 48], dtype="double", n_trials=1, autotune_backend=True),
+]
+
+
+@pytest.fixture(scope="module")
+def eight_results():
+    return _run(8, EIGHT)[0]
+
+
+@pytest.mark.parametrize("i", range(len(EIGHT)), ids=[c["name"] for c in EIGHT])
+def test_eight_ranks(eight_results, i):
+    _assert_case(eight_results, i, EIGHT[i])
