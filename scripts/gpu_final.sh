@@ -15,7 +15,7 @@ for l in sys.stdin:
 run
 run --no-e2e --inplace
 run --no-e2e --grid 512 --dtype float_complex
-if [ "$N" = "8" ]; then run --no-e2e --grid 2048; fi
+echo "== 8-rank parity"; (python -m pytest tests/test_gpu_parity.py -q -m gpu -k "eight or four_ranks and Baseline") > gpurun_out/t_eight_${N}.log 2>&1; tail -3 gpurun_out/t_eight_${N}.log
 echo "== fft_benchmark 1024"
 $TR --master-port 29800 bench/fft_benchmark.py --grid 1024 > gpurun_out/fft_${N}.log 2>&1; grep '^{' gpurun_out/fft_${N}.log || tail -5 gpurun_out/fft_${N}.log
 $TR --master-port 29810 bench/fft_benchmark.py --grid 1024 --axis-contiguous > gpurun_out/fft_ac_${N}.log 2>&1; grep '^{' gpurun_out/fft_ac_${N}.log || tail -5 gpurun_out/fft_ac_${N}.log
@@ -25,7 +25,5 @@ import sys,json
 for l in sys.stdin:
     d=json.loads(l)
     for c in d['calls']: print(c['pencil'], 'dim', c['dim'], c['path'], round(c['us'],1), 'us', round(c['moved_bytes']/1e6,1), 'MB', round(c['gbs'] or 0,1), 'GB/s')" || tail -5 gpurun_out/halo_${N}.log
-$TR --master-port 29830 bench/halo_benchmark.py --nonperiodic --staged > gpurun_out/halo_st_${N}.log 2>&1; grep '^{' gpurun_out/halo_st_${N}.log | cut -c1-300
 echo "== autotune 768^3"
 $TR --master-port 29900 scripts/autotune_bench.py --grid 768 --backend > gpurun_out/autotune_768_${N}.log 2>&1; grep -E "SELECTED|\"autotune\"" gpurun_out/autotune_768_${N}.log
-$TR --master-port 29910 scripts/autotune_bench.py --grid 768 --inplace > gpurun_out/autotune_768_inplace_${N}.log 2>&1; grep -E "SELECTED|\"autotune\"" gpurun_out/autotune_768_inplace_${N}.log
