@@ -137,7 +137,8 @@ API_SYMBOLS = [
     "cudecompUpdateHalosZ",
 ]
 EXT_SYMBOLS = ["cudecompB200GetLaunchCount", "cudecompB200GetLastPath", "cudecompB200SetTuning",
-               "cudecompB200CheckErrors", "cudecompB200DescribeTransposeBoxes", "cudecompB200DescribeHaloBoxes"]
+               "cudecompB200CheckErrors", "cudecompB200DescribeTransposeBoxes", "cudecompB200DescribeHaloBoxes",
+               "cudecompB200PlanTransposeBoxes", "cudecompB200PlanHaloBoxes"]
 MPI_SHIM_SYMBOLS = ["MPI_Init", "MPI_Init_thread", "MPI_Initialized", "MPI_Finalize", "MPI_Finalized", "MPI_Abort",
                     "MPI_Wtime", "MPI_Get_processor_name", "MPI_Error_string", "MPI_Comm_rank", "MPI_Comm_size",
                     "MPI_Comm_split", "MPI_Comm_split_type", "MPI_Comm_dup", "MPI_Comm_free", "MPI_Comm_c2f",
@@ -194,6 +195,10 @@ _sig("cudecompB200DescribeTransposeBoxes", _i32,
 _sig("cudecompB200DescribeHaloBoxes", _i32,
      [cudecompHandle_t, cudecompGridDesc_t, _i32, _i32, _i32p, _P(ctypes.c_bool), _i32p, _i32,
       _P(cudecompB200Box_t), _i32])
+_sig("cudecompB200PlanTransposeBoxes", _i32,
+     [_P(cudecompGridDescConfig_t), _i32, _i32, _i32, _i32p, _i32p, _i32p, _i32p, _i32, _P(cudecompB200Box_t), _i32])
+_sig("cudecompB200PlanHaloBoxes", _i32,
+     [_P(cudecompGridDescConfig_t), _i32, _i32, _i32, _i32p, _P(ctypes.c_bool), _i32p, _i32, _P(cudecompB200Box_t), _i32])
 _sig("MPI_Init", ctypes.c_int, [_vp, _vp])
 _sig("MPI_Finalize", ctypes.c_int, [])
 _sig("MPI_Comm_rank", ctypes.c_int, [ctypes.c_int, _P(ctypes.c_int)])
@@ -463,4 +468,25 @@ def describe_halo_boxes(handle, grid_desc, ax, dim, halo_extents, halo_periods=N
                                           _arr3(padding), 1 if staged else 0, arr, max_boxes)
     if n < 0:
         raise CudecompError(CUDECOMP_RESULT_INVALID_USAGE, "cudecompB200DescribeHaloBoxes")
+    return _boxes(n, arr)
+
+
+def plan_transpose_boxes(config, rank, ax, direction, input_halo_extents=None, output_halo_extents=None,
+                         input_padding=None, output_padding=None, staged=False, max_boxes=256):
+    """Handle-free planner (any rank of any process grid). Raises CudecompError with the library's result code."""
+    arr = (cudecompB200Box_t * max_boxes)()
+    n = lib.cudecompB200PlanTransposeBoxes(ctypes.byref(config), rank, ax, direction, _arr3(input_halo_extents),
+                                           _arr3(output_halo_extents), _arr3(input_padding), _arr3(output_padding),
+                                           1 if staged else 0, arr, max_boxes)
+    if n < 0:
+        raise CudecompError(-n, "cudecompB200PlanTransposeBoxes")
+    return _boxes(n, arr)
+
+
+def plan_halo_boxes(config, rank, ax, dim, halo_extents, halo_periods=None, padding=None, staged=False, max_boxes=16):
+    arr = (cudecompB200Box_t * max_boxes)()
+    n = lib.cudecompB200PlanHaloBoxes(ctypes.byref(config), rank, ax, dim, _arr3(halo_extents), _bool3(halo_periods),
+                                      _arr3(padding), 1 if staged else 0, arr, max_boxes)
+    if n < 0:
+        raise CudecompError(-n, "cudecompB200PlanHaloBoxes")
     return _boxes(n, arr)

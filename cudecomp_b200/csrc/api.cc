@@ -611,6 +611,78 @@ cudecompResult_t cudecompB200CheckErrors(cudecompHandle_t handle, cudecompGridDe
   API_CATCH()
 }
 
+static int32_t emitBoxes(const std::vector<BoxDesc>& push, const std::vector<BoxDesc>& unpack, cudecompB200Box_t* boxes,
+                         int32_t max_boxes) {
+  std::vector<BoxDesc> all = push;
+  for (auto& u : unpack) all.push_back(u);
+  int32_t n = 0;
+  for (size_t i = 0; i < all.size() && n < max_boxes; ++i, ++n) {
+    cudecompB200Box_t& o = boxes[n];
+    o.peer_rank = all[i].peer_world;
+    o.is_unpack = (i >= push.size()) ? 1 : 0;
+    o.src_offset = all[i].src_off;
+    o.dst_offset = all[i].dst_off;
+    for (int k = 0; k < 3; ++k) {
+      o.extent[k] = all[i].ext[k];
+      o.src_stride[k] = all[i].sstr[k];
+      o.dst_stride[k] = all[i].dstr[k];
+    }
+  }
+  return static_cast<int32_t>(all.size());
+}
+
+// geometry of a config without a handle (same resolution rules as cudecompGridDescCreateVersioned)
+static GridGeom geomFromConfig(const cudecompGridDescConfig_t* c) {
+  if (!c) THROW_INVALID_USAGE("config argument cannot be null");
+  if (c->pdims[0] < 1 || c->pdims[1] < 1) THROW_INVALID_USAGE("pdims values are invalid");
+  GridGeom g;
+  const bool dist_set = c->gdims_dist[0] != 0 && c->gdims_dist[1] != 0 && c->gdims_dist[2] != 0;
+  const bool order_set = c->transpose_mem_order[0][0] >= 0;
+  for (int i = 0; i < 3; ++i) {
+    g.gdims[i] = c->gdims[i];
+    g.gdims_dist[i] = dist_set ? c->gdims_dist[i] : c->gdims[i];
+    for (int j = 0; j < 3; ++j)
+      g.order[i][j] = order_set ? c->transpose_mem_order[i][j] : (c->transpose_axis_contiguous[i] ? (i + j) % 3 : j);
+  }
+  g.pdims = {c->pdims[0], c->pdims[1]};
+  g.col_major = (c->rank_order == CUDECOMP_RANK_ORDER_COL_MAJOR);
+  return g;
+}
+
+int32_t cudecompB200PlanTransposeBoxes(const cudecompGridDescConfig_t* config, int32_t rank, int32_t ax, int32_t dir,
+                                       const int32_t input_halo_extents[], const int32_t output_halo_extents[],
+                                       const int32_t input_padding[], const int32_t output_padding[], int32_t staged,
+                                       cudecompB200Box_t* boxes, int32_t max_boxes) {
+  try {
+    GridGeom g = geomFromConfig(config);
+    if (rank < 0 || rank >= g.pdims[0] * g.pdims[1]) THROW_INVALID_USAGE("rank out of range");
+    TransposePlan plan = buildTransposePlan(g, pidxOfRank(g, rank), ax, dir, input_halo_extents, output_halo_extents,
+                                            input_padding, output_padding, staged ? DstKind::STAGE : DstKind::FINAL, false);
+    return emitBoxes(plan.push, plan.unpack, boxes, max_boxes);
+  } catch (const cdb::Error& e) {
+    return -static_cast<int32_t>(e.code());
+  } catch (const std::exception&) {
+    return -static_cast<int32_t>(CUDECOMP_RESULT_INTERNAL_ERROR);
+  }
+}
+
+int32_t cudecompB200PlanHaloBoxes(const cudecompGridDescConfig_t* config, int32_t rank, int32_t ax, int32_t dim,
+                                  const int32_t halo_extents[], const bool halo_periods[], const int32_t padding[],
+                                  int32_t staged, cudecompB200Box_t* boxes, int32_t max_boxes) {
+  try {
+    GridGeom g = geomFromConfig(config);
+    if (rank < 0 || rank >= g.pdims[0] * g.pdims[1]) THROW_INVALID_USAGE("rank out of range");
+    HaloPlan plan = buildHaloPlan(g, pidxOfRank(g, rank), ax, dim, halo_extents, halo_periods, padding,
+                                  staged ? DstKind::STAGE : DstKind::FINAL);
+    if (plan.nothing) return 0;
+    return emitBoxes(plan.push, plan.unpack, boxes, max_boxes);
+  } catch (const cdb::Error& e) {
+    return -static_cast<int32_t>(e.code());
+  } catch (const std::exception&) {
+    return -static_cast<int32_t>(CUDECOMP_RESULT_INTERNAL_ERROR);
+  }
+}
+
 int32_t cudecompB200DescribeTransposeBoxes(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t ax,
                                            int32_t dir, const int32_t input_halo_extents[],
                                            const int32_t output_halo_extents[], const int32_t input_padding[],
@@ -622,22 +694,7 @@ int32_t cudecompB200DescribeTransposeBoxes(cudecompHandle_t handle, cudecompGrid
     TransposePlan plan =
         buildTransposePlan(grid_desc->geom, grid_desc->pidx, ax, dir, input_halo_extents, output_halo_extents,
                            input_padding, output_padding, staged ? DstKind::STAGE : DstKind::FINAL, false);
-    std::vector<BoxDesc> all = plan.push;
-    for (auto& u : plan.unpack) all.push_back(u);
-    int32_t n = 0;
-    for (size_t i = 0; i < all.size() && n < max_boxes; ++i, ++n) {
-      cudecompB200Box_t& o = boxes[n];
-      o.peer_rank = all[i].peer_world;
-      o.is_unpack = (i >= plan.push.size()) ? 1 : 0;
-      o.src_offset = all[i].src_off;
-      o.dst_offset = all[i].dst_off;
-      for (int k = 0; k < 3; ++k) {
-        o.extent[k] = all[i].ext[k];
-        o.src_stride[k] = all[i].sstr[k];
-        o.dst_stride[k] = all[i].dstr[k];
-      }
-    }
-    return static_cast<int32_t>(all.size());
+    return emitBoxes(plan.push, plan.unpack, boxes, max_boxes);
   } catch (const std::exception& e) {
     std::cerr << e.what();
     return -1;
@@ -653,22 +710,7 @@ int32_t cudecompB200DescribeHaloBoxes(cudecompHandle_t handle, cudecompGridDesc_
     HaloPlan plan = buildHaloPlan(grid_desc->geom, grid_desc->pidx, ax, dim, halo_extents, halo_periods, padding,
                                   staged ? DstKind::STAGE : DstKind::FINAL);
     if (plan.nothing) return 0;
-    std::vector<BoxDesc> all = plan.push;
-    for (auto& u : plan.unpack) all.push_back(u);
-    int32_t n = 0;
-    for (size_t i = 0; i < all.size() && n < max_boxes; ++i, ++n) {
-      cudecompB200Box_t& o = boxes[n];
-      o.peer_rank = all[i].peer_world;
-      o.is_unpack = (i >= plan.push.size()) ? 1 : 0;
-      o.src_offset = all[i].src_off;
-      o.dst_offset = all[i].dst_off;
-      for (int k = 0; k < 3; ++k) {
-        o.extent[k] = all[i].ext[k];
-        o.src_stride[k] = all[i].sstr[k];
-        o.dst_stride[k] = all[i].dstr[k];
-      }
-    }
-    return static_cast<int32_t>(all.size());
+    return emitBoxes(plan.push, plan.unpack, boxes, max_boxes);
   } catch (const std::exception& e) {
     std::cerr << e.what();
     return -1;

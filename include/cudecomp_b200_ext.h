@@ -47,6 +47,18 @@ int32_t cudecompB200DescribeHaloBoxes(cudecompHandle_t handle, cudecompGridDesc_
                                       const int32_t halo_extents[], const bool halo_periods[], const int32_t padding[],
                                       int32_t staged, cudecompB200Box_t* boxes, int32_t max_boxes);
 
+/* Handle-free variants: the plan any `rank` of a `pdims[0] x pdims[1]` grid would execute for `config` (only gdims,
+ * gdims_dist, pdims, rank_order, transpose_axis_contiguous and transpose_mem_order are read). Pure host arithmetic,
+ * used to property-test the planner over arbitrary decompositions in one process. Returns the number of boxes, or
+ * minus the cudecompResult_t code on error (e.g. -2 for decompositions with empty pencils). */
+int32_t cudecompB200PlanTransposeBoxes(const cudecompGridDescConfig_t* config, int32_t rank, int32_t ax, int32_t dir,
+                                       const int32_t input_halo_extents[], const int32_t output_halo_extents[],
+                                       const int32_t input_padding[], const int32_t output_padding[], int32_t staged,
+                                       cudecompB200Box_t* boxes, int32_t max_boxes);
+int32_t cudecompB200PlanHaloBoxes(const cudecompGridDescConfig_t* config, int32_t rank, int32_t ax, int32_t dim,
+                                  const int32_t halo_extents[], const bool halo_periods[], const int32_t padding[],
+                                  int32_t staged, cudecompB200Box_t* boxes, int32_t max_boxes);
+
 #ifdef __cplusplus
 }
 #endif

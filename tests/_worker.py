@@ -336,6 +336,81 @@ def plan_case(handle, rank, case):
         cd.cudecompGridDescDestroy(handle, gd)
 
 
+def shim_battery(rank, nranks):
+    """Exercises the MPI subset of include/mpi_shim/mpi.h through the exported C symbols."""
+    L = cd.lib
+    MPI_INT, MPI_DOUBLE, MPI_FLOAT, MPI_INT64 = (1 << 8) | 4, (3 << 8) | 8, (3 << 8) | 4, (1 << 8) | 8
+    SUM, MAX, MIN, LOR = 1, 2, 3, 4
+    W = cd.MPI_COMM_WORLD
+    IN_PLACE = ctypes.c_void_p(-1)
+    out = {}
+    v = (ctypes.c_int * 2)(rank + 1, 10 * rank)
+    r = (ctypes.c_int * 2)()
+    assert L.MPI_Allreduce(v, r, 2, MPI_INT, SUM, W) == 0
+    out["allreduce_int_sum"] = list(r)
+    d = (ctypes.c_double * 1)(1.5 * rank)
+    assert L.MPI_Allreduce(IN_PLACE, d, 1, MPI_DOUBLE, MAX, W) == 0
+    out["allreduce_double_max_inplace"] = d[0]
+    f = (ctypes.c_float * 1)(float(rank) - 2.0)
+    assert L.MPI_Allreduce(IN_PLACE, f, 1, MPI_FLOAT, MIN, W) == 0
+    out["allreduce_float_min"] = f[0]
+    flag = (ctypes.c_int * 1)(1 if rank == nranks - 1 else 0)
+    assert L.MPI_Allreduce(IN_PLACE, flag, 1, MPI_INT, LOR, W) == 0
+    out["allreduce_lor"] = flag[0]
+    b = (ctypes.c_int64 * 3)(*([7, 8, 9] if rank == 1 % nranks else [0, 0, 0]))
+    assert L.MPI_Bcast(b, 3, MPI_INT64, 1 % nranks, W) == 0
+    out["bcast"] = list(b)
+    g = (ctypes.c_int * nranks)()
+    mine = (ctypes.c_int * 1)(100 + rank)
+    assert L.MPI_Allgather(mine, 1, MPI_INT, g, 1, MPI_INT, W) == 0
+    out["allgather"] = list(g)
+    L.MPI_Gather.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                             ctypes.c_int, ctypes.c_int]
+    g2 = (ctypes.c_int * nranks)()
+    assert L.MPI_Gather(mine, 1, MPI_INT, g2, 1, MPI_INT, 0, W) == 0
+    out["gather_root0"] = list(g2) if rank == 0 else None
+    L.MPI_Reduce.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                             ctypes.c_int]
+    res = (ctypes.c_int * 1)(rank * rank)
+    if rank == 0:  # the pattern of the reference's test drivers (tests/cc/transpose_test.cc:617)
+        assert L.MPI_Reduce(IN_PLACE, res, 1, MPI_INT, MAX, 0, W) == 0
+    else:
+        assert L.MPI_Reduce(res, res, 1, MPI_INT, MAX, 0, W) == 0
+    out["reduce_max_root0"] = res[0] if rank == 0 else None
+    # sub-communicators: even / odd ranks, reversed order inside
+    sub = cd.MPI_Comm_split(W, rank % 2, -rank)
+    out["split_rank"], out["split_size"] = cd.MPI_Comm_rank(sub), cd.MPI_Comm_size(sub)
+    s = (ctypes.c_int * 1)(rank)
+    assert L.MPI_Allreduce(IN_PLACE, s, 1, MPI_INT, SUM, sub) == 0
+    out["split_sum"] = s[0]
+    L.MPI_Comm_dup.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    dup = ctypes.c_int(0)
+    assert L.MPI_Comm_dup(sub, ctypes.byref(dup)) == 0
+    out["dup_size"] = cd.MPI_Comm_size(dup.value)
+    assert cd.MPI_Barrier(dup.value) == 0
+    c1, c2 = ctypes.c_int(sub), ctypes.c_int(dup.value)
+    L.MPI_Comm_free(ctypes.byref(c1))
+    L.MPI_Comm_free(ctypes.byref(c2))
+    out["freed"] = [c1.value, c2.value]
+    # a cuDecomp handle on a sub-communicator (the reference's tests do this, mpi_test_utils.cc:56-66)
+    sub2 = cd.MPI_Comm_split(W, 0 if rank < 2 else 1, rank)
+    res_, h = cd.cudecompInit(sub2)
+    cfg = cd.cudecompGridDescConfig_t()
+    cd.cudecompGridDescConfigSetDefaults(cfg)
+    cfg.gdims[:] = [8, 8, 8]
+    n_sub = cd.MPI_Comm_size(sub2)
+    cfg.pdims[:] = [1, n_sub]
+    res2, gd = cd.cudecompGridDescCreate(h, cfg)
+    out["subcomm_handle"] = [res_, res2]
+    if res2 == 0:
+        _, p = cd.cudecompGetPencilInfo(h, gd, 0)
+        out["subcomm_shape"] = list(p.shape)
+        cd.cudecompGridDescDestroy(h, gd)
+    cd.cudecompFinalize(h)
+    out["wtime_positive"] = cd.lib.MPI_Wtime() > 0
+    return out
+
+
 def main():
     payload_path, out_dir = sys.argv[1], sys.argv[2]
     with open(payload_path) as f:
@@ -352,7 +427,9 @@ def main():
             results.append(dict(ok=False, msg="skipped after an earlier failure that may have desynchronised the ranks"))
             continue
         try:
-            if payload["mode"] == "plan":
+            if payload["mode"] == "shim":
+                results.append(shim_battery(rank, int(os.environ["WORLD_SIZE"])))
+            elif payload["mode"] == "plan":
                 results.append(plan_case(handle, rank, case))
             elif case["kind"] == "halo":
                 results.append(halo_case(gpu, handle, rank, case))

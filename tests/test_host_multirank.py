@@ -179,3 +179,26 @@ def test_two_ranks_with_gloo_cross_check():
             yz = per_rank[r]["transposes"]["YZ/0"]
             assert len(xy) == (2 if case["name"] == "2x1" else 1)
             assert len(yz) == (2 if case["name"] == "1x2" else 1)
+
+
+def test_mpi_shim_collectives_on_4_ranks():
+    """The MPI subset exported for callers without MPI (include/mpi_shim/mpi.h), exercised through the C symbols."""
+    results, _ = run_ranks(4, "shim", [dict(name="battery")], timeout=300)
+    for r in range(4):
+        out = results[r][0]
+        assert out.get("ok", True) is not False, out
+        assert out["allreduce_int_sum"] == [1 + 2 + 3 + 4, 10 * (0 + 1 + 2 + 3)]
+        assert out["allreduce_double_max_inplace"] == 4.5
+        assert out["allreduce_float_min"] == -2.0
+        assert out["allreduce_lor"] == 1
+        assert out["bcast"] == [7, 8, 9]
+        assert out["allgather"] == [100, 101, 102, 103]
+        assert out["split_size"] == 2 and out["dup_size"] == 2
+        # key = -rank reverses the order inside each colour
+        assert out["split_rank"] == (1 if r < 2 else 0)
+        assert out["split_sum"] == (0 + 2 if r % 2 == 0 else 1 + 3)
+        assert out["freed"] == [0, 0]
+        assert out["subcomm_handle"] == [0, 0] and out["subcomm_shape"] == [8, 8, 4]
+        assert out["wtime_positive"]
+    assert results[0][0]["gather_root0"] == [100, 101, 102, 103]
+    assert results[0][0]["reduce_max_root0"] == 9

@@ -1,0 +1,141 @@
+"""Property tests of the transfer planner over arbitrary decompositions (CPU only, one process).
+
+For random grids, process grids (incl. non-power-of-two and slab grids up to 8 ranks), rank orders, memory orders,
+gdims_dist, halos and padding, the plans of ALL ranks (handle-free planner entry points of libcudecomp.so) are executed
+with numpy and must reproduce the oracle's result byte for byte -- interior cells and the cells that must stay
+untouched -- for all four transposes in both schedules (direct / staged) and for halo updates of every pencil axis and
+dimension. Error behaviour must agree too: empty pencils -> NOT_SUPPORTED, halo wider than a slab -> INVALID_USAGE.
+"""
+import itertools
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+from cudecomp_b200 import capi as cd
+from oracle import oracle as orc
+from tests.test_host_multirank import apply_box, simulate_transpose
+
+PDIMS = [(1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (1, 3), (2, 3), (3, 2), (4, 2), (2, 4), (1, 8), (8, 1), (5, 1), (3, 3)]
+PERMS = [list(p) for p in itertools.permutations(range(3))]
+OPS = {"XY": (0, 1), "YZ": (1, 1), "ZY": (2, -1), "YX": (1, -1)}
+
+
+@st.composite
+def decompositions(draw):
+    pd = draw(st.sampled_from(PDIMS))
+    gdims = [draw(st.integers(1, 14)) for _ in range(3)]
+    layout = draw(st.sampled_from(["default", "axis_contiguous", "explicit"]))
+    ac = [False] * 3
+    mo = None
+    if layout == "axis_contiguous":
+        ac = [draw(st.booleans()) for _ in range(3)]
+    elif layout == "explicit":
+        mo = [draw(st.sampled_from(PERMS)) for _ in range(3)]
+    dist = None
+    if draw(st.booleans()):
+        dist = [draw(st.integers(1, g)) for g in gdims]
+    col_major = draw(st.booleans())
+    halos = {str(a): [draw(st.integers(0, 2)) for _ in range(3)] for a in range(3)}
+    pads = {str(a): [draw(st.integers(0, 2)) for _ in range(3)] for a in range(3)}
+    return dict(gdims=gdims, pdims=list(pd), axis_contiguous=ac, mem_order=mo, gdims_dist=dist, col_major=col_major,
+                halos=halos, pads=pads)
+
+
+def make_config(d):
+    c = cd.cudecompGridDescConfig_t()
+    cd.cudecompGridDescConfigSetDefaults(c)
+    c.gdims[:] = d["gdims"]
+    c.pdims[:] = d["pdims"]
+    if d["gdims_dist"]:
+        c.gdims_dist[:] = d["gdims_dist"]
+    c.rank_order = cd.CUDECOMP_RANK_ORDER_COL_MAJOR if d["col_major"] else cd.CUDECOMP_RANK_ORDER_ROW_MAJOR
+    for i in range(3):
+        c.transpose_axis_contiguous[i] = d["axis_contiguous"][i]
+    if d["mem_order"]:
+        for i in range(3):
+            c.transpose_mem_order[i][:] = d["mem_order"][i]
+    return c
+
+
+def make_oracle(d):
+    return orc.Oracle(d["gdims"], d["pdims"], d["axis_contiguous"], d["mem_order"], d["gdims_dist"], d["col_major"])
+
+
+@settings(max_examples=int(__import__("os").environ.get("CDB_HYPOTHESIS_EXAMPLES", "150")), deadline=None, suppress_health_check=list(HealthCheck))
+@given(decompositions())
+def test_transpose_plans_equal_oracle(d):
+    cfg, o = make_config(d), make_oracle(d)
+    n = o.nranks
+    for op, (ax, direction) in OPS.items():
+        a, b = orc.transpose_axes(op)
+        ha, hb, pa, pb = d["halos"][str(a)], d["halos"][str(b)], d["pads"][str(a)], d["pads"][str(b)]
+        if o.has_empty_pencils(a) or o.has_empty_pencils(b):
+            with pytest.raises(cd.CudecompError) as e:
+                cd.plan_transpose_boxes(cfg, 0, ax, direction, ha, hb, pa, pb)
+            assert e.value.code == cd.CUDECOMP_RESULT_NOT_SUPPORTED
+            continue
+        rng = np.random.default_rng(7)
+        ins = [rng.integers(1, 1 << 40, o.pencil_info(r, a, ha, pa).size).astype(np.int64) for r in range(n)]
+        want = [np.full(o.pencil_info(r, b, hb, pb).size, -3, np.int64) for r in range(n)]
+        o.transpose(op, ins, want, ha, hb, pa, pb)
+        for staged in (False, True):
+            plans = [cd.plan_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, staged) for r in range(n)]
+            outs = [np.full(w.size, -3, np.int64) for w in want]
+            works = [np.full(max(o.transpose_workspace_size(), 1), -9, np.int64) for _ in range(n)]
+            simulate_transpose(plans, ins, outs, works, staged)
+            for r in range(n):
+                assert np.array_equal(outs[r], want[r]), (d, op, staged, r)
+
+
+@settings(max_examples=int(__import__("os").environ.get("CDB_HYPOTHESIS_EXAMPLES", "150")), deadline=None, suppress_health_check=list(HealthCheck))
+@given(decompositions(), st.lists(st.integers(0, 3), min_size=3, max_size=3), st.lists(st.booleans(), min_size=3, max_size=3),
+       st.lists(st.integers(0, 2), min_size=3, max_size=3))
+def test_halo_plans_equal_oracle(d, halo, periods, padding):
+    cfg, o = make_config(d), make_oracle(d)
+    n = o.nranks
+    for ax in range(3):
+        if o.has_empty_pencils(ax):
+            if any(halo):
+                with pytest.raises(cd.CudecompError) as e:
+                    cd.plan_halo_boxes(cfg, 0, ax, 0, halo, periods, padding)
+                assert e.value.code == cd.CUDECOMP_RESULT_NOT_SUPPORTED
+            continue
+        rng = np.random.default_rng(11)
+        data = [rng.integers(1, 1 << 40, o.pencil_info(r, ax, halo, padding).size).astype(np.int64) for r in range(n)]
+        for staged in (False, True):
+            mine = [x.copy() for x in data]
+            ref = [x.copy() for x in data]
+            for dim in range(3):
+                try:
+                    o.halo(ax, dim, ref, halo, periods, padding)
+                    oracle_ok = True
+                except RuntimeError:
+                    oracle_ok = False
+                plans, codes = [], set()
+                for r in range(n):
+                    try:
+                        plans.append(cd.plan_halo_boxes(cfg, r, ax, dim, halo, periods, padding, staged))
+                    except cd.CudecompError as e:
+                        codes.add(e.code)
+                        plans.append(None)
+                if not oracle_ok:
+                    # the halo does not fit the thinnest slab: at least the ranks that touch it refuse (the engine then
+                    # refuses on every rank, engine.cc runHalo)
+                    assert codes == {cd.CUDECOMP_RESULT_INVALID_USAGE}, (d, ax, dim, halo)
+                    break
+                assert not codes, (d, ax, dim, codes)
+                works = [np.full(max(o.halo_workspace_size(r, ax, halo), 1), -9, np.int64) for r in range(n)]
+                snap = [x.copy() for x in mine]
+                for r in range(n):
+                    for box in plans[r]:
+                        if not box["is_unpack"]:
+                            apply_box(box, snap[r], (works if staged else mine)[box["peer_rank"]])
+                if staged:
+                    for r in range(n):
+                        for box in plans[r]:
+                            if box["is_unpack"]:
+                                apply_box(box, works[r], mine[r])
+                for r in range(n):
+                    assert np.array_equal(mine[r], ref[r]), (d, ax, dim, staged, r, halo, periods, padding)
