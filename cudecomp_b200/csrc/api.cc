@@ -236,6 +236,7 @@ cudecompResult_t cudecompInit(cudecompHandle_t* handle_in, MPI_Comm mpi_comm) {
     (void)cudaGetLastError();
   }
   h->env_col_major = envFlag("CUDECOMP_USE_COL_MAJOR_RANK_ORDER");
+  h->perf.readEnvironment();
   if (const char* v = std::getenv("CUDECOMP_B200_DIRECT")) h->allow_direct = std::strcmp(v, "0") != 0;
   double spin_s = 60.0;
   if (const char* v = std::getenv("CUDECOMP_B200_DEVICE_TIMEOUT")) spin_s = std::atof(v);
@@ -331,6 +332,8 @@ cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudeco
   }
   setGeometry(gd, {gd->config.pdims[0], gd->config.pdims[1]});
   if (gd->mbox.valid()) gd->mbox.reset(*handle->comm);
+  // samples taken from here on (autotuning trials are not part of the report, reference src/autotune.cc "reset")
+  if (handle->perf.enabled && handle->have_device) gd->perf.reset(new PerfReport(handle->perf));
 
   handle->live_grid_descs++;
   *grid_desc_in = gd;
@@ -346,6 +349,10 @@ cudecompResult_t cudecompGridDescDestroy(cudecompHandle_t handle, cudecompGridDe
   checkHandle(handle);
   checkGridDesc(handle, grid_desc);
   if (handle->have_device) cudaDeviceSynchronize();
+  if (grid_desc->perf) {
+    grid_desc->perf->print(handle, grid_desc); // collective, like the reference (src/cudecomp.cc:1278)
+    grid_desc->perf.reset();
+  }
   destroyGridDescResources(grid_desc, true);
   grid_desc->initialized = false;
   handle->live_grid_descs--;

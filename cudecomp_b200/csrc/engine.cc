@@ -198,6 +198,23 @@ void processReleases(cudecompHandle_t h, const std::vector<int>& group_world, in
     if (static_cast<int>(i) != me) h->peers.noteReleases(group_world[i], msgs[i].release_count, msgs[i].released);
 }
 
+// Ends the current performance sample on every way out of a call (including exceptions).
+struct PerfGuard {
+  PerfSample* sample;
+  cudaStream_t stream;
+  bool exchange = false;
+  ~PerfGuard() { PerfReport::end(sample, exchange, stream); }
+};
+
+bool isManaged(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeManaged;
+}
+
 uint32_t transposeOpcode(int ax, int dir) { return 0x100u + static_cast<uint32_t>(ax) * 4u + (dir > 0 ? 1u : 0u); }
 uint32_t haloOpcode(int ax, int dim) { return 0x200u + static_cast<uint32_t>(ax) * 4u + static_cast<uint32_t>(dim); }
 
@@ -213,6 +230,11 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
   // Geometry and argument errors surface here, before any communication (every rank fails alike).
   TransposePlan probe = buildTransposePlan(gd->geom, gd->pidx, ax, dir, in_halo, out_halo, in_pad, out_pad,
                                            DstKind::FINAL, inplace);
+  PerfGuard perf{nullptr, stream};
+  if (gd->perf && h->have_device)
+    perf.sample = gd->perf->beginTranspose(ax, dir, dtype, in_halo, out_halo, in_pad, out_pad, inplace,
+                                           isManaged(input) || isManaged(output),
+                                           pencilInfo(gd->geom, gd->pidx, probe.axes.a, nullptr, nullptr).size * es, stream);
   if (probe.noop) {
     gd->last_path = CUDECOMP_B200_PATH_NONE;
     return;
@@ -241,6 +263,7 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
     }
     return;
   }
+  perf.exchange = true;
 
   // Tell the other members which buffers this call uses and learn theirs.
   CallMsg mine;
@@ -293,6 +316,7 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
     SyncParams nosync;
     std::memset(&nosync, 0, sizeof(nosync));
     launchBoxes(gd, push, es, sync, stream);
+    PerfReport::markExchangeDone(perf.sample, stream);
     launchBoxes(gd, unpack, es, nosync, stream);
   }
 }
@@ -321,6 +345,11 @@ void runHalo(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, void* input, voi
   }
   requireDevice(h);
   checkDeviceError(gd);
+  PerfGuard perf{nullptr, stream};
+  if (gd->perf)
+    perf.sample = gd->perf->beginHalo(ax, dim, dtype, halo, periods, pad, isManaged(input),
+                                      probe.face_elems * es * ((probe.neighbor[0] >= 0) + (probe.neighbor[1] >= 0)),
+                                      stream);
 
   SyncParams nosync;
   std::memset(&nosync, 0, sizeof(nosync));
@@ -334,6 +363,7 @@ void runHalo(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, void* input, voi
     return;
   }
 
+  perf.exchange = true;
   CallMsg mine;
   std::memset(&mine, 0, sizeof(mine));
   mine.opcode = haloOpcode(ax, dim);
@@ -381,6 +411,7 @@ void runHalo(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, void* input, voi
     }
     for (auto& b : st.unpack) unpack.push_back({b, static_cast<const char*>(work), static_cast<char*>(input)});
     launchBoxes(gd, push, es, sync, stream);
+    PerfReport::markExchangeDone(perf.sample, stream);
     launchBoxes(gd, unpack, es, nosync, stream);
   }
 }

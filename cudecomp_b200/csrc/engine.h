@@ -5,6 +5,7 @@
 
 #include <array>
 #include <cstdint>
+#include <memory>
 #include <set>
 #include <vector>
 
@@ -13,6 +14,7 @@
 #include "geometry.h"
 #include "kernels.h"
 #include "peer.h"
+#include "perf_report.h"
 #include "plan.h"
 
 // Which way the last operation on a grid descriptor moved its data (cudecompB200GetLastPath).
@@ -41,6 +43,7 @@ struct cudecompHandle {
   cdb::SignalArena arena;        // device flag pages, one slot per grid descriptor (created with the first one)
   std::vector<int> free_slots;   // recycled slots (create/destroy are collective, so all ranks agree)
   int next_slot = 0;
+  cdb::PerfSettings perf;        // CUDECOMP_ENABLE_PERFORMANCE_REPORT and friends
   uint64_t release_count = 0;    // buffers freed through cudecompFree so far
   uint64_t released[cdb::kReleaseSlots] = {0}; // ids of the most recent ones, newest first
 };
@@ -61,6 +64,7 @@ struct cudecompGridDesc {
   int grid_ctas = 0;       // 0: all resident CTAs
   bool force_staged = false;
   int last_path = CUDECOMP_B200_PATH_NONE;
+  std::unique_ptr<cdb::PerfReport> perf; // only when the performance report is enabled
 };
 
 namespace cdb {
