@@ -138,7 +138,7 @@ API_SYMBOLS = [
 ]
 EXT_SYMBOLS = ["cudecompB200GetLaunchCount", "cudecompB200GetLastPath", "cudecompB200SetTuning",
                "cudecompB200CheckErrors", "cudecompB200DescribeTransposeBoxes", "cudecompB200DescribeHaloBoxes",
-               "cudecompB200PlanTransposeBoxes", "cudecompB200PlanHaloBoxes"]
+               "cudecompB200PlanTransposeBoxes", "cudecompB200PlanHaloBoxes", "cudecompB200SelfTestMailbox"]
 MPI_SHIM_SYMBOLS = ["MPI_Init", "MPI_Init_thread", "MPI_Initialized", "MPI_Finalize", "MPI_Finalized", "MPI_Abort",
                     "MPI_Wtime", "MPI_Get_processor_name", "MPI_Error_string", "MPI_Comm_rank", "MPI_Comm_size",
                     "MPI_Comm_split", "MPI_Comm_split_type", "MPI_Comm_dup", "MPI_Comm_free", "MPI_Comm_c2f",
@@ -199,6 +199,7 @@ _sig("cudecompB200PlanTransposeBoxes", _i32,
      [_P(cudecompGridDescConfig_t), _i32, _i32, _i32, _i32p, _i32p, _i32p, _i32p, _i32, _P(cudecompB200Box_t), _i32])
 _sig("cudecompB200PlanHaloBoxes", _i32,
      [_P(cudecompGridDescConfig_t), _i32, _i32, _i32, _i32p, _P(ctypes.c_bool), _i32p, _i32, _P(cudecompB200Box_t), _i32])
+_sig("cudecompB200SelfTestMailbox", ctypes.c_int, [cudecompHandle_t, _i32, ctypes.c_uint32])
 _sig("MPI_Init", ctypes.c_int, [_vp, _vp])
 _sig("MPI_Finalize", ctypes.c_int, [])
 _sig("MPI_Comm_rank", ctypes.c_int, [ctypes.c_int, _P(ctypes.c_int)])

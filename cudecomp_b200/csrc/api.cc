@@ -11,6 +11,8 @@
 #include <iostream>
 #include <set>
 
+#include <unistd.h>
+
 #include "cudecomp.h"
 #include "cudecomp_b200_ext.h"
 #include "engine.h"
@@ -615,6 +617,63 @@ cudecompResult_t cudecompB200CheckErrors(cudecompHandle_t handle, cudecompGridDe
   checkHandle(handle);
   checkGridDesc(handle, grid_desc);
   checkDeviceError(grid_desc);
+  API_CATCH()
+}
+
+cudecompResult_t cudecompB200SelfTestMailbox(cudecompHandle_t handle, int32_t iterations, uint32_t seed) {
+  API_TRY
+  checkHandle(handle);
+  const int n = handle->nranks, me = handle->rank;
+  if (n == 1) return CUDECOMP_RESULT_SUCCESS;
+  Mailbox box;
+  box.create(*handle->comm, handle->token ^ 0x5e1f7e57ull, 1000000 + handle->next_instance++);
+  // Group shapes as the engine uses them: channel 0 = "column" groups {r : r % cols == me % cols},
+  // channel 1 = "row" groups {r : r / cols == me / cols}, for a process grid that changes every few iterations.
+  uint32_t lcg = seed * 2654435761u + 12345u;
+  auto rnd = [&]() { return lcg = lcg * 1664525u + 1013904223u; };
+  uint32_t my_lcg = (seed + 17u * static_cast<uint32_t>(me)) * 2246822519u + 1u;
+  std::vector<int> divisors;
+  for (int d = 1; d <= n; ++d)
+    if (n % d == 0) divisors.push_back(d);
+  int cols = 1;
+  for (int it = 0; it < iterations; ++it) {
+    // The process grid (and with it the membership of the row/column groups) only changes together with a reset,
+    // exactly as in autotuning; between resets every member of a group issues the same sequence of exchanges.
+    if (it % 7 == 0) {
+      box.reset(*handle->comm);
+      cols = divisors[rnd() % divisors.size()]; // same on every rank
+    }
+    const int channel = static_cast<int>(rnd() % 2);
+    std::vector<int> members;
+    int my_index = -1;
+    for (int r = 0; r < n; ++r) {
+      const bool in = (channel == 0) ? (r % cols == me % cols) : (r / cols == me / cols);
+      if (in) {
+        if (r == me) my_index = static_cast<int>(members.size());
+        members.push_back(r);
+      }
+    }
+    if (members.size() < 2) continue;
+    my_lcg = my_lcg * 1664525u + 1013904223u;
+    if ((my_lcg >> 28) == 0) usleep((my_lcg >> 8) % 300); // desynchronise the ranks a little
+    CallMsg mine;
+    std::memset(&mine, 0, sizeof(mine));
+    mine.opcode = 0x700u + static_cast<uint32_t>(channel);
+    mine.flags = static_cast<uint32_t>(it);
+    mine.data.offset = static_cast<uint64_t>(me) * 1000003ull + static_cast<uint64_t>(it);
+    mine.release_count = static_cast<uint64_t>(it) ^ 0xabcdu;
+    std::vector<CallMsg> got;
+    box.exchange(channel, members, my_index, mine, got);
+    for (size_t i = 0; i < members.size(); ++i) {
+      const uint64_t want = static_cast<uint64_t>(members[i]) * 1000003ull + static_cast<uint64_t>(it);
+      if (got[i].flags != static_cast<uint32_t>(it) || got[i].data.offset != want ||
+          got[i].release_count != (static_cast<uint64_t>(it) ^ 0xabcdu))
+        THROW_INTERNAL_ERROR("mailbox self test: wrong message from rank " + std::to_string(members[i]) + " at iteration " +
+                             std::to_string(it));
+    }
+  }
+  barrier(*handle->comm);
+  box.destroy();
   API_CATCH()
 }
 

@@ -59,6 +59,11 @@ int32_t cudecompB200PlanHaloBoxes(const cudecompGridDescConfig_t* config, int32_
                                   const int32_t halo_extents[], const bool halo_periods[], const int32_t padding[],
                                   int32_t staged, cudecompB200Box_t* boxes, int32_t max_boxes);
 
+/* Host-only self test of the shared-memory descriptor mailbox (collective over the handle's communicator, no GPU
+ * needed): `iterations` exchanges on alternating channels with rank groups of varying shape and randomised delays;
+ * every received message is checked. Returns CUDECOMP_RESULT_SUCCESS or INTERNAL_ERROR. */
+cudecompResult_t cudecompB200SelfTestMailbox(cudecompHandle_t handle, int32_t iterations, uint32_t seed);
+
 #ifdef __cplusplus
 }
 #endif

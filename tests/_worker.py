@@ -411,6 +411,10 @@ def shim_battery(rank, nranks):
     return out
 
 
+def mailbox_selftest(handle, case):
+    return dict(ok=cd.lib.cudecompB200SelfTestMailbox(handle, case.get("iterations", 2000), case.get("seed", 1)) == 0)
+
+
 def main():
     payload_path, out_dir = sys.argv[1], sys.argv[2]
     with open(payload_path) as f:
@@ -429,6 +433,8 @@ def main():
         try:
             if payload["mode"] == "shim":
                 results.append(shim_battery(rank, int(os.environ["WORLD_SIZE"])))
+            elif payload["mode"] == "mailbox":
+                results.append(mailbox_selftest(handle, case))
             elif payload["mode"] == "plan":
                 results.append(plan_case(handle, rank, case))
             elif case["kind"] == "halo":

@@ -202,3 +202,13 @@ def test_mpi_shim_collectives_on_4_ranks():
         assert out["wtime_positive"]
     assert results[0][0]["gather_root0"] == [100, 101, 102, 103]
     assert results[0][0]["reduce_max_root0"] == 9
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 6, 8])
+def test_descriptor_mailbox_stress(nranks):
+    """The shared-memory mailbox every multi-rank operation relies on: thousands of exchanges on both channels with
+    changing row/column group shapes, resets and randomised rank delays; every message is verified in the library."""
+    results, _ = run_ranks(nranks, "mailbox", [dict(name="stress", iterations=4000, seed=s) for s in (1, 2, 3)],
+                           timeout=300)
+    for r in range(nranks):
+        assert all(c["ok"] for c in results[r]), results[r]
