@@ -80,6 +80,7 @@ __device__ __forceinline__ void syncExit(const SyncParams& s) {
   __syncthreads();
   if (!is_last) return;
   __threadfence_system(); // order the other CTAs' (already fenced) stores before the flags below
+  __syncthreads();        // ... for every flag-writing thread: thread 0 observed the counter, its fence precedes all flags
   const int t = threadIdx.x;
   if (t < s.npeers) {
     stReleaseSys(s.peer_pad[t] + kPadExit + s.my_world, s.epoch);
