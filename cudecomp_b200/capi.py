@@ -114,7 +114,8 @@ class cudecompPencilInfo_t(ctypes.Structure):
 
 
 class cudecompB200Box_t(ctypes.Structure):
-    _fields_ = [("peer_rank", _i32), ("is_unpack", _i32), ("src_offset", _i64), ("dst_offset", _i64),
+    _fields_ = [("peer_rank", _i32), ("is_unpack", _i32), ("step", _i32), ("reserved", _i32),
+                ("src_offset", _i64), ("dst_offset", _i64),
                 ("extent", _i64 * 3), ("src_stride", _i64 * 3), ("dst_stride", _i64 * 3)]
 
 
@@ -137,8 +138,9 @@ API_SYMBOLS = [
     "cudecompUpdateHalosZ",
 ]
 EXT_SYMBOLS = ["cudecompB200GetLaunchCount", "cudecompB200GetLastPath", "cudecompB200SetTuning",
-               "cudecompB200CheckErrors", "cudecompB200DescribeTransposeBoxes", "cudecompB200DescribeHaloBoxes",
-               "cudecompB200PlanTransposeBoxes", "cudecompB200PlanHaloBoxes", "cudecompB200SelfTestMailbox"]
+               "cudecompB200CheckErrors", "cudecompB200SetPipelineChunks", "cudecompB200DescribeTransposeBoxes", "cudecompB200DescribeHaloBoxes",
+               "cudecompB200PlanTransposeBoxes", "cudecompB200PlanHaloBoxes", "cudecompB200PlanPipelinedTransposeBoxes",
+               "cudecompB200SelfTestMailbox"]
 MPI_SHIM_SYMBOLS = ["MPI_Init", "MPI_Init_thread", "MPI_Initialized", "MPI_Finalize", "MPI_Finalized", "MPI_Abort",
                     "MPI_Wtime", "MPI_Get_processor_name", "MPI_Error_string", "MPI_Comm_rank", "MPI_Comm_size",
                     "MPI_Comm_split", "MPI_Comm_split_type", "MPI_Comm_dup", "MPI_Comm_free", "MPI_Comm_c2f",
@@ -190,6 +192,7 @@ _sig("cudecompB200GetLaunchCount", ctypes.c_int, [_P(ctypes.c_uint64)])
 _sig("cudecompB200GetLastPath", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32p])
 _sig("cudecompB200SetTuning", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32, _i32])
 _sig("cudecompB200CheckErrors", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t])
+_sig("cudecompB200SetPipelineChunks", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32])
 _sig("cudecompB200DescribeTransposeBoxes", _i32,
      [cudecompHandle_t, cudecompGridDesc_t, _i32, _i32, _i32p, _i32p, _i32p, _i32p, _i32, _P(cudecompB200Box_t), _i32])
 _sig("cudecompB200DescribeHaloBoxes", _i32,
@@ -199,6 +202,8 @@ _sig("cudecompB200PlanTransposeBoxes", _i32,
      [_P(cudecompGridDescConfig_t), _i32, _i32, _i32, _i32p, _i32p, _i32p, _i32p, _i32, _P(cudecompB200Box_t), _i32])
 _sig("cudecompB200PlanHaloBoxes", _i32,
      [_P(cudecompGridDescConfig_t), _i32, _i32, _i32, _i32p, _P(ctypes.c_bool), _i32p, _i32, _P(cudecompB200Box_t), _i32])
+_sig("cudecompB200PlanPipelinedTransposeBoxes", _i32,
+     [_P(cudecompGridDescConfig_t), _i32, _i32, _i32, _i32p, _i32p, _i32p, _i32p, _i32, _i32, _P(cudecompB200Box_t), _i32])
 _sig("cudecompB200SelfTestMailbox", ctypes.c_int, [cudecompHandle_t, _i32, ctypes.c_uint32])
 _sig("MPI_Init", ctypes.c_int, [_vp, _vp])
 _sig("MPI_Finalize", ctypes.c_int, [])
@@ -437,6 +442,10 @@ def set_tuning(handle, grid_desc, grid_ctas=0, force_staged=False):
     return lib.cudecompB200SetTuning(handle, grid_desc, int(grid_ctas), 1 if force_staged else 0)
 
 
+def set_pipeline_chunks(handle, grid_desc, nchunks):
+    return lib.cudecompB200SetPipelineChunks(handle, grid_desc, int(nchunks))
+
+
 def check_errors(handle, grid_desc):
     return lib.cudecompB200CheckErrors(handle, grid_desc)
 
@@ -445,7 +454,7 @@ def _boxes(n, arr):
     out = []
     for i in range(n):
         b = arr[i]
-        out.append(dict(peer_rank=b.peer_rank, is_unpack=bool(b.is_unpack), src_offset=b.src_offset,
+        out.append(dict(peer_rank=b.peer_rank, is_unpack=bool(b.is_unpack), step=b.step, src_offset=b.src_offset,
                         dst_offset=b.dst_offset, extent=tuple(b.extent), src_stride=tuple(b.src_stride),
                         dst_stride=tuple(b.dst_stride)))
     return out
@@ -490,4 +499,19 @@ def plan_halo_boxes(config, rank, ax, dim, halo_extents, halo_periods=None, padd
                                       _arr3(padding), 1 if staged else 0, arr, max_boxes)
     if n < 0:
         raise CudecompError(-n, "cudecompB200PlanHaloBoxes")
+    return _boxes(n, arr)
+
+
+def plan_pipelined_transpose_boxes(config, rank, ax, direction, input_halo_extents=None, output_halo_extents=None,
+                                   input_padding=None, output_padding=None, inplace=False, nchunks=4, max_boxes=1024):
+    """Chunked staged schedule (boxes carry their step). Empty list when chunking does not apply."""
+    arr = (cudecompB200Box_t * max_boxes)()
+    n = lib.cudecompB200PlanPipelinedTransposeBoxes(ctypes.byref(config), rank, ax, direction,
+                                                    _arr3(input_halo_extents), _arr3(output_halo_extents),
+                                                    _arr3(input_padding), _arr3(output_padding), 1 if inplace else 0,
+                                                    nchunks, arr, max_boxes)
+    if n < 0:
+        raise CudecompError(-n, "cudecompB200PlanPipelinedTransposeBoxes")
+    if n > max_boxes:
+        raise ValueError("plan has %d boxes, buffer holds %d" % (n, max_boxes))
     return _boxes(n, arr)

@@ -189,6 +189,11 @@ void destroyGridDescResources(cudecompGridDesc_t gd, bool collective) {
     gd->pad_slot = -1;
   }
   gd->mbox.destroy();
+  for (cudaEvent_t e : gd->side_events) cudaEventDestroy(e);
+  gd->side_events.clear();
+  if (gd->side_stream) cudaStreamDestroy(gd->side_stream);
+  gd->side_stream = nullptr;
+  (void)cudaGetLastError();
 }
 
 } // namespace
@@ -239,6 +244,7 @@ cudecompResult_t cudecompInit(cudecompHandle_t* handle_in, MPI_Comm mpi_comm) {
   }
   h->env_col_major = envFlag("CUDECOMP_USE_COL_MAJOR_RANK_ORDER");
   h->perf.readEnvironment();
+  if (const char* v = std::getenv("CUDECOMP_B200_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(0, std::atoi(v));
   if (const char* v = std::getenv("CUDECOMP_B200_DIRECT")) h->allow_direct = std::strcmp(v, "0") != 0;
   double spin_s = 60.0;
   if (const char* v = std::getenv("CUDECOMP_B200_DEVICE_TIMEOUT")) spin_s = std::atof(v);
@@ -297,6 +303,7 @@ cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudeco
   gd->initialized = true;
   gd->handle = handle;
   gd->config = *config;
+  gd->pipeline_chunks = handle->pipeline_chunks;
   if (gd->config.rank_order == CUDECOMP_RANK_ORDER_DEFAULT)
     gd->config.rank_order = handle->env_col_major ? CUDECOMP_RANK_ORDER_COL_MAJOR : CUDECOMP_RANK_ORDER_ROW_MAJOR;
 
@@ -612,6 +619,15 @@ cudecompResult_t cudecompB200SetTuning(cudecompHandle_t handle, cudecompGridDesc
   API_CATCH()
 }
 
+cudecompResult_t cudecompB200SetPipelineChunks(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t nchunks) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (nchunks < 0 || nchunks > 64) THROW_INVALID_USAGE("nchunks must be in [0, 64]");
+  grid_desc->pipeline_chunks = nchunks; // must be set to the same value on every rank
+  API_CATCH()
+}
+
 cudecompResult_t cudecompB200CheckErrors(cudecompHandle_t handle, cudecompGridDesc_t grid_desc) {
   API_TRY
   checkHandle(handle);
@@ -686,6 +702,8 @@ static int32_t emitBoxes(const std::vector<BoxDesc>& push, const std::vector<Box
     cudecompB200Box_t& o = boxes[n];
     o.peer_rank = all[i].peer_world;
     o.is_unpack = (i >= push.size()) ? 1 : 0;
+    o.step = 0;
+    o.reserved = 0;
     o.src_offset = all[i].src_off;
     o.dst_offset = all[i].dst_off;
     for (int k = 0; k < 3; ++k) {
@@ -725,6 +743,47 @@ int32_t cudecompB200PlanTransposeBoxes(const cudecompGridDescConfig_t* config, i
     TransposePlan plan = buildTransposePlan(g, pidxOfRank(g, rank), ax, dir, input_halo_extents, output_halo_extents,
                                             input_padding, output_padding, staged ? DstKind::STAGE : DstKind::FINAL, false);
     return emitBoxes(plan.push, plan.unpack, boxes, max_boxes);
+  } catch (const cdb::Error& e) {
+    return -static_cast<int32_t>(e.code());
+  } catch (const std::exception&) {
+    return -static_cast<int32_t>(CUDECOMP_RESULT_INTERNAL_ERROR);
+  }
+}
+
+int32_t cudecompB200PlanPipelinedTransposeBoxes(const cudecompGridDescConfig_t* config, int32_t rank, int32_t ax,
+                                                int32_t dir, const int32_t input_halo_extents[],
+                                                const int32_t output_halo_extents[], const int32_t input_padding[],
+                                                const int32_t output_padding[], int32_t inplace, int32_t nchunks,
+                                                cudecompB200Box_t* boxes, int32_t max_boxes) {
+  try {
+    GridGeom g = geomFromConfig(config);
+    if (rank < 0 || rank >= g.pdims[0] * g.pdims[1]) THROW_INVALID_USAGE("rank out of range");
+    PipelinedPlan pp = buildPipelinedTransposePlan(g, pidxOfRank(g, rank), ax, dir, input_halo_extents,
+                                                   output_halo_extents, input_padding, output_padding, inplace != 0,
+                                                   nchunks);
+    int32_t n = 0, total = 0;
+    for (size_t s = 0; s < pp.steps.size(); ++s) {
+      for (int pass = 0; pass < 2; ++pass) {
+        const auto& list = pass == 0 ? pp.steps[s].push : pp.steps[s].unpack;
+        for (const BoxDesc& bx : list) {
+          ++total;
+          if (n >= max_boxes) continue;
+          cudecompB200Box_t& o = boxes[n++];
+          o.peer_rank = bx.peer_world;
+          o.is_unpack = pass;
+          o.step = static_cast<int32_t>(s);
+          o.reserved = 0;
+          o.src_offset = bx.src_off;
+          o.dst_offset = bx.dst_off;
+          for (int k = 0; k < 3; ++k) {
+            o.extent[k] = bx.ext[k];
+            o.src_stride[k] = bx.sstr[k];
+            o.dst_stride[k] = bx.dstr[k];
+          }
+        }
+      }
+    }
+    return total;
   } catch (const cdb::Error& e) {
     return -static_cast<int32_t>(e.code());
   } catch (const std::exception&) {

@@ -218,6 +218,57 @@ bool isManaged(const void* p) {
 uint32_t transposeOpcode(int ax, int dir) { return 0x100u + static_cast<uint32_t>(ax) * 4u + (dir > 0 ? 1u : 0u); }
 uint32_t haloOpcode(int ax, int dim) { return 0x200u + static_cast<uint32_t>(ax) * 4u + static_cast<uint32_t>(dim); }
 
+// Chunked schedule of the staged path (plan.h PipelinedPlan): K push launches on the caller's stream, each with its
+// own handshake epoch; the unpack pieces that become writable after push s run on a side stream beside push s+1.
+// The caller's stream rejoins the side stream at the end, so stream semantics are unchanged. Returns false when
+// chunking does not apply (the caller then runs the unchunked schedule). Every rank of the job takes the same
+// decision and advances the epoch by the same amount: it only depends on the geometry and on K.
+bool runPipelinedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, void* input, void* output, void* work,
+                        int es, const int32_t in_halo[], const int32_t out_halo[], const int32_t in_pad[],
+                        const int32_t out_pad[], bool inplace, const std::vector<CallMsg>& msgs,
+                        const std::vector<int>& peers, PerfSample* perf, cudaStream_t stream) {
+  PipelinedPlan pp = buildPipelinedTransposePlan(gd->geom, gd->pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, inplace,
+                                                 gd->pipeline_chunks);
+  if (pp.steps.empty()) return false;
+  const size_t K = pp.steps.size();
+  if (!gd->side_stream) {
+    int lo = 0, hi = 0;
+    CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CHECK_CUDA(cudaStreamCreateWithPriority(&gd->side_stream, cudaStreamNonBlocking, hi));
+  }
+  while (gd->side_events.size() < K + 1) {
+    cudaEvent_t e;
+    CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    gd->side_events.push_back(e);
+  }
+  SyncParams nosync;
+  std::memset(&nosync, 0, sizeof(nosync));
+  bool used_side = false;
+  for (size_t s = 0; s < K; ++s) {
+    if (s > 0) gd->epoch++; // the first step uses the epoch the call was given
+    const SyncParams sync = makeSync(gd, peers);
+    std::vector<ResolvedBox> push, unpack;
+    for (auto& b : pp.steps[s].push) {
+      char* dst = (b.peer == pp.base.me) ? static_cast<char*>(work)
+                                         : static_cast<char*>(h->peers.resolve(b.peer_world, msgs[b.peer].work));
+      push.push_back({b, static_cast<const char*>(input), dst});
+    }
+    launchBoxes(gd, push, es, sync, stream);
+    if (s + 1 == K) PerfReport::markExchangeDone(perf, stream);
+    if (pp.steps[s].unpack.empty()) continue;
+    for (auto& b : pp.steps[s].unpack) unpack.push_back({b, static_cast<const char*>(work), static_cast<char*>(output)});
+    CHECK_CUDA(cudaEventRecord(gd->side_events[s], stream));
+    CHECK_CUDA(cudaStreamWaitEvent(gd->side_stream, gd->side_events[s], 0));
+    launchBoxes(gd, unpack, es, nosync, gd->side_stream);
+    used_side = true;
+  }
+  if (used_side) {
+    CHECK_CUDA(cudaEventRecord(gd->side_events[K], gd->side_stream));
+    CHECK_CUDA(cudaStreamWaitEvent(stream, gd->side_events[K], 0));
+  }
+  return true;
+}
+
 } // namespace
 
 void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, void* input, void* output, void* work,
@@ -304,6 +355,10 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
     launchBoxes(gd, boxes, es, sync, stream);
   } else {
     gd->last_path = CUDECOMP_B200_PATH_STAGED;
+    if (gd->pipeline_chunks > 1 &&
+        runPipelinedStaged(h, gd, ax, dir, input, output, work, es, in_halo, out_halo, in_pad, out_pad, inplace, msgs,
+                           peers, perf.sample, stream))
+      return;
     TransposePlan st = buildTransposePlan(gd->geom, gd->pidx, ax, dir, in_halo, out_halo, in_pad, out_pad,
                                           DstKind::STAGE, inplace);
     std::vector<ResolvedBox> push, unpack;

@@ -44,6 +44,7 @@ struct cudecompHandle {
   std::vector<int> free_slots;   // recycled slots (create/destroy are collective, so all ranks agree)
   int next_slot = 0;
   cdb::PerfSettings perf;        // CUDECOMP_ENABLE_PERFORMANCE_REPORT and friends
+  int pipeline_chunks = 0;       // CUDECOMP_B200_PIPELINE_CHUNKS: chunked schedule of staged transposes (0/1 = off)
   uint64_t release_count = 0;    // buffers freed through cudecompFree so far
   uint64_t released[cdb::kReleaseSlots] = {0}; // ids of the most recent ones, newest first
 };
@@ -65,6 +66,10 @@ struct cudecompGridDesc {
   bool force_staged = false;
   int last_path = CUDECOMP_B200_PATH_NONE;
   std::unique_ptr<cdb::PerfReport> perf; // only when the performance report is enabled
+  // chunked (pipelined) staged schedule: unpack kernels run on a side stream beside the next chunk's push
+  int pipeline_chunks = 0;
+  cudaStream_t side_stream = nullptr;
+  std::vector<cudaEvent_t> side_events;
 };
 
 namespace cdb {

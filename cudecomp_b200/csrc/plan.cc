@@ -107,6 +107,118 @@ TransposePlan buildTransposePlan(const GridGeom& g, const std::array<int, 2>& pi
   return plan;
 }
 
+namespace {
+// chunk k of [0, n) cut into K parts
+inline std::pair<int64_t, int64_t> chunkRange(int64_t n, int K, int k) { return {k * n / K, (k + 1) * n / K}; }
+} // namespace
+
+PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dir,
+                                          const int32_t in_halo[3], const int32_t out_halo[3], const int32_t in_pad[3],
+                                          const int32_t out_pad[3], bool inplace, int nchunks) {
+  PipelinedPlan pp;
+  pp.base = buildTransposePlan(g, pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, DstKind::STAGE, inplace);
+  if (pp.base.noop || nchunks <= 1 || pp.base.push.empty()) return pp;
+  const int K = nchunks;
+  const int a = pp.base.axes.a, b = pp.base.axes.b;
+  const int P = pp.base.comm_size, me = pp.base.me;
+
+  const Pencil pa = pencilInfo(g, pidx, a, nullptr, nullptr);
+  const Pencil pa_h = pencilInfo(g, pidx, a, in_halo, in_pad);
+  const Pencil pb = pencilInfo(g, pidx, b, nullptr, nullptr);
+  const Pencil pb_h = pencilInfo(g, pidx, b, out_halo, out_pad);
+  const int G = pa.order[2]; // slowest axis of the source: chunks are ranges of source planes
+  pp.chunk_axis = G;
+  const auto splits_a = getSplits(g.gdims_dist[a], P, g.gdims[a] - g.gdims_dist[a]);
+  const auto splits_b = getSplits(g.gdims_dist[b], P, g.gdims[b] - g.gdims_dist[b]);
+  const auto off_a = prefixOffsets(splits_a);
+  const auto off_b = prefixOffsets(splits_b);
+  const auto shape_a = pa.shapeG();
+  const auto shape_b = pb.shapeG();
+  const auto in_str = pa_h.strideG();
+  pp.steps.resize(K);
+
+  // ---- push: every box cut by my chunks of the source planes
+  const int64_t nG_me = shape_a[G];
+  for (const BoxDesc& box : pp.base.push) {
+    const int64_t start = (G == a) ? off_a[box.peer] : 0; // where the box begins along G in my pencil
+    const int64_t len = box.ext[G];
+    for (int k = 0; k < K; ++k) {
+      auto [c0, c1] = chunkRange(nG_me, K, k);
+      const int64_t lo = std::max(c0, start), hi = std::min(c1, start + len);
+      if (hi <= lo) continue;
+      BoxDesc sub = box;
+      sub.ext[G] = hi - lo;
+      sub.src_off += (lo - start) * box.sstr[G];
+      sub.dst_off += (lo - start) * box.dstr[G];
+      pp.steps[k].push.push_back(sub);
+    }
+  }
+
+  // ---- unpack: what source j's chunk k leaves in my workspace, and the first step at which its destination is free
+  const auto dense = pb.strideG();
+  const auto out_str = pb_h.strideG();
+  for (int j = 0; j < P; ++j) {
+    // extent of rank j's source pencil along G, and the part of it that travels to me
+    int64_t nG_j, startj, lenj;
+    if (G == a) {
+      nG_j = g.gdims[a];
+      startj = off_a[me];
+      lenj = splits_a[me];
+    } else if (G == b) {
+      nG_j = splits_b[j];
+      startj = 0;
+      lenj = splits_b[j];
+    } else {
+      nG_j = shape_a[G];
+      startj = 0;
+      lenj = shape_a[G];
+    }
+    for (int k = 0; k < K; ++k) {
+      auto [c0, c1] = chunkRange(nG_j, K, k);
+      const int64_t u0 = std::max(c0, startj), u1 = std::min(c1, startj + lenj);
+      if (u1 <= u0) continue;
+      // the piece in the coordinates of my (dense) destination pencil
+      std::array<int64_t, 3> s0{}, ext{};
+      for (int d = 0; d < 3; ++d) {
+        s0[d] = 0;
+        ext[d] = shape_b[d];
+      }
+      s0[b] = off_b[j];
+      ext[b] = splits_b[j];
+      if (G == a) {
+        s0[G] = u0 - off_a[me];
+      } else if (G == b) {
+        s0[G] = off_b[j] + u0;
+      } else {
+        s0[G] = u0;
+      }
+      ext[G] = u1 - u0;
+      BoxDesc piece;
+      piece.peer = me;
+      piece.peer_world = pp.base.group_world[me];
+      piece.ext = ext;
+      piece.sstr = dense;
+      piece.dstr = out_str;
+      piece.src_off = dot3(s0, dense);
+      std::array<int64_t, 3> d0{s0[0] + pb_h.halo[0], s0[1] + pb_h.halo[1], s0[2] + pb_h.halo[2]};
+      piece.dst_off = dot3(d0, out_str);
+      if (piece.count() == 0) continue;
+
+      int step = k;
+      if (inplace) {
+        // last element this piece writes, against the first source plane no push has read yet
+        const int64_t last = piece.dst_off + (ext[0] - 1) * out_str[0] + (ext[1] - 1) * out_str[1] + (ext[2] - 1) * out_str[2];
+        for (step = k; step < K - 1; ++step) {
+          const int64_t first_unread = (chunkRange(nG_me, K, step + 1).first + pa_h.halo[G]) * in_str[G];
+          if (last < first_unread) break;
+        }
+      }
+      pp.steps[step].unpack.push_back(piece);
+    }
+  }
+  return pp;
+}
+
 HaloPlan buildHaloPlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dim, const int32_t halo[3],
                        const bool periods[3], const int32_t pad[3], DstKind kind) {
   HaloPlan plan;

@@ -55,6 +55,24 @@ TransposePlan buildTransposePlan(const GridGeom& g, const std::array<int, 2>& pi
                                  const int32_t in_halo[3], const int32_t out_halo[3], const int32_t in_pad[3],
                                  const int32_t out_pad[3], DstKind kind, bool inplace);
 
+// Chunked schedule of a staged transpose: the pencil is cut into K chunks along the slowest axis of the SOURCE memory
+// order; step s pushes chunk s to every peer's workspace and, once that has landed, unpacks every piece whose
+// destination memory is free by then. In place, "free" means the push has already consumed the source planes the piece
+// overwrites (pieces that land beyond the consumed prefix wait for a later step); out of place a piece is unpacked in the
+// step it arrives. Consecutive steps overlap on the device: unpack(s) runs beside push(s+1).
+struct PipelineStep {
+  std::vector<BoxDesc> push;   // sub-boxes of TransposePlan::push restricted to chunk s
+  std::vector<BoxDesc> unpack; // pieces of the dense pencil in my workspace -> output that become writable in step s
+};
+struct PipelinedPlan {
+  TransposePlan base;              // the unchunked staged plan (geometry, group, noop)
+  int chunk_axis = -1;             // global axis the chunks run along
+  std::vector<PipelineStep> steps; // empty: not applicable, run `base` as is
+};
+PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dir,
+                                          const int32_t in_halo[3], const int32_t out_halo[3], const int32_t in_pad[3],
+                                          const int32_t out_pad[3], bool inplace, int nchunks);
+
 struct HaloPlan {
   bool nothing = false; // zero halo width, or no neighbour in this dimension
   CommAxis comm = COMM_COL;

@@ -15,6 +15,8 @@ extern "C" {
 typedef struct {
   int32_t peer_rank;  /* global rank that owns the destination */
   int32_t is_unpack;  /* 1: local workspace -> destination buffer copy of the staged path */
+  int32_t step;       /* step of a chunked (pipelined) schedule, 0 otherwise */
+  int32_t reserved;
   int64_t src_offset; /* first element in the source buffer */
   int64_t dst_offset; /* first element in the destination buffer (of peer_rank) */
   int64_t extent[3];
@@ -31,6 +33,12 @@ cudecompResult_t cudecompB200GetLastPath(cudecompHandle_t handle, cudecompGridDe
 /* grid_ctas: CTAs per launch (0 = all resident CTAs); force_staged != 0 routes every exchange through the workspace. */
 cudecompResult_t cudecompB200SetTuning(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t grid_ctas,
                                        int32_t force_staged);
+
+/* Chunked schedule of staged transposes (in-place calls, NVSHMEM-family backends, non-exportable outputs): the pencil
+ * is pushed in `nchunks` chunks and unpacking overlaps the next chunk's push (csrc/plan.h PipelinedPlan). 0 or 1 = off
+ * (default; also settable for all descriptors with CUDECOMP_B200_PIPELINE_CHUNKS). Same value on every rank.
+ * EXPERIMENTAL in round 1: the schedule is property-tested on the host, its device execution is not yet validated. */
+cudecompResult_t cudecompB200SetPipelineChunks(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t nchunks);
 
 /* Reports (and clears) a device-side handshake timeout of an earlier operation. */
 cudecompResult_t cudecompB200CheckErrors(cudecompHandle_t handle, cudecompGridDesc_t grid_desc);
@@ -58,6 +66,14 @@ int32_t cudecompB200PlanTransposeBoxes(const cudecompGridDescConfig_t* config, i
 int32_t cudecompB200PlanHaloBoxes(const cudecompGridDescConfig_t* config, int32_t rank, int32_t ax, int32_t dim,
                                   const int32_t halo_extents[], const bool halo_periods[], const int32_t padding[],
                                   int32_t staged, cudecompB200Box_t* boxes, int32_t max_boxes);
+
+/* The chunked (pipelined) variant of the staged schedule for `nchunks` chunks (csrc/plan.h PipelinedPlan): boxes carry
+ * the step they run in. Returns 0 boxes when chunking does not apply. */
+int32_t cudecompB200PlanPipelinedTransposeBoxes(const cudecompGridDescConfig_t* config, int32_t rank, int32_t ax,
+                                                int32_t dir, const int32_t input_halo_extents[],
+                                                const int32_t output_halo_extents[], const int32_t input_padding[],
+                                                const int32_t output_padding[], int32_t inplace, int32_t nchunks,
+                                                cudecompB200Box_t* boxes, int32_t max_boxes);
 
 /* Host-only self test of the shared-memory descriptor mailbox (collective over the handle's communicator, no GPU
  * needed): `iterations` exchanges on alternating channels with rank groups of varying shape and randomised delays;

@@ -112,6 +112,8 @@ def transpose_case(gpu, handle, rank, case):
             cd.check(cd.set_tuning(handle, gd, 0, True))
         if case.get("grid_ctas"):
             cd.check(cd.set_tuning(handle, gd, case["grid_ctas"], bool(case.get("force_staged"))))
+        if case.get("pipeline_chunks"):
+            cd.check(cd.set_pipeline_chunks(handle, gd, case["pipeline_chunks"]))
 
         def h(ax):
             return halos.get(str(ax))

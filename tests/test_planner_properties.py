@@ -139,3 +139,76 @@ def test_halo_plans_equal_oracle(d, halo, periods, padding):
                                 apply_box(box, works[r], mine[r])
                 for r in range(n):
                     assert np.array_equal(mine[r], ref[r]), (d, ax, dim, staged, r, halo, periods, padding)
+
+
+# ----------------------------------------------------------------------------------- chunked (pipelined) schedule
+def _box_cells(box, which):
+    idx = np.indices(box["extent"], dtype=np.int64).reshape(3, -1)
+    off, strides = (box["src_offset"], box["src_stride"]) if which == "src" else (box["dst_offset"], box["dst_stride"])
+    return off + sum(idx[k] * strides[k] for k in range(3))
+
+
+def run_pipelined(cfg, o, op, ha, hb, pa, pb, inplace, K, ins):
+    """Executes the chunked schedule of every rank step by step the way the device would be allowed to:
+    step s = all pushes of chunk s, then all unpacks scheduled for step s. Returns the output buffers, or None if
+    chunking does not apply."""
+    ax, direction = OPS[op]
+    a, b = orc.transpose_axes(op)
+    n = o.nranks
+    plans = [cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, inplace, K) for r in range(n)]
+    if not any(plans):
+        return None
+    sizes = [max(o.pencil_info(r, a, ha, pa).size, o.pencil_info(r, b, hb, pb).size) for r in range(n)]
+    bufs = []
+    for r in range(n):
+        buf = np.full(sizes[r], -3, np.int64)
+        buf[:ins[r].size] = ins[r]
+        bufs.append(buf)
+    outs = bufs if inplace else [np.full(sizes[r], -3, np.int64) for r in range(n)]
+    works = [np.full(max(o.transpose_workspace_size(), 1), -9, np.int64) for _ in range(n)]
+    arrived = [np.full(w.size, -1, np.int64) for w in works]  # step in which a workspace cell was written
+    for s in range(K):
+        for r in range(n):
+            for box in plans[r]:
+                if box["step"] == s and not box["is_unpack"]:
+                    dst = _box_cells(box, "dst")
+                    peer = box["peer_rank"]
+                    assert (arrived[peer][dst] == -1).all(), "a workspace cell is written twice"
+                    arrived[peer][dst] = s
+                    works[peer][dst] = bufs[r][_box_cells(box, "src")]
+        for r in range(n):
+            for box in plans[r]:
+                if box["step"] == s and box["is_unpack"]:
+                    src = _box_cells(box, "src")
+                    assert ((arrived[r][src] >= 0) & (arrived[r][src] <= s)).all(), "unpack before the data arrived"
+                    outs[r][_box_cells(box, "dst")] = works[r][src]
+    return outs
+
+
+@settings(max_examples=int(__import__("os").environ.get("CDB_HYPOTHESIS_EXAMPLES", "150")), deadline=None,
+          suppress_health_check=list(HealthCheck))
+@given(decompositions(), st.sampled_from([2, 3, 4, 8]), st.booleans())
+def test_pipelined_schedule_equals_oracle(d, K, inplace):
+    cfg, o = make_config(d), make_oracle(d)
+    n = o.nranks
+    for op in OPS:
+        a, b = orc.transpose_axes(op)
+        if o.has_empty_pencils(a) or o.has_empty_pencils(b):
+            continue
+        ha, hb, pa, pb = d["halos"][str(a)], d["halos"][str(b)], d["pads"][str(a)], d["pads"][str(b)]
+        rng = np.random.default_rng(5)
+        ins = [rng.integers(1, 1 << 40, o.pencil_info(r, a, ha, pa).size).astype(np.int64) for r in range(n)]
+        sizes = [max(o.pencil_info(r, a, ha, pa).size, o.pencil_info(r, b, hb, pb).size) for r in range(n)]
+        # oracle result with the same pre-existing buffer contents
+        ref_in = []
+        for r in range(n):
+            buf = np.full(sizes[r], -3, np.int64)
+            buf[:ins[r].size] = ins[r]
+            ref_in.append(buf)
+        ref_out = ref_in if inplace else [np.full(sizes[r], -3, np.int64) for r in range(n)]
+        o.transpose(op, ref_in, ref_out, ha, hb, pa, pb)
+        got = run_pipelined(cfg, o, op, ha, hb, pa, pb, inplace, K, ins)
+        if got is None:
+            continue
+        for r in range(n):
+            assert np.array_equal(got[r], ref_out[r]), (d, op, K, inplace, r)
