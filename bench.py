@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--staged", action="store_true", help="force the workspace-staged schedule")
     ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--bulk", action="store_true", help="TMA bulk row-copy variant (experimental)")
+    ap.add_argument("--chunks", type=int, default=0, help="chunked schedule of staged transposes (experimental)")
     return ap.parse_args()
 
 
@@ -221,6 +223,10 @@ def run_native(args, rank, world, local_rank):
     cd.check(res, "cudecompGridDescCreate")
     if args.staged or args.ctas:
         cd.check(cd.set_tuning(handle, gd, args.ctas, args.staged))
+    if args.bulk:
+        cd.check(cd.set_kernel_variant(handle, gd, 1))
+    if args.chunks:
+        cd.check(cd.set_pipeline_chunks(handle, gd, args.chunks))
 
     sizes = [cd.cudecompGetPencilInfo(handle, gd, ax)[1].size for ax in range(3)]
     S = sizes[0] * es  # bytes of this rank's pencil (equal for the three orientations on even grids)

@@ -138,7 +138,7 @@ API_SYMBOLS = [
     "cudecompUpdateHalosZ",
 ]
 EXT_SYMBOLS = ["cudecompB200GetLaunchCount", "cudecompB200GetLastPath", "cudecompB200SetTuning",
-               "cudecompB200CheckErrors", "cudecompB200SetPipelineChunks", "cudecompB200DescribeTransposeBoxes", "cudecompB200DescribeHaloBoxes",
+               "cudecompB200CheckErrors", "cudecompB200SetPipelineChunks", "cudecompB200SetKernelVariant", "cudecompB200DescribeTransposeBoxes", "cudecompB200DescribeHaloBoxes",
                "cudecompB200PlanTransposeBoxes", "cudecompB200PlanHaloBoxes", "cudecompB200PlanPipelinedTransposeBoxes",
                "cudecompB200SelfTestMailbox"]
 MPI_SHIM_SYMBOLS = ["MPI_Init", "MPI_Init_thread", "MPI_Initialized", "MPI_Finalize", "MPI_Finalized", "MPI_Abort",
@@ -193,6 +193,7 @@ _sig("cudecompB200GetLastPath", ctypes.c_int, [cudecompHandle_t, cudecompGridDes
 _sig("cudecompB200SetTuning", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32, _i32])
 _sig("cudecompB200CheckErrors", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t])
 _sig("cudecompB200SetPipelineChunks", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32])
+_sig("cudecompB200SetKernelVariant", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32])
 _sig("cudecompB200DescribeTransposeBoxes", _i32,
      [cudecompHandle_t, cudecompGridDesc_t, _i32, _i32, _i32p, _i32p, _i32p, _i32p, _i32, _P(cudecompB200Box_t), _i32])
 _sig("cudecompB200DescribeHaloBoxes", _i32,
@@ -440,6 +441,10 @@ def last_path(handle, grid_desc):
 
 def set_tuning(handle, grid_desc, grid_ctas=0, force_staged=False):
     return lib.cudecompB200SetTuning(handle, grid_desc, int(grid_ctas), 1 if force_staged else 0)
+
+
+def set_kernel_variant(handle, grid_desc, variant):
+    return lib.cudecompB200SetKernelVariant(handle, grid_desc, int(variant))
 
 
 def set_pipeline_chunks(handle, grid_desc, nchunks):

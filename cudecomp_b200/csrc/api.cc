@@ -245,6 +245,7 @@ cudecompResult_t cudecompInit(cudecompHandle_t* handle_in, MPI_Comm mpi_comm) {
   h->env_col_major = envFlag("CUDECOMP_USE_COL_MAJOR_RANK_ORDER");
   h->perf.readEnvironment();
   if (const char* v = std::getenv("CUDECOMP_B200_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(0, std::atoi(v));
+  if (const char* v = std::getenv("CUDECOMP_B200_KERNEL")) h->kernel_variant = (std::strcmp(v, "bulk") == 0) ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_DIRECT")) h->allow_direct = std::strcmp(v, "0") != 0;
   double spin_s = 60.0;
   if (const char* v = std::getenv("CUDECOMP_B200_DEVICE_TIMEOUT")) spin_s = std::atof(v);
@@ -304,6 +305,7 @@ cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudeco
   gd->handle = handle;
   gd->config = *config;
   gd->pipeline_chunks = handle->pipeline_chunks;
+  gd->kernel_variant = handle->kernel_variant;
   if (gd->config.rank_order == CUDECOMP_RANK_ORDER_DEFAULT)
     gd->config.rank_order = handle->env_col_major ? CUDECOMP_RANK_ORDER_COL_MAJOR : CUDECOMP_RANK_ORDER_ROW_MAJOR;
 
@@ -616,6 +618,15 @@ cudecompResult_t cudecompB200SetTuning(cudecompHandle_t handle, cudecompGridDesc
   if (grid_ctas < 0) THROW_INVALID_USAGE("grid_ctas must be >= 0");
   grid_desc->grid_ctas = grid_ctas;
   grid_desc->force_staged = force_staged != 0;
+  API_CATCH()
+}
+
+cudecompResult_t cudecompB200SetKernelVariant(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t variant) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (variant < 0 || variant > 1) THROW_INVALID_USAGE("variant must be 0 (LDG/STG) or 1 (TMA bulk)");
+  grid_desc->kernel_variant = variant;
   API_CATCH()
 }
 

@@ -77,13 +77,14 @@ SyncParams makeSync(cudecompGridDesc_t gd, const std::vector<int>& peers) {
   return s;
 }
 
-void fillRowCopy(KBox& kb, const CanonBox& c, int es, int V) {
-  const uint32_t tile_vecs = 32768u / static_cast<uint32_t>(V);
+void fillRowCopy(KBox& kb, const CanonBox& c, int es, int V, bool bulk = false) {
+  // SIMT: tiles of ~32 KiB (several short rows or one segment of a long row); bulk: one row segment of <= 16 KiB
+  const uint32_t tile_vecs = (bulk ? kBulkChunkBytes : 32768u) / static_cast<uint32_t>(V);
   kb.row_vecs = static_cast<uint32_t>(c.n[0] * es / V);
   kb.seg_vecs = std::min(kb.row_vecs, tile_vecs);
   if (kb.seg_vecs == 0) kb.seg_vecs = 1;
   kb.segs_per_row = (kb.row_vecs + kb.seg_vecs - 1) / kb.seg_vecs;
-  kb.rows_per_tile = std::max(1u, tile_vecs / kb.seg_vecs);
+  kb.rows_per_tile = bulk ? 1u : std::max(1u, tile_vecs / kb.seg_vecs);
   const int64_t rows = c.n[1] * c.n[2];
   const int64_t row_tiles = (rows + kb.rows_per_tile - 1) / kb.rows_per_tile;
   const int64_t tiles = (c.n[0] == 0) ? 0 : row_tiles * kb.segs_per_row;
@@ -112,7 +113,7 @@ void launchBoxes(cudecompGridDesc_t gd, const std::vector<ResolvedBox>& boxes, i
     for (auto& c : canon)
       if (!c.rowCopy()) all_rows = false;
   }
-  const KernelKind kind = all_rows ? KernelKind::ROWCOPY : KernelKind::TRANSPOSE;
+  KernelKind kind = all_rows ? KernelKind::ROWCOPY : KernelKind::TRANSPOSE;
 
   int V = 16;
   if (kind == KernelKind::ROWCOPY) {
@@ -128,6 +129,14 @@ void launchBoxes(cudecompGridDesc_t gd, const std::vector<ResolvedBox>& boxes, i
     }
     V = static_cast<int>(std::min<uint64_t>(a, 16));
     if (V < 4) THROW_INVALID_USAGE("buffers must be aligned to the element size");
+  }
+
+  // TMA bulk variant: only when every row is 16-byte aligned and long enough for one bulk copy to pay off
+  if (kind == KernelKind::ROWCOPY && gd->kernel_variant == 1 && V == 16) {
+    bool ok = !canon.empty();
+    for (auto& c : canon)
+      if (c.n[0] * es < 2048) ok = false;
+    if (ok) kind = KernelKind::ROWCOPY_BULK;
   }
 
   LaunchConfig cfg;
@@ -148,13 +157,13 @@ void launchBoxes(cudecompGridDesc_t gd, const std::vector<ResolvedBox>& boxes, i
       KBox& kb = p.box[p.nboxes++];
       kb.src = live[i]->src_base + live[i]->d.src_off * es;
       kb.dst = live[i]->dst_base + live[i]->d.dst_off * es;
-      if (kind == KernelKind::ROWCOPY) {
+      if (kind == KernelKind::ROWCOPY || kind == KernelKind::ROWCOPY_BULK) {
         for (int k = 0; k < 3; ++k) {
           kb.n[k] = c.n[k];
           kb.ss[k] = c.ss[k];
           kb.ds[k] = c.ds[k];
         }
-        fillRowCopy(kb, c, es, V);
+        fillRowCopy(kb, c, es, V, kind == KernelKind::ROWCOPY_BULK);
       } else {
         // axis 0: contiguous in the source; axis 1: contiguous in the destination when there is one
         int a1 = c.dstUnitAxis();

@@ -45,6 +45,7 @@ struct cudecompHandle {
   int next_slot = 0;
   cdb::PerfSettings perf;        // CUDECOMP_ENABLE_PERFORMANCE_REPORT and friends
   int pipeline_chunks = 0;       // CUDECOMP_B200_PIPELINE_CHUNKS: chunked schedule of staged transposes (0/1 = off)
+  int kernel_variant = 0;        // CUDECOMP_B200_KERNEL=bulk -> 1: TMA bulk row copy where it applies (0 = LDG/STG)
   uint64_t release_count = 0;    // buffers freed through cudecompFree so far
   uint64_t released[cdb::kReleaseSlots] = {0}; // ids of the most recent ones, newest first
 };
@@ -68,6 +69,7 @@ struct cudecompGridDesc {
   std::unique_ptr<cdb::PerfReport> perf; // only when the performance report is enabled
   // chunked (pipelined) staged schedule: unpack kernels run on a side stream beside the next chunk's push
   int pipeline_chunks = 0;
+  int kernel_variant = 0; // 0: SIMT row copy, 1: TMA bulk row copy for 16-byte aligned rows of at least 2 KiB
   cudaStream_t side_stream = nullptr;
   std::vector<cudaEvent_t> side_events;
 };

@@ -227,6 +227,110 @@ template <typename T> __global__ void __launch_bounds__(256) transposeKernel(con
   syncExit(p.sync);
 }
 
+// ---------------------------------------------------------------------------------------------
+// ROWCOPY_BULK: TMA-driven variant of the row copy (cp.async.bulk, SASS UBLKCP). One thread per CTA keeps a ring of
+// kBulkStages row segments in flight: bulk load global->shared completes on an mbarrier, bulk store shared->global
+// (local HBM or the peer over NVLink) is tracked by bulk groups. Measured on B200 (profiles/r1_microbench_copy_2gpu.txt)
+// it moves data exactly as fast as the LDG/STG kernel on both paths while occupying one warp per SM; it needs 16-byte
+// alignment everywhere, so the SIMT kernel stays the default and the fallback.
+// ---------------------------------------------------------------------------------------------
+namespace bulk {
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbarInit(uint64_t* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(b)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbarTryWait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok)
+               : "r"(smemAddr(b)), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void load(void* smem, const void* g, uint32_t bytes, uint64_t* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(smem)),
+               "l"(g), "r"(bytes), "r"(smemAddr(b))
+               : "memory");
+}
+__device__ __forceinline__ void store(void* g, const void* smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(smemAddr(smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+} // namespace bulk
+
+__global__ void __launch_bounds__(32) rowCopyBulkKernel(const __grid_constant__ CopyParams p) {
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  __shared__ uint64_t full[kBulkStages];
+  syncEntry(p.sync);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBulkStages; ++s) bulk::mbarInit(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t total = p.nboxes * p.max_tiles;
+    const int64_t esz = p.elem_size;
+
+    // decode launch tile t -> (source, destination, bytes); false when the slot is empty for that box
+    auto decode = [&](uint32_t t, const char*& src, char*& dst, uint32_t& bytes) -> bool {
+      const uint32_t b = t % p.nboxes;
+      const uint32_t j = t / p.nboxes;
+      const KBox& bx = p.box[b];
+      if (j >= bx.tiles) return false;
+      const uint32_t seg = j % bx.segs_per_row;
+      const int64_t row = j / bx.segs_per_row; // rows_per_tile == 1
+      const int64_t i1 = row % bx.n[1];
+      const int64_t i2 = row / bx.n[1];
+      const uint32_t c0 = seg * bx.seg_vecs;
+      const uint32_t nvec = min(bx.seg_vecs, bx.row_vecs - c0);
+      src = bx.src + (i1 * bx.ss[1] + i2 * bx.ss[2]) * esz + static_cast<int64_t>(c0) * 16;
+      dst = bx.dst + (i1 * bx.ds[1] + i2 * bx.ds[2]) * esz + static_cast<int64_t>(c0) * 16;
+      bytes = nvec * 16u;
+      return true;
+    };
+
+    uint32_t t_load = blockIdx.x;   // next tile to look at for loading
+    uint32_t n_loaded = 0, n_stored = 0;
+    char* dst_of[kBulkStages];
+    uint32_t bytes_of[kBulkStages];
+    auto issueLoad = [&]() -> bool {
+      while (t_load < total) {
+        const char* src;
+        char* dst;
+        uint32_t bytes;
+        const bool ok = decode(t_load, src, dst, bytes);
+        t_load += gridDim.x;
+        if (!ok) continue;
+        const int s = static_cast<int>(n_loaded % kBulkStages);
+        dst_of[s] = dst;
+        bytes_of[s] = bytes;
+        bulk::mbarExpectTx(&full[s], bytes);
+        bulk::load(bulk_smem + static_cast<size_t>(s) * kBulkChunkBytes, src, bytes, &full[s]);
+        ++n_loaded;
+        return true;
+      }
+      return false;
+    };
+    for (int s = 0; s < kBulkStages - 1; ++s)
+      if (!issueLoad()) break;
+    while (n_stored < n_loaded) {
+      const int s = static_cast<int>(n_stored % kBulkStages);
+      const uint32_t parity = (n_stored / kBulkStages) & 1u;
+      while (!bulk::mbarTryWait(&full[s], parity)) {}
+      bulk::store(dst_of[s], bulk_smem + static_cast<size_t>(s) * kBulkChunkBytes, bytes_of[s]);
+      ++n_stored;
+      // the slot stored one iteration ago may be refilled once its store has finished reading shared memory
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      issueLoad();
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // all stores performed
+    asm volatile("fence.proxy.async;" ::: "memory");            // ... and ordered before the generic-proxy flags below
+  }
+  __syncwarp();
+  syncExit(p.sync);
+}
+
 namespace {
 
 using KernelFn = void (*)(const CopyParams);
@@ -238,12 +342,14 @@ KernelFn pickKernel(KernelKind kind, int size) {
     case 8: return rowCopyKernel<uint2>;
     case 4: return rowCopyKernel<uint32_t>;
     }
-  } else {
+  } else if (kind == KernelKind::TRANSPOSE) {
     switch (size) {
     case 16: return transposeKernel<uint4>;
     case 8: return transposeKernel<uint2>;
     case 4: return transposeKernel<uint32_t>;
     }
+  } else if (size == 16) {
+    return rowCopyBulkKernel;
   }
   return nullptr;
 }
@@ -260,6 +366,7 @@ int maxResidentCtas(KernelKind kind, int size, int threads) {
       for (int& v : row) v = 0;
     cache_dev = dev;
   }
+  if (kind == KernelKind::ROWCOPY_BULK) return 0; // not used: launchBulk sizes its own grid
   const int ki = (kind == KernelKind::ROWCOPY) ? 0 : 1;
   const int si = (size == 16) ? 2 : (size == 8 ? 1 : 0);
   if (threads == 256 && cache[ki][si] > 0) return cache[ki][si];
@@ -272,7 +379,29 @@ int maxResidentCtas(KernelKind kind, int size, int threads) {
   return total;
 }
 
+static cudaError_t launchBulk(const CopyParams& p, const LaunchConfig& cfg, cudaStream_t stream) {
+  static bool configured = false;
+  const int smem = kBulkStages * static_cast<int>(kBulkChunkBytes);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(rowCopyBulkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint64_t total = static_cast<uint64_t>(p.nboxes) * p.max_tiles;
+  int grid = cfg.grid > 0 ? cfg.grid : sms; // one TMA-driving CTA per SM (3 fit by shared memory)
+  if (grid > 3 * sms) grid = 3 * sms;
+  if (static_cast<uint64_t>(grid) > total) grid = static_cast<int>(total);
+  if (grid < 1) grid = 1;
+  rowCopyBulkKernel<<<grid, 32, smem, stream>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
 cudaError_t launchCopy(KernelKind kind, const CopyParams& p, const LaunchConfig& cfg, cudaStream_t stream) {
+  if (kind == KernelKind::ROWCOPY_BULK) return launchBulk(p, cfg, stream);
   const int size = (kind == KernelKind::ROWCOPY) ? static_cast<int>(p.vec_size) : static_cast<int>(p.elem_size);
   KernelFn fn = pickKernel(kind, size);
   if (!fn) return cudaErrorInvalidValue;

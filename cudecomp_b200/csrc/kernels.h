@@ -66,7 +66,13 @@ struct CopyParams {
   uint32_t vec_size;  // ROWCOPY: 4, 8 or 16
 };
 
-enum class KernelKind { ROWCOPY, TRANSPOSE };
+// ROWCOPY_BULK: the row copy driven by the TMA unit instead of LDG/STG: one elected thread per CTA moves row segments
+// global -> shared -> global with cp.async.bulk and an mbarrier ring. Same boxes and tiling fields as ROWCOPY, but a
+// tile is ONE row segment of at most kBulkChunkBytes (rows_per_tile = 1) and everything must be 16-byte aligned.
+enum class KernelKind { ROWCOPY, TRANSPOSE, ROWCOPY_BULK };
+
+constexpr int kBulkStages = 4;
+constexpr uint32_t kBulkChunkBytes = 16384;
 
 struct LaunchConfig {
   int grid = 0;    // CTAs (0: library default = all SMs x resident CTAs)

@@ -34,6 +34,12 @@ cudecompResult_t cudecompB200GetLastPath(cudecompHandle_t handle, cudecompGridDe
 cudecompResult_t cudecompB200SetTuning(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t grid_ctas,
                                        int32_t force_staged);
 
+/* Row-copy kernel variant: 0 = LDG/STG.128 (default), 1 = TMA bulk copies (cp.async.bulk through shared memory) for
+ * launches whose rows are all 16-byte aligned and at least 2 KiB long; other launches keep variant 0. Also settable
+ * with CUDECOMP_B200_KERNEL=bulk. EXPERIMENTAL in round 1 (measured equal in bench/microbench_copy.cu, the product
+ * kernel is not yet confirmed on hardware). */
+cudecompResult_t cudecompB200SetKernelVariant(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t variant);
+
 /* Chunked schedule of staged transposes (in-place calls, NVSHMEM-family backends, non-exportable outputs): the pencil
  * is pushed in `nchunks` chunks and unpacking overlaps the next chunk's push (csrc/plan.h PipelinedPlan). 0 or 1 = off
  * (default; also settable for all descriptors with CUDECOMP_B200_PIPELINE_CHUNKS). Same value on every rank.

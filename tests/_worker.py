@@ -114,6 +114,8 @@ def transpose_case(gpu, handle, rank, case):
             cd.check(cd.set_tuning(handle, gd, case["grid_ctas"], bool(case.get("force_staged"))))
         if case.get("pipeline_chunks"):
             cd.check(cd.set_pipeline_chunks(handle, gd, case["pipeline_chunks"]))
+        if case.get("kernel_variant"):
+            cd.check(cd.set_kernel_variant(handle, gd, case["kernel_variant"]))
 
         def h(ax):
             return halos.get(str(ax))

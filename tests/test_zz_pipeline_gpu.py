@@ -37,3 +37,27 @@ def test_pipelined_staged_transposes(pipe_results, i):
     bad = ["rank %d: %s" % (r, pipe_results[r][i].get("msg")) for r in range(4) if not pipe_results[r][i]["ok"]]
     assert not bad, "\n".join(bad)
     assert 3 in set(pipe_results[0][i]["paths"])  # the staged path really ran
+
+
+# ------------------------------------------------------------------------------------ TMA bulk row-copy variant
+BULK_CASES = [
+    dict(kind="transpose", name="Bulk_oop_2x2_c128", gdims=[256, 64, 48], pdims=[2, 2], dtype="double_complex",
+         ops=["XY", "YZ", "ZY", "YX"], out_of_place=True, kernel_variant=1),
+    dict(kind="transpose", name="Bulk_inplace_2x2_double", gdims=[512, 48, 40], pdims=[2, 2], dtype="double",
+         ops=["XY", "YZ", "ZY", "YX"], kernel_variant=1),
+    dict(kind="transpose", name="Bulk_falls_back_on_short_rows", gdims=[9, 10, 11], pdims=[2, 2], dtype="float",
+         ops=["XY", "YZ", "ZY", "YX"], out_of_place=True, kernel_variant=1),
+    dict(kind="transpose", name="Bulk_pipelined_inplace", gdims=[256, 64, 48], pdims=[2, 2], dtype="double_complex",
+         ops=["XY", "YZ", "ZY", "YX"], kernel_variant=1, pipeline_chunks=4),
+]
+
+
+@pytest.fixture(scope="module")
+def bulk_results():
+    return run_ranks(4, "gpu", BULK_CASES, timeout=900)[0]
+
+
+@pytest.mark.parametrize("i", range(len(BULK_CASES)), ids=[c["name"] for c in BULK_CASES])
+def test_tma_bulk_variant(bulk_results, i):
+    bad = ["rank %d: %s" % (r, bulk_results[r][i].get("msg")) for r in range(4) if not bulk_results[r][i]["ok"]]
+    assert not bad, "\n".join(bad)
