@@ -13,8 +13,23 @@ FLAGS := -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -x cu \
 
 TYPES := R32 R64 C32 C64
 BINS := $(foreach t,$(TYPES),$(OUT)/transpose_test_$(t) $(OUT)/halo_test_$(t))
+# the reference's FFT benchmark (benchmark/benchmark.cu: cuFFT per pencil + the four transposes), also unmodified
+BENCH := $(OUT)/benchmark_c2c $(OUT)/benchmark_r2c $(OUT)/benchmark_c2c_f $(OUT)/benchmark_r2c_f
 
-all: $(BINS)
+all: $(BINS) $(BENCH)
+
+$(OUT)/benchmark_c2c: $(REF)/benchmark/benchmark.cu $(ROOT)/cudecomp_b200/lib/libcudecomp.so
+	@mkdir -p $(OUT)
+	$(NVCC) $(FLAGS) -DC2C $< -lcufft -o $@
+$(OUT)/benchmark_r2c: $(REF)/benchmark/benchmark.cu $(ROOT)/cudecomp_b200/lib/libcudecomp.so
+	@mkdir -p $(OUT)
+	$(NVCC) $(FLAGS) -DR2C $< -lcufft -o $@
+$(OUT)/benchmark_c2c_f: $(REF)/benchmark/benchmark.cu $(ROOT)/cudecomp_b200/lib/libcudecomp.so
+	@mkdir -p $(OUT)
+	$(NVCC) $(FLAGS) -DC2C -DUSE_FLOAT $< -lcufft -o $@
+$(OUT)/benchmark_r2c_f: $(REF)/benchmark/benchmark.cu $(ROOT)/cudecomp_b200/lib/libcudecomp.so
+	@mkdir -p $(OUT)
+	$(NVCC) $(FLAGS) -DR2C -DUSE_FLOAT $< -lcufft -o $@
 
 $(OUT)/transpose_test_%: $(REF)/tests/cc/transpose_test.cc $(ROOT)/cudecomp_b200/lib/libcudecomp.so
 	@mkdir -p $(OUT)
