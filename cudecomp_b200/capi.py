@@ -140,7 +140,7 @@ API_SYMBOLS = [
 EXT_SYMBOLS = ["cudecompB200GetLaunchCount", "cudecompB200GetLastPath", "cudecompB200SetTuning",
                "cudecompB200CheckErrors", "cudecompB200SetPipelineChunks", "cudecompB200SetKernelVariant", "cudecompB200DescribeTransposeBoxes", "cudecompB200DescribeHaloBoxes",
                "cudecompB200PlanTransposeBoxes", "cudecompB200PlanHaloBoxes", "cudecompB200PlanPipelinedTransposeBoxes",
-               "cudecompB200SelfTestMailbox"]
+               "cudecompB200SelfTestMailbox", "cudecompB200GetAutotuneCandidates"]
 MPI_SHIM_SYMBOLS = ["MPI_Init", "MPI_Init_thread", "MPI_Initialized", "MPI_Finalize", "MPI_Finalized", "MPI_Abort",
                     "MPI_Wtime", "MPI_Get_processor_name", "MPI_Error_string", "MPI_Comm_rank", "MPI_Comm_size",
                     "MPI_Comm_split", "MPI_Comm_split_type", "MPI_Comm_dup", "MPI_Comm_free", "MPI_Comm_c2f",
@@ -520,3 +520,15 @@ def plan_pipelined_transpose_boxes(config, rank, ax, direction, input_halo_exten
     if n > max_boxes:
         raise ValueError("plan has %d boxes, buffer holds %d" % (n, max_boxes))
     return _boxes(n, arr)
+
+
+def autotune_candidates(options, nranks=1, rank_order=CUDECOMP_RANK_ORDER_ROW_MAJOR):
+    """-> (result, transpose backends, halo backends, pdims candidates) after environment filters and disable flags."""
+    tb, hb = (_i32 * 8)(), (_i32 * 5)()
+    nt, nh, npd = _i32(0), _i32(0), _i32(0)
+    pd = ((_i32 * 2) * 64)()
+    fn = lib.cudecompB200GetAutotuneCandidates
+    fn.restype = ctypes.c_int
+    res = fn(ctypes.byref(options), _i32(nranks), ctypes.c_int(rank_order), tb, ctypes.byref(nt), hb, ctypes.byref(nh), pd,
+             _i32(64), ctypes.byref(npd))
+    return res, list(tb[:nt.value]), list(hb[:nh.value]), [tuple(pd[i]) for i in range(npd.value)]

@@ -647,6 +647,35 @@ cudecompResult_t cudecompB200CheckErrors(cudecompHandle_t handle, cudecompGridDe
   API_CATCH()
 }
 
+cudecompResult_t cudecompB200GetAutotuneCandidates(const cudecompGridDescAutotuneOptions_t* options, int32_t nranks,
+                                                   cudecompRankOrder_t rank_order, int32_t transpose_backends[8],
+                                                   int32_t* n_transpose, int32_t halo_backends[5], int32_t* n_halo,
+                                                   int32_t pdims[][2], int32_t max_pdims, int32_t* n_pdims) {
+  API_TRY
+  if (!options) THROW_INVALID_USAGE("options argument cannot be null");
+  checkOptionsStruct(options);
+  if (transpose_backends && n_transpose) {
+    auto c = autotuneTransposeBackendCandidates(options);
+    *n_transpose = static_cast<int32_t>(c.size());
+    for (size_t i = 0; i < c.size(); ++i) transpose_backends[i] = c[i];
+  }
+  if (halo_backends && n_halo) {
+    auto c = autotuneHaloBackendCandidates(options);
+    *n_halo = static_cast<int32_t>(c.size());
+    for (size_t i = 0; i < c.size(); ++i) halo_backends[i] = c[i];
+  }
+  if (pdims && n_pdims) {
+    if (nranks < 1) THROW_INVALID_USAGE("nranks must be positive");
+    auto c = autotunePdimCandidates(nranks, rank_order == CUDECOMP_RANK_ORDER_COL_MAJOR);
+    *n_pdims = static_cast<int32_t>(c.size());
+    for (size_t i = 0; i < c.size() && static_cast<int32_t>(i) < max_pdims; ++i) {
+      pdims[i][0] = c[i][0];
+      pdims[i][1] = c[i][1];
+    }
+  }
+  API_CATCH()
+}
+
 cudecompResult_t cudecompB200SelfTestMailbox(cudecompHandle_t handle, int32_t iterations, uint32_t seed) {
   API_TRY
   checkHandle(handle);

@@ -26,29 +26,102 @@ namespace {
 
 bool backendIsStaged(int b) { return b >= CUDECOMP_TRANSPOSE_COMM_NVSHMEM; }
 
+// "min,max" with nonnegative min, positive max, min <= max (reference src/autotune.cc:192-213)
 std::pair<int32_t, int32_t> parseRange(const char* name) {
-  // "lo:hi" or "n" (reference src/autotune.cc:192-253)
   const char* v = std::getenv(name);
-  std::pair<int32_t, int32_t> r{1, std::numeric_limits<int32_t>::max()};
-  if (!v || !*v) return r;
-  std::string s(v);
-  try {
-    auto pos = s.find(':');
-    if (pos == std::string::npos) {
-      r.first = r.second = std::stoi(s);
-    } else {
-      if (pos > 0) r.first = std::stoi(s.substr(0, pos));
-      if (pos + 1 < s.size()) r.second = std::stoi(s.substr(pos + 1));
-    }
-  } catch (...) {
-    THROW_INVALID_USAGE(std::string(name) + " is malformed");
+  if (!v) return {1, std::numeric_limits<int32_t>::max()};
+  const std::string s(v);
+  const size_t comma = s.find(',');
+  bool valid = comma != std::string::npos && comma > 0 && comma + 1 < s.size() && s.find(',', comma + 1) == std::string::npos;
+  long lo = 0, hi = 0;
+  if (valid) {
+    char* e1 = nullptr;
+    char* e2 = nullptr;
+    const std::string a = s.substr(0, comma), b = s.substr(comma + 1);
+    lo = std::strtol(a.c_str(), &e1, 10);
+    hi = std::strtol(b.c_str(), &e2, 10);
+    valid = *e1 == 0 && *e2 == 0 && a.find_first_not_of("0123456789") == std::string::npos &&
+            b.find_first_not_of("0123456789") == std::string::npos && lo >= 0 && hi > 0 && lo <= hi;
   }
-  if (r.first < 1 || r.second < r.first) THROW_INVALID_USAGE(std::string(name) + " is malformed");
-  return r;
+  if (!valid)
+    THROW_INVALID_USAGE(std::string(name) + " must be comma-separated nonnegative min and positive max with min <= max");
+  return {static_cast<int32_t>(lo), static_cast<int32_t>(hi)};
 }
 
-std::vector<std::array<int32_t, 2>> autotunePdims(cudecompHandle_t h, cudecompGridDesc_t gd) {
-  auto cand = pdimCandidates(h->nranks, gd->config.rank_order == CUDECOMP_RANK_ORDER_COL_MAJOR);
+// CUDECOMP_AUTOTUNE_{TRANSPOSE,HALO}_BACKENDS: comma-separated backend names, a leading '^' turns the list into an
+// exclusion list; unknown or empty names are errors (reference src/autotune.cc:108-143)
+std::vector<int> filterByEnvironment(const char* env_name, const std::vector<std::pair<std::string, int>>& supported,
+                                     std::vector<int> available) {
+  const char* env = std::getenv(env_name);
+  if (!env) return available;
+  std::string value(env);
+  const bool exclude = !value.empty() && value[0] == '^';
+  if (exclude) value.erase(0, 1);
+  std::vector<int> listed;
+  size_t start = 0;
+  for (;;) {
+    size_t end = value.find(',', start);
+    if (end == std::string::npos) end = value.size();
+    const std::string name = value.substr(start, end - start);
+    auto it = std::find_if(supported.begin(), supported.end(), [&](const auto& e) { return e.first == name; });
+    if (it == supported.end())
+      THROW_INVALID_USAGE(std::string(env_name) + " contains unknown or empty backend name '" + name + "'");
+    listed.push_back(it->second);
+    if (end == value.size()) break;
+    start = end + 1;
+  }
+  available.erase(std::remove_if(available.begin(), available.end(),
+                                 [&](int b) {
+                                   const bool is_listed = std::find(listed.begin(), listed.end(), b) != listed.end();
+                                   return exclude ? is_listed : !is_listed;
+                                 }),
+                  available.end());
+  return available;
+}
+
+} // namespace
+
+std::vector<int> autotuneTransposeBackendCandidates(const cudecompGridDescAutotuneOptions_t* o) {
+  static const std::vector<std::pair<std::string, int>> supported = {
+      {"MPI_P2P", CUDECOMP_TRANSPOSE_COMM_MPI_P2P},       {"MPI_P2P_PL", CUDECOMP_TRANSPOSE_COMM_MPI_P2P_PL},
+      {"MPI_A2A", CUDECOMP_TRANSPOSE_COMM_MPI_A2A},       {"NCCL", CUDECOMP_TRANSPOSE_COMM_NCCL},
+      {"NCCL_PL", CUDECOMP_TRANSPOSE_COMM_NCCL_PL},       {"NVSHMEM", CUDECOMP_TRANSPOSE_COMM_NVSHMEM},
+      {"NVSHMEM_PL", CUDECOMP_TRANSPOSE_COMM_NVSHMEM_PL}, {"NVSHMEM_SM", CUDECOMP_TRANSPOSE_COMM_NVSHMEM_SM}};
+  std::vector<int> c = {1, 2, 3, 4, 5, 6, 7, 8}; // every value is a schedule of the one engine, so all are available
+  c = filterByEnvironment("CUDECOMP_AUTOTUNE_TRANSPOSE_BACKENDS", supported, c);
+  c.erase(std::remove_if(c.begin(), c.end(),
+                         [&](int b) {
+                           return (o->disable_mpi_backends && b <= CUDECOMP_TRANSPOSE_COMM_MPI_A2A) ||
+                                  (o->disable_nccl_backends &&
+                                   (b == CUDECOMP_TRANSPOSE_COMM_NCCL || b == CUDECOMP_TRANSPOSE_COMM_NCCL_PL)) ||
+                                  (o->disable_nvshmem_backends && b >= CUDECOMP_TRANSPOSE_COMM_NVSHMEM);
+                         }),
+          c.end());
+  if (c.empty()) THROW_INVALID_USAGE("Transpose backend autotuning has no usable candidates after applying filters");
+  return c;
+}
+
+std::vector<int> autotuneHaloBackendCandidates(const cudecompGridDescAutotuneOptions_t* o) {
+  static const std::vector<std::pair<std::string, int>> supported = {{"MPI", CUDECOMP_HALO_COMM_MPI},
+                                                                     {"MPI_BLOCKING", CUDECOMP_HALO_COMM_MPI_BLOCKING},
+                                                                     {"NCCL", CUDECOMP_HALO_COMM_NCCL},
+                                                                     {"NVSHMEM", CUDECOMP_HALO_COMM_NVSHMEM},
+                                                                     {"NVSHMEM_BLOCKING", CUDECOMP_HALO_COMM_NVSHMEM_BLOCKING}};
+  std::vector<int> c = {1, 2, 3, 4, 5};
+  c = filterByEnvironment("CUDECOMP_AUTOTUNE_HALO_BACKENDS", supported, c);
+  c.erase(std::remove_if(c.begin(), c.end(),
+                         [&](int b) {
+                           return (o->disable_mpi_backends && b <= CUDECOMP_HALO_COMM_MPI_BLOCKING) ||
+                                  (o->disable_nccl_backends && b == CUDECOMP_HALO_COMM_NCCL) ||
+                                  (o->disable_nvshmem_backends && b >= CUDECOMP_HALO_COMM_NVSHMEM);
+                         }),
+          c.end());
+  if (c.empty()) THROW_INVALID_USAGE("Halo backend autotuning has no usable candidates after applying filters");
+  return c;
+}
+
+std::vector<std::array<int32_t, 2>> autotunePdimCandidates(int nranks, bool col_major) {
+  auto cand = pdimCandidates(nranks, col_major);
   auto rows = parseRange("CUDECOMP_AUTOTUNE_P_ROW_RANGE");
   auto cols = parseRange("CUDECOMP_AUTOTUNE_P_COL_RANGE");
   cand.erase(std::remove_if(cand.begin(), cand.end(),
@@ -58,6 +131,12 @@ std::vector<std::array<int32_t, 2>> autotunePdims(cudecompHandle_t h, cudecompGr
              cand.end());
   if (cand.empty()) THROW_INVALID_USAGE("Process-grid autotuning has no usable candidates after applying filters");
   return cand;
+}
+
+namespace {
+
+std::vector<std::array<int32_t, 2>> autotunePdims(cudecompHandle_t h, cudecompGridDesc_t gd) {
+  return autotunePdimCandidates(h->nranks, gd->config.rank_order == CUDECOMP_RANK_ORDER_COL_MAJOR);
 }
 
 bool gridUsable(const cudecompGridDesc_t gd, const std::array<int32_t, 2>& p, bool allow_uneven) {
@@ -130,13 +209,14 @@ void autotuneTransposes(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecom
 
   std::vector<int> backends;
   if (tune_backend) {
-    // one representative per schedule family that the options leave enabled
-    if (!o->disable_nccl_backends)
-      backends.push_back(CUDECOMP_TRANSPOSE_COMM_NCCL);
-    else if (!o->disable_mpi_backends)
-      backends.push_back(CUDECOMP_TRANSPOSE_COMM_MPI_P2P);
-    if (!o->disable_nvshmem_backends) backends.push_back(CUDECOMP_TRANSPOSE_COMM_NVSHMEM);
-    if (backends.empty()) THROW_INVALID_USAGE("Transpose backend autotuning has no usable candidates");
+    // Backend values of one family run the same schedule (1-5 direct, 6-8 staged): time one representative of each
+    // family that the filters leave enabled, the first in enum order.
+    bool have_direct = false, have_staged = false;
+    for (int b : autotuneTransposeBackendCandidates(o)) {
+      bool& seen = backendIsStaged(b) ? have_staged : have_direct;
+      if (!seen) backends.push_back(b);
+      seen = true;
+    }
   } else {
     backends.push_back(gd->config.transpose_comm_backend);
   }
@@ -319,16 +399,7 @@ void autotuneHalos(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecompGrid
 
   // all halo backend values run the same peer-store schedule; keep the caller's value unless it asked to tune
   int backend = gd->config.halo_comm_backend;
-  if (tune_backend) {
-    if (!o->disable_nccl_backends)
-      backend = CUDECOMP_HALO_COMM_NCCL;
-    else if (!o->disable_mpi_backends)
-      backend = CUDECOMP_HALO_COMM_MPI;
-    else if (!o->disable_nvshmem_backends)
-      backend = CUDECOMP_HALO_COMM_NVSHMEM;
-    else
-      THROW_INVALID_USAGE("Halo backend autotuning has no usable candidates");
-  }
+  if (tune_backend) backend = autotuneHaloBackendCandidates(o).front();
   const int64_t es = dtypeSize(o->dtype);
   const int ax = o->halo_axis;
 

@@ -91,6 +91,9 @@ void runHalo(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, void* input, voi
 void checkDeviceError(cudecompGridDesc_t gd);
 
 // grid-descriptor autotuning (autotune.cc)
+std::vector<int> autotuneTransposeBackendCandidates(const cudecompGridDescAutotuneOptions_t* options);
+std::vector<int> autotuneHaloBackendCandidates(const cudecompGridDescAutotuneOptions_t* options);
+std::vector<std::array<int32_t, 2>> autotunePdimCandidates(int nranks, bool col_major);
 void autotune(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecompGridDescAutotuneOptions_t* options);
 
 } // namespace cdb

@@ -81,6 +81,14 @@ int32_t cudecompB200PlanPipelinedTransposeBoxes(const cudecompGridDescConfig_t* 
                                                 const int32_t output_padding[], int32_t inplace, int32_t nchunks,
                                                 cudecompB200Box_t* boxes, int32_t max_boxes);
 
+/* What the autotuner would sweep for `options` on `nranks` ranks after the reference's environment filters
+ * (CUDECOMP_AUTOTUNE_TRANSPOSE_BACKENDS / _HALO_BACKENDS comma lists with '^' exclusion, CUDECOMP_AUTOTUNE_P_ROW_RANGE /
+ * _P_COL_RANGE "min,max") and the disable_* flags: reference src/autotune.cc:108-273. Any output pair may be NULL. */
+cudecompResult_t cudecompB200GetAutotuneCandidates(const cudecompGridDescAutotuneOptions_t* options, int32_t nranks,
+                                                   cudecompRankOrder_t rank_order, int32_t transpose_backends[8],
+                                                   int32_t* n_transpose, int32_t halo_backends[5], int32_t* n_halo,
+                                                   int32_t pdims[][2], int32_t max_pdims, int32_t* n_pdims);
+
 /* Host-only self test of the shared-memory descriptor mailbox (collective over the handle's communicator, no GPU
  * needed): `iterations` exchanges on alternating channels with rank groups of varying shape and randomised delays;
  * every received message is checked. Returns CUDECOMP_RESULT_SUCCESS or INTERNAL_ERROR. */
