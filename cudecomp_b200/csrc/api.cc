@@ -293,6 +293,9 @@ cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudeco
     checkOptionsStruct(options);
     if (options->struct_size != options_struct_size || options->version != options_version)
       THROW_INVALID_USAGE("options metadata does not match the requested cuDecomp layout version");
+    // rejected even when nothing is left to tune (reference src/cudecomp.cc:1201-1210)
+    if (options->grid_mode != CUDECOMP_AUTOTUNE_GRID_TRANSPOSE && options->grid_mode != CUDECOMP_AUTOTUNE_GRID_HALO)
+      THROW_INVALID_USAGE("unknown value of autotune_grid_mode encountered.");
   }
   const bool autotune_transpose = options && options->autotune_transpose_backend;
   const bool autotune_halo = options && options->autotune_halo_backend;

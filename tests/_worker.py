@@ -4,6 +4,8 @@ mode 'gpu'  : runs each case through the C ABI of libcudecomp.so on this rank's 
               (a) the analytic global-index pattern of the reference's tests and (b) the CPU oracle fed with the
               same seeded inputs. Ranks share a GPU when there are fewer GPUs than ranks (the reference's tests do
               the same under MPS, tests/README.md:69-82).
+mode 'api'  : host only. The reference's API contract tests (tests/_api_battery.py); 'api_gpu' adds the parts that
+              allocate device memory.
 mode 'plan' : host only. Dumps the rank's pencil infos and transfer plans so the parent can execute the plans with
               numpy and compare with the oracle (covers the N>1 planning logic without a GPU).
 """
@@ -425,7 +427,7 @@ def main():
         payload = json.load(f)
     rank = int(os.environ.get("RANK", "0"))
     results = []
-    gpu = Gpu() if payload["mode"] == "gpu" else None
+    gpu = Gpu() if payload["mode"] in ("gpu", "api_gpu") else None
     assert cd.MPI_Init() == 0
     res, handle = cd.cudecompInit(cd.MPI_COMM_WORLD)
     cd.check(res, "cudecompInit")
@@ -441,6 +443,9 @@ def main():
                 results.append(mailbox_selftest(handle, case))
             elif payload["mode"] == "plan":
                 results.append(plan_case(handle, rank, case))
+            elif payload["mode"] in ("api", "api_gpu"):
+                from tests import _api_battery
+                results.append(_api_battery.run(handle, rank, case["name"], payload["mode"] == "api_gpu"))
             elif case["kind"] == "halo":
                 results.append(halo_case(gpu, handle, rank, case))
             elif case["kind"] == "autotune":
