@@ -16,6 +16,7 @@
 #include "cudecomp.h"
 #include "cudecomp_b200_ext.h"
 #include "engine.h"
+#include "launch_params.h"
 #include "errors.h"
 #include "mpi_shim.h"
 
@@ -246,6 +247,10 @@ cudecompResult_t cudecompInit(cudecompHandle_t* handle_in, MPI_Comm mpi_comm) {
   h->perf.readEnvironment();
   if (const char* v = std::getenv("CUDECOMP_B200_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(0, std::atoi(v));
   if (const char* v = std::getenv("CUDECOMP_B200_KERNEL")) h->kernel_variant = (std::strcmp(v, "bulk") == 0) ? 1 : 0;
+  if (const char* v = std::getenv("CUDECOMP_B200_TILE_BYTES")) h->tile_bytes = std::max(0, std::atoi(v));
+  if (const char* v = std::getenv("CUDECOMP_B200_PEER_ORDER"))
+    h->peer_order = (std::strcmp(v, "pairwise") == 0 || std::strcmp(v, "1") == 0) ? 1 : 0;
+  if (const char* v = std::getenv("CUDECOMP_B200_BALANCE_GRID")) h->balance_grid = std::atoi(v) != 0 ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_DIRECT")) h->allow_direct = std::strcmp(v, "0") != 0;
   double spin_s = 60.0;
   if (const char* v = std::getenv("CUDECOMP_B200_DEVICE_TIMEOUT")) spin_s = std::atof(v);
@@ -309,6 +314,9 @@ cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudeco
   gd->config = *config;
   gd->pipeline_chunks = handle->pipeline_chunks;
   gd->kernel_variant = handle->kernel_variant;
+  gd->tile_bytes = handle->tile_bytes;
+  gd->peer_order = handle->peer_order;
+  gd->balance_grid = handle->balance_grid;
   if (gd->config.rank_order == CUDECOMP_RANK_ORDER_DEFAULT)
     gd->config.rank_order = handle->env_col_major ? CUDECOMP_RANK_ORDER_COL_MAJOR : CUDECOMP_RANK_ORDER_ROW_MAJOR;
 
@@ -630,6 +638,20 @@ cudecompResult_t cudecompB200SetKernelVariant(cudecompHandle_t handle, cudecompG
   checkGridDesc(handle, grid_desc);
   if (variant < 0 || variant > 1) THROW_INVALID_USAGE("variant must be 0 (LDG/STG) or 1 (TMA bulk)");
   grid_desc->kernel_variant = variant;
+  API_CATCH()
+}
+
+cudecompResult_t cudecompB200SetSchedule(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t tile_bytes,
+                                         int32_t peer_order, int32_t balance_grid) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (tile_bytes != 0 && (tile_bytes < kMinTileBytes || tile_bytes > kMaxTileBytes || (tile_bytes & (tile_bytes - 1)) != 0))
+    THROW_INVALID_USAGE("tile_bytes must be 0 or a power of two in [4096, 262144]");
+  if (peer_order < 0 || peer_order > 1) THROW_INVALID_USAGE("peer_order must be 0 (interleaved) or 1 (pairwise rounds)");
+  grid_desc->tile_bytes = tile_bytes;
+  grid_desc->peer_order = peer_order;
+  grid_desc->balance_grid = balance_grid != 0 ? 1 : 0;
   API_CATCH()
 }
 

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "errors.h"
+#include "launch_params.h"
 
 namespace cdb {
 
@@ -45,13 +46,7 @@ void checkDeviceError(cudecompGridDesc_t gd) {
 
 namespace {
 
-struct ResolvedBox {
-  BoxDesc d;
-  const char* src_base;
-  char* dst_base;
-};
-
-uint64_t lowBit(uint64_t x) { return x ? (x & (~x + 1)) : (1ull << 62); }
+using ResolvedBox = LaunchBox;
 
 // Fills the per-launch handshake block. `peers` are global ranks other than mine.
 SyncParams makeSync(cudecompGridDesc_t gd, const std::vector<int>& peers) {
@@ -77,117 +72,28 @@ SyncParams makeSync(cudecompGridDesc_t gd, const std::vector<int>& peers) {
   return s;
 }
 
-void fillRowCopy(KBox& kb, const CanonBox& c, int es, int V, bool bulk = false) {
-  // SIMT: tiles of ~32 KiB (several short rows or one segment of a long row); bulk: one row segment of <= 16 KiB
-  const uint32_t tile_vecs = (bulk ? kBulkChunkBytes : 32768u) / static_cast<uint32_t>(V);
-  kb.row_vecs = static_cast<uint32_t>(c.n[0] * es / V);
-  kb.seg_vecs = std::min(kb.row_vecs, tile_vecs);
-  if (kb.seg_vecs == 0) kb.seg_vecs = 1;
-  kb.segs_per_row = (kb.row_vecs + kb.seg_vecs - 1) / kb.seg_vecs;
-  kb.rows_per_tile = bulk ? 1u : std::max(1u, tile_vecs / kb.seg_vecs);
-  const int64_t rows = c.n[1] * c.n[2];
-  const int64_t row_tiles = (rows + kb.rows_per_tile - 1) / kb.rows_per_tile;
-  const int64_t tiles = (c.n[0] == 0) ? 0 : row_tiles * kb.segs_per_row;
-  if (tiles > 0x7fffffff) THROW_NOT_SUPPORTED("box too large for one launch");
-  kb.tiles = static_cast<uint32_t>(tiles);
-  kb.tiles0 = kb.tiles1 = 0;
-}
-
 // Enqueue the copy of `boxes` (all with the same element size). `sync` handshakes with peers (may be empty).
+// `me` / `comm_size`: my index in the communicator the boxes' peers belong to (orders the boxes for the pairwise
+// slot order; -1 / 0 for purely local launches).
 void launchBoxes(cudecompGridDesc_t gd, const std::vector<ResolvedBox>& boxes, int es, const SyncParams& sync,
-                 cudaStream_t stream) {
-  std::vector<CanonBox> canon;
-  std::vector<const ResolvedBox*> live;
-  for (auto& b : boxes) {
-    if (b.d.count() == 0) continue;
-    canon.push_back(canonicalize(b.d, true));
-    live.push_back(&b);
-  }
-  bool all_rows = true;
-  for (auto& c : canon)
-    if (!c.rowCopy()) all_rows = false;
-  if (all_rows) {
-    // keep row lengths addressable with 32-bit vector indices
-    for (size_t i = 0; i < canon.size(); ++i)
-      if (canon[i].n[0] * es / std::min(es, 16) >= (1ll << 31)) canon[i] = canonicalize(live[i]->d, false);
-    for (auto& c : canon)
-      if (!c.rowCopy()) all_rows = false;
-  }
-  KernelKind kind = all_rows ? KernelKind::ROWCOPY : KernelKind::TRANSPOSE;
-
-  int V = 16;
-  if (kind == KernelKind::ROWCOPY) {
-    uint64_t a = 16;
-    for (size_t i = 0; i < canon.size(); ++i) {
-      const CanonBox& c = canon[i];
-      const uint64_t sa = reinterpret_cast<uint64_t>(live[i]->src_base) + static_cast<uint64_t>(live[i]->d.src_off) * es;
-      const uint64_t da = reinterpret_cast<uint64_t>(live[i]->dst_base) + static_cast<uint64_t>(live[i]->d.dst_off) * es;
-      a = std::min({a, lowBit(sa), lowBit(da), lowBit(static_cast<uint64_t>(c.n[0]) * es)});
-      for (int k = 1; k < 3; ++k) {
-        if (c.n[k] > 1) a = std::min({a, lowBit(static_cast<uint64_t>(c.ss[k]) * es), lowBit(static_cast<uint64_t>(c.ds[k]) * es)});
-      }
-    }
-    V = static_cast<int>(std::min<uint64_t>(a, 16));
-    if (V < 4) THROW_INVALID_USAGE("buffers must be aligned to the element size");
-  }
-
-  // TMA bulk variant: only when every row is 16-byte aligned and long enough for one bulk copy to pay off
-  if (kind == KernelKind::ROWCOPY && gd->kernel_variant == 1 && V == 16) {
-    bool ok = !canon.empty();
-    for (auto& c : canon)
-      if (c.n[0] * es < 2048) ok = false;
-    if (ok) kind = KernelKind::ROWCOPY_BULK;
-  }
+                 cudaStream_t stream, int me = -1, int comm_size = 0) {
+  LaunchTuning tuning;
+  tuning.tile_bytes = gd->tile_bytes;
+  tuning.peer_order = gd->peer_order;
+  tuning.kernel_variant = gd->kernel_variant;
+  std::vector<PreparedLaunch> launches = prepareLaunches(boxes, es, tuning, me, comm_size);
 
   LaunchConfig cfg;
   cfg.grid = gd->grid_ctas;
+  cfg.balance = gd->balance_grid;
 
-  const size_t nlaunch = std::max<size_t>(1, (canon.size() + kMaxBoxes - 1) / kMaxBoxes);
-  for (size_t l = 0; l < nlaunch; ++l) {
-    CopyParams p;
-    std::memset(&p, 0, sizeof(p));
-    p.elem_size = static_cast<uint32_t>(es);
-    p.vec_size = static_cast<uint32_t>(V);
+  for (size_t l = 0; l < launches.size(); ++l) {
+    CopyParams& p = launches[l].params;
     p.sync = sync;
     p.sync.do_entry = (sync.npeers > 0 && l == 0) ? 1 : 0;
-    p.sync.do_exit = (sync.npeers > 0 && l + 1 == nlaunch) ? 1 : 0;
-    const size_t lo = l * kMaxBoxes, hi = std::min(canon.size(), lo + kMaxBoxes);
-    for (size_t i = lo; i < hi; ++i) {
-      const CanonBox& c = canon[i];
-      KBox& kb = p.box[p.nboxes++];
-      kb.src = live[i]->src_base + live[i]->d.src_off * es;
-      kb.dst = live[i]->dst_base + live[i]->d.dst_off * es;
-      if (kind == KernelKind::ROWCOPY || kind == KernelKind::ROWCOPY_BULK) {
-        for (int k = 0; k < 3; ++k) {
-          kb.n[k] = c.n[k];
-          kb.ss[k] = c.ss[k];
-          kb.ds[k] = c.ds[k];
-        }
-        fillRowCopy(kb, c, es, V, kind == KernelKind::ROWCOPY_BULK);
-      } else {
-        // axis 0: contiguous in the source; axis 1: contiguous in the destination when there is one
-        int a1 = c.dstUnitAxis();
-        if (a1 <= 0) a1 = (c.nd > 1) ? 1 : -1;
-        int a2 = -1;
-        for (int k = 1; k < c.nd; ++k)
-          if (k != a1) a2 = k;
-        const int map[3] = {0, a1, a2};
-        for (int k = 0; k < 3; ++k) {
-          kb.n[k] = (map[k] >= 0) ? c.n[map[k]] : 1;
-          kb.ss[k] = (map[k] >= 0) ? c.ss[map[k]] : 0;
-          kb.ds[k] = (map[k] >= 0) ? c.ds[map[k]] : 0;
-        }
-        kb.tiles0 = static_cast<uint32_t>((kb.n[0] + 31) / 32);
-        kb.tiles1 = static_cast<uint32_t>((kb.n[1] + 31) / 32);
-        const int64_t tiles = static_cast<int64_t>(kb.tiles0) * kb.tiles1 * kb.n[2];
-        if (tiles > 0x7fffffff) THROW_NOT_SUPPORTED("box too large for one launch");
-        kb.tiles = static_cast<uint32_t>(tiles);
-      }
-      p.max_tiles = std::max(p.max_tiles, kb.tiles);
-    }
-    if (static_cast<uint64_t>(p.nboxes) * p.max_tiles > 0xffffffffull) THROW_NOT_SUPPORTED("launch too large");
+    p.sync.do_exit = (sync.npeers > 0 && l + 1 == launches.size()) ? 1 : 0;
     if (p.nboxes == 0 && sync.npeers == 0) continue;
-    cudaError_t err = launchCopy(kind, p, cfg, stream);
+    cudaError_t err = launchCopy(launches[l].kind, p, cfg, stream);
     if (err != cudaSuccess) THROW_CUDA_ERROR(std::string("kernel launch failed: ") + cudaGetErrorString(err));
   }
 }
@@ -262,7 +168,7 @@ bool runPipelinedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int d
                                          : static_cast<char*>(h->peers.resolve(b.peer_world, msgs[b.peer].work));
       push.push_back({b, static_cast<const char*>(input), dst});
     }
-    launchBoxes(gd, push, es, sync, stream);
+    launchBoxes(gd, push, es, sync, stream, pp.base.me, pp.base.comm_size);
     if (s + 1 == K) PerfReport::markExchangeDone(perf, stream);
     if (pp.steps[s].unpack.empty()) continue;
     for (auto& b : pp.steps[s].unpack) unpack.push_back({b, static_cast<const char*>(work), static_cast<char*>(output)});
@@ -361,7 +267,7 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
                                        : static_cast<char*>(h->peers.resolve(b.peer_world, msgs[b.peer].data));
       boxes.push_back({b, static_cast<const char*>(input), dst});
     }
-    launchBoxes(gd, boxes, es, sync, stream);
+    launchBoxes(gd, boxes, es, sync, stream, probe.me, P);
   } else {
     gd->last_path = CUDECOMP_B200_PATH_STAGED;
     if (gd->pipeline_chunks > 1 &&
@@ -379,7 +285,7 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
     for (auto& b : st.unpack) unpack.push_back({b, static_cast<const char*>(work), static_cast<char*>(output)});
     SyncParams nosync;
     std::memset(&nosync, 0, sizeof(nosync));
-    launchBoxes(gd, push, es, sync, stream);
+    launchBoxes(gd, push, es, sync, stream, st.me, P);
     PerfReport::markExchangeDone(perf.sample, stream);
     launchBoxes(gd, unpack, es, nosync, stream);
   }
@@ -463,7 +369,7 @@ void runHalo(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, void* input, voi
                                        : static_cast<char*>(h->peers.resolve(b.peer_world, msgs[b.peer].data));
       boxes.push_back({b, static_cast<const char*>(input), dst});
     }
-    launchBoxes(gd, boxes, es, sync, stream);
+    launchBoxes(gd, boxes, es, sync, stream, probe.me, probe.comm_size);
   } else {
     gd->last_path = CUDECOMP_B200_PATH_STAGED;
     HaloPlan st = buildHaloPlan(gd->geom, gd->pidx, ax, dim, halo, periods, pad, DstKind::STAGE);
@@ -474,7 +380,7 @@ void runHalo(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, void* input, voi
       push.push_back({b, static_cast<const char*>(input), dst});
     }
     for (auto& b : st.unpack) unpack.push_back({b, static_cast<const char*>(work), static_cast<char*>(input)});
-    launchBoxes(gd, push, es, sync, stream);
+    launchBoxes(gd, push, es, sync, stream, st.me, st.comm_size);
     PerfReport::markExchangeDone(perf.sample, stream);
     launchBoxes(gd, unpack, es, nosync, stream);
   }

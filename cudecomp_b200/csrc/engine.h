@@ -46,6 +46,9 @@ struct cudecompHandle {
   cdb::PerfSettings perf;        // CUDECOMP_ENABLE_PERFORMANCE_REPORT and friends
   int pipeline_chunks = 0;       // CUDECOMP_B200_PIPELINE_CHUNKS: chunked schedule of staged transposes (0/1 = off)
   int kernel_variant = 0;        // CUDECOMP_B200_KERNEL=bulk -> 1: TMA bulk row copy where it applies (0 = LDG/STG)
+  int tile_bytes = 0;            // CUDECOMP_B200_TILE_BYTES
+  int peer_order = 0;            // CUDECOMP_B200_PEER_ORDER=pairwise -> 1
+  int balance_grid = 0;          // CUDECOMP_B200_BALANCE_GRID=1
   uint64_t release_count = 0;    // buffers freed through cudecompFree so far
   uint64_t released[cdb::kReleaseSlots] = {0}; // ids of the most recent ones, newest first
 };
@@ -70,6 +73,9 @@ struct cudecompGridDesc {
   // chunked (pipelined) staged schedule: unpack kernels run on a side stream beside the next chunk's push
   int pipeline_chunks = 0;
   int kernel_variant = 0; // 0: SIMT row copy, 1: TMA bulk row copy for 16-byte aligned rows of at least 2 KiB
+  int tile_bytes = 0;     // row-copy tile size (0: 32 KiB), see launch_params.h
+  int peer_order = 0;     // 0: slots interleaved over the peers (one-shot), 1: one peer after the other (pairwise rounds)
+  int balance_grid = 0;   // 1: pick the CTA count whose last grid-stride round is fullest (kernels.h chooseGrid)
   cudaStream_t side_stream = nullptr;
   std::vector<cudaEvent_t> side_events;
 };

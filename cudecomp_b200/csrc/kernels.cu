@@ -16,6 +16,8 @@
 
 #include <atomic>
 
+#include "tiling.h"
+
 namespace cdb {
 
 namespace {
@@ -100,7 +102,8 @@ template <typename V> __device__ __forceinline__ void storeStream(V* p, const V&
 // A tile is rows_per_tile rows x seg_vecs vectors (about 32 KiB); inside a tile each warp takes
 // 128-vector pieces (4 independent loads per lane in flight, then 4 stores).
 // ---------------------------------------------------------------------------------------------
-template <typename V> __global__ void __launch_bounds__(256) rowCopyKernel(const __grid_constant__ CopyParams p) {
+// kOrder: slot order (CopyParams::peer_order), a template parameter so that the default order keeps its register budget.
+template <typename V, int kOrder> __global__ void __launch_bounds__(256) rowCopyKernel(const __grid_constant__ CopyParams p) {
   syncEntry(p.sync);
 
   const uint32_t lane = threadIdx.x & 31u;
@@ -111,18 +114,16 @@ template <typename V> __global__ void __launch_bounds__(256) rowCopyKernel(const
   constexpr uint32_t kPiece = 32 * kUnroll;
 
   for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
-    const uint32_t b = t % p.nboxes;
-    const uint32_t j = t / p.nboxes;
+    uint32_t b, j;
+    slotToBoxTile(t, p.nboxes, p.max_tiles, static_cast<uint32_t>(kOrder), b, j);
     const KBox& bx = p.box[b];
     if (j >= bx.tiles) continue;
-    const uint32_t seg = j % bx.segs_per_row;
-    const uint32_t row_tile = j / bx.segs_per_row;
-    const int64_t row0 = static_cast<int64_t>(row_tile) * bx.rows_per_tile;
-    const int64_t nrows = bx.n[1] * bx.n[2];
-    const uint32_t c0 = seg * bx.seg_vecs;
-    const uint32_t nvec = min(bx.seg_vecs, bx.row_vecs - c0);
+    const RowTile rt = decodeRowTile(bx, j);
+    const int64_t row0 = rt.row0;
+    const uint32_t c0 = rt.c0;
+    const uint32_t nvec = rt.nvec;
+    const uint32_t rows_here = rt.rows_here;
     const uint32_t pieces_per_row = (nvec + kPiece - 1) / kPiece;
-    const uint32_t rows_here = static_cast<uint32_t>(min(static_cast<int64_t>(bx.rows_per_tile), nrows - row0));
     const uint32_t npieces = rows_here * pieces_per_row;
     const int64_t esz = p.elem_size;
 
@@ -140,11 +141,10 @@ template <typename V> __global__ void __launch_bounds__(256) rowCopyKernel(const
           if (e < total_vecs) {
             const uint32_t r = e / nvec;
             const uint32_t c = e - r * nvec;
-            const int64_t row = row0 + r;
-            const int64_t i1 = row % bx.n[1];
-            const int64_t i2 = row / bx.n[1];
-            v[k] = loadStream(reinterpret_cast<const V*>(bx.src + (i1 * bx.ss[1] + i2 * bx.ss[2]) * esz) + c0 + c);
-            dptr[k] = reinterpret_cast<V*>(bx.dst + (i1 * bx.ds[1] + i2 * bx.ds[2]) * esz) + c0 + c;
+            int64_t so, dof;
+            rowOffsets(bx, row0 + r, esz, so, dof);
+            v[k] = loadStream(reinterpret_cast<const V*>(bx.src + so) + c0 + c);
+            dptr[k] = reinterpret_cast<V*>(bx.dst + dof) + c0 + c;
           }
         }
 #pragma unroll
@@ -157,11 +157,10 @@ template <typename V> __global__ void __launch_bounds__(256) rowCopyKernel(const
     for (uint32_t pc = warp; pc < npieces; pc += nwarps) {
       const uint32_t r = pc / pieces_per_row;
       const uint32_t q = pc - r * pieces_per_row;
-      const int64_t row = row0 + r;
-      const int64_t i1 = row % bx.n[1];
-      const int64_t i2 = row / bx.n[1];
-      const V* s = reinterpret_cast<const V*>(bx.src + (i1 * bx.ss[1] + i2 * bx.ss[2]) * esz) + c0;
-      V* d = reinterpret_cast<V*>(bx.dst + (i1 * bx.ds[1] + i2 * bx.ds[2]) * esz) + c0;
+      int64_t so, dof;
+      rowOffsets(bx, row0 + r, esz, so, dof);
+      const V* s = reinterpret_cast<const V*>(bx.src + so) + c0;
+      V* d = reinterpret_cast<V*>(bx.dst + dof) + c0;
       const uint32_t base = q * kPiece + lane;
       V v[kUnroll];
 #pragma unroll
@@ -185,7 +184,7 @@ template <typename V> __global__ void __launch_bounds__(256) rowCopyKernel(const
 // axis-contiguous layouts). 32x32 element tiles through shared memory: coalesced on both sides.
 // T is the element itself (4, 8 or 16 bytes).
 // ---------------------------------------------------------------------------------------------
-template <typename T> __global__ void __launch_bounds__(256) transposeKernel(const __grid_constant__ CopyParams p) {
+template <typename T, int kOrder> __global__ void __launch_bounds__(256) transposeKernel(const __grid_constant__ CopyParams p) {
   __shared__ T tile[32][33];
   syncEntry(p.sync);
 
@@ -194,13 +193,14 @@ template <typename T> __global__ void __launch_bounds__(256) transposeKernel(con
   const uint32_t total = p.nboxes * p.max_tiles;
 
   for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
-    const uint32_t b = t % p.nboxes;
-    const uint32_t j = t / p.nboxes;
+    uint32_t b, j;
+    slotToBoxTile(t, p.nboxes, p.max_tiles, static_cast<uint32_t>(kOrder), b, j);
     const KBox& bx = p.box[b];
     if (j < bx.tiles) { // uniform per CTA
-      const uint32_t j0 = j % bx.tiles0;
-      const uint32_t j1 = (j / bx.tiles0) % bx.tiles1;
-      const int64_t i2 = j / (bx.tiles0 * bx.tiles1);
+      const TransTile tt = decodeTransposeTile(bx, j);
+      const uint32_t j0 = tt.j0;
+      const uint32_t j1 = tt.j1;
+      const int64_t i2 = tt.i2;
       const T* s = reinterpret_cast<const T*>(bx.src) + i2 * bx.ss[2];
       T* d = reinterpret_cast<T*>(bx.dst) + i2 * bx.ds[2];
       {
@@ -274,19 +274,16 @@ __global__ void __launch_bounds__(32) rowCopyBulkKernel(const __grid_constant__ 
 
     // decode launch tile t -> (source, destination, bytes); false when the slot is empty for that box
     auto decode = [&](uint32_t t, const char*& src, char*& dst, uint32_t& bytes) -> bool {
-      const uint32_t b = t % p.nboxes;
-      const uint32_t j = t / p.nboxes;
+      uint32_t b, j;
+      slotToBoxTile(t, p.nboxes, p.max_tiles, p.peer_order, b, j);
       const KBox& bx = p.box[b];
       if (j >= bx.tiles) return false;
-      const uint32_t seg = j % bx.segs_per_row;
-      const int64_t row = j / bx.segs_per_row; // rows_per_tile == 1
-      const int64_t i1 = row % bx.n[1];
-      const int64_t i2 = row / bx.n[1];
-      const uint32_t c0 = seg * bx.seg_vecs;
-      const uint32_t nvec = min(bx.seg_vecs, bx.row_vecs - c0);
-      src = bx.src + (i1 * bx.ss[1] + i2 * bx.ss[2]) * esz + static_cast<int64_t>(c0) * 16;
-      dst = bx.dst + (i1 * bx.ds[1] + i2 * bx.ds[2]) * esz + static_cast<int64_t>(c0) * 16;
-      bytes = nvec * 16u;
+      const RowTile rt = decodeRowTile(bx, j); // rows_per_tile == 1: one row segment
+      int64_t so, dof;
+      rowOffsets(bx, rt.row0, esz, so, dof);
+      src = bx.src + so + static_cast<int64_t>(rt.c0) * 16;
+      dst = bx.dst + dof + static_cast<int64_t>(rt.c0) * 16;
+      bytes = rt.nvec * 16u;
       return true;
     };
 
@@ -335,23 +332,27 @@ namespace {
 
 using KernelFn = void (*)(const CopyParams);
 
-KernelFn pickKernel(KernelKind kind, int size) {
+template <int kOrder> KernelFn pickKernelOrdered(KernelKind kind, int size) {
   if (kind == KernelKind::ROWCOPY) {
     switch (size) {
-    case 16: return rowCopyKernel<uint4>;
-    case 8: return rowCopyKernel<uint2>;
-    case 4: return rowCopyKernel<uint32_t>;
+    case 16: return rowCopyKernel<uint4, kOrder>;
+    case 8: return rowCopyKernel<uint2, kOrder>;
+    case 4: return rowCopyKernel<uint32_t, kOrder>;
     }
   } else if (kind == KernelKind::TRANSPOSE) {
     switch (size) {
-    case 16: return transposeKernel<uint4>;
-    case 8: return transposeKernel<uint2>;
-    case 4: return transposeKernel<uint32_t>;
+    case 16: return transposeKernel<uint4, kOrder>;
+    case 8: return transposeKernel<uint2, kOrder>;
+    case 4: return transposeKernel<uint32_t, kOrder>;
     }
   } else if (size == 16) {
     return rowCopyBulkKernel;
   }
   return nullptr;
+}
+
+KernelFn pickKernel(KernelKind kind, int size, uint32_t peer_order = 0) {
+  return peer_order ? pickKernelOrdered<1>(kind, size) : pickKernelOrdered<0>(kind, size);
 }
 
 } // namespace
@@ -391,10 +392,8 @@ static cudaError_t launchBulk(const CopyParams& p, const LaunchConfig& cfg, cuda
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const uint64_t total = static_cast<uint64_t>(p.nboxes) * p.max_tiles;
-  int grid = cfg.grid > 0 ? cfg.grid : sms; // one TMA-driving CTA per SM (3 fit by shared memory)
-  if (grid > 3 * sms) grid = 3 * sms;
-  if (static_cast<uint64_t>(grid) > total) grid = static_cast<int>(total);
-  if (grid < 1) grid = 1;
+  // one TMA-driving CTA per SM by default (3 fit by shared memory)
+  const int grid = chooseGrid(cfg.grid, sms, 3 * sms, total, cfg.balance);
   rowCopyBulkKernel<<<grid, 32, smem, stream>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
@@ -403,24 +402,19 @@ static cudaError_t launchBulk(const CopyParams& p, const LaunchConfig& cfg, cuda
 cudaError_t launchCopy(KernelKind kind, const CopyParams& p, const LaunchConfig& cfg, cudaStream_t stream) {
   if (kind == KernelKind::ROWCOPY_BULK) return launchBulk(p, cfg, stream);
   const int size = (kind == KernelKind::ROWCOPY) ? static_cast<int>(p.vec_size) : static_cast<int>(p.elem_size);
-  KernelFn fn = pickKernel(kind, size);
+  KernelFn fn = pickKernel(kind, size, p.peer_order);
   if (!fn) return cudaErrorInvalidValue;
   const uint64_t total = static_cast<uint64_t>(p.nboxes) * p.max_tiles;
-  int grid = cfg.grid;
   const int resident = maxResidentCtas(kind, size, cfg.threads);
   if (resident <= 0) return cudaErrorInvalidDevice;
-  if (grid <= 0) {
-    // Measured on B200 (profiles/r1_n1_cta_sweep.txt): HBM streams best with a moderate number of CTAs in flight;
-    // filling every resident slot costs 6-8 % of copy bandwidth. 2.5 CTAs/SM for the row copy, 4/SM for the
-    // shared-memory transpose. NVLink-bound launches are insensitive to the count (profiles/r1_n2_sweep.txt).
-    int sms = 0, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    grid = (kind == KernelKind::ROWCOPY) ? (5 * sms) / 2 : 4 * sms;
-  }
-  if (grid > resident) grid = resident;
-  if (static_cast<uint64_t>(grid) > total) grid = static_cast<int>(total);
-  if (grid < 1) grid = 1; // still runs the handshake when this rank has nothing to move
+  // Measured on B200 (profiles/r1_n1_cta_sweep.txt): HBM streams best with a moderate number of CTAs in flight;
+  // filling every resident slot costs 6-8 % of copy bandwidth. 2.5 CTAs/SM for the row copy, 4/SM for the
+  // shared-memory transpose. NVLink-bound launches are insensitive to the count (profiles/r1_n2_sweep.txt).
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int dflt = (kind == KernelKind::ROWCOPY) ? (5 * sms) / 2 : 4 * sms;
+  const int grid = chooseGrid(cfg.grid, dflt, resident, total, cfg.balance);
   fn<<<grid, cfg.threads, 0, stream>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();

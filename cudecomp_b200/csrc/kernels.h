@@ -61,9 +61,11 @@ struct CopyParams {
   KBox box[kMaxBoxes];
   SyncParams sync;
   uint32_t nboxes;
-  uint32_t max_tiles; // max over boxes; tile t of the launch -> box t % nboxes, tile t / nboxes
+  uint32_t max_tiles; // max over boxes; slot t of the launch -> (box, tile) by slotToBoxTile (tiling.h)
   uint32_t elem_size; // 4, 8 or 16
   uint32_t vec_size;  // ROWCOPY: 4, 8 or 16
+  uint32_t peer_order; // slot order: 0 interleaved over the boxes (one-shot), 1 rounds, one peer after the other (pairwise)
+  uint32_t pad_[3];
 };
 
 // ROWCOPY_BULK: the row copy driven by the TMA unit instead of LDG/STG: one elected thread per CTA moves row segments
@@ -75,9 +77,14 @@ constexpr int kBulkStages = 4;
 constexpr uint32_t kBulkChunkBytes = 16384;
 
 struct LaunchConfig {
-  int grid = 0;    // CTAs (0: library default = all SMs x resident CTAs)
+  int grid = 0;    // CTAs (0: library default, see defaultGrid)
   int threads = 256;
+  int balance = 0; // 1: shrink the grid (by at most 20 %) to the CTA count whose last round of slots is fullest
 };
+
+// CTA count of a launch: `requested` (0: `dflt`), capped by the resident CTAs and the slot count; with balance != 0
+// the count in [0.8 * that, that] that wastes the least of its last grid-stride round (ties: the larger count).
+int chooseGrid(int requested, int dflt, int resident, uint64_t total_slots, int balance);
 
 // Enqueues the copy described by `p` on `stream`. Returns the CUDA status of the launch.
 cudaError_t launchCopy(KernelKind kind, const CopyParams& p, const LaunchConfig& cfg, cudaStream_t stream);

@@ -1,0 +1,160 @@
+// See launch_params.h.
+#include "launch_params.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "errors.h"
+
+namespace cdb {
+
+namespace {
+
+uint64_t lowBit(uint64_t x) { return x ? (x & (~x + 1)) : (1ull << 62); }
+
+void fillRowCopy(KBox& kb, const CanonBox& c, int es, int V, uint32_t tile_bytes, bool bulk) {
+  // SIMT: tiles of tile_bytes (several short rows or one segment of a long row); bulk: one row segment of <= 16 KiB
+  const uint32_t tile_vecs = (bulk ? kBulkChunkBytes : tile_bytes) / static_cast<uint32_t>(V);
+  kb.row_vecs = static_cast<uint32_t>(c.n[0] * es / V);
+  kb.seg_vecs = std::min(kb.row_vecs, tile_vecs);
+  if (kb.seg_vecs == 0) kb.seg_vecs = 1;
+  kb.segs_per_row = (kb.row_vecs + kb.seg_vecs - 1) / kb.seg_vecs;
+  kb.rows_per_tile = bulk ? 1u : std::max(1u, tile_vecs / kb.seg_vecs);
+  const int64_t rows = c.n[1] * c.n[2];
+  const int64_t row_tiles = (rows + kb.rows_per_tile - 1) / kb.rows_per_tile;
+  const int64_t tiles = (c.n[0] == 0) ? 0 : row_tiles * kb.segs_per_row;
+  if (tiles > 0x7fffffff) THROW_NOT_SUPPORTED("box too large for one launch");
+  kb.tiles = static_cast<uint32_t>(tiles);
+  kb.tiles0 = kb.tiles1 = 0;
+}
+
+} // namespace
+
+std::vector<PreparedLaunch> prepareLaunches(const std::vector<LaunchBox>& boxes, int es, const LaunchTuning& tuning, int me,
+                                            int comm_size) {
+  std::vector<CanonBox> canon;
+  std::vector<const LaunchBox*> live;
+  for (auto& b : boxes) {
+    if (b.d.count() == 0) continue;
+    live.push_back(&b);
+  }
+  if (tuning.peer_order == 1 && comm_size > 1 && me >= 0)
+    std::stable_sort(live.begin(), live.end(), [&](const LaunchBox* x, const LaunchBox* y) {
+      return ((x->d.peer - me) % comm_size + comm_size) % comm_size < ((y->d.peer - me) % comm_size + comm_size) % comm_size;
+    });
+  for (auto* b : live) canon.push_back(canonicalize(b->d, true));
+
+  bool all_rows = true;
+  for (auto& c : canon)
+    if (!c.rowCopy()) all_rows = false;
+  if (all_rows) {
+    // keep row lengths addressable with 32-bit vector indices
+    for (size_t i = 0; i < canon.size(); ++i)
+      if (canon[i].n[0] * es / std::min(es, 16) >= (1ll << 31)) canon[i] = canonicalize(live[i]->d, false);
+    for (auto& c : canon)
+      if (!c.rowCopy()) all_rows = false;
+  }
+  KernelKind kind = all_rows ? KernelKind::ROWCOPY : KernelKind::TRANSPOSE;
+
+  int V = 16;
+  if (kind == KernelKind::ROWCOPY) {
+    uint64_t a = 16;
+    for (size_t i = 0; i < canon.size(); ++i) {
+      const CanonBox& c = canon[i];
+      const uint64_t sa = reinterpret_cast<uint64_t>(live[i]->src_base) + static_cast<uint64_t>(live[i]->d.src_off) * es;
+      const uint64_t da = reinterpret_cast<uint64_t>(live[i]->dst_base) + static_cast<uint64_t>(live[i]->d.dst_off) * es;
+      a = std::min({a, lowBit(sa), lowBit(da), lowBit(static_cast<uint64_t>(c.n[0]) * es)});
+      for (int k = 1; k < 3; ++k) {
+        if (c.n[k] > 1) a = std::min({a, lowBit(static_cast<uint64_t>(c.ss[k]) * es), lowBit(static_cast<uint64_t>(c.ds[k]) * es)});
+      }
+    }
+    V = static_cast<int>(std::min<uint64_t>(a, 16));
+    if (V < 4) THROW_INVALID_USAGE("buffers must be aligned to the element size");
+  }
+
+  // TMA bulk variant: only when every row is 16-byte aligned and long enough for one bulk copy to pay off
+  if (kind == KernelKind::ROWCOPY && tuning.kernel_variant == 1 && V == 16) {
+    bool ok = !canon.empty();
+    for (auto& c : canon)
+      if (c.n[0] * es < 2048) ok = false;
+    if (ok) kind = KernelKind::ROWCOPY_BULK;
+  }
+
+  uint32_t tile_bytes = static_cast<uint32_t>(tuning.tile_bytes > 0 ? tuning.tile_bytes : kDefaultTileBytes);
+  tile_bytes = std::min<uint32_t>(std::max<uint32_t>(tile_bytes, kMinTileBytes), kMaxTileBytes);
+
+  std::vector<PreparedLaunch> out;
+  const size_t nlaunch = std::max<size_t>(1, (canon.size() + kMaxBoxes - 1) / kMaxBoxes);
+  for (size_t l = 0; l < nlaunch; ++l) {
+    PreparedLaunch pl;
+    pl.kind = kind;
+    CopyParams& p = pl.params;
+    std::memset(&p, 0, sizeof(p));
+    p.elem_size = static_cast<uint32_t>(es);
+    p.vec_size = static_cast<uint32_t>(V);
+    p.peer_order = (tuning.peer_order == 1) ? 1u : 0u;
+    const size_t lo = l * kMaxBoxes, hi = std::min(canon.size(), lo + kMaxBoxes);
+    for (size_t i = lo; i < hi; ++i) {
+      const CanonBox& c = canon[i];
+      KBox& kb = p.box[p.nboxes++];
+      kb.src = live[i]->src_base + live[i]->d.src_off * es;
+      kb.dst = live[i]->dst_base + live[i]->d.dst_off * es;
+      if (kind == KernelKind::ROWCOPY || kind == KernelKind::ROWCOPY_BULK) {
+        for (int k = 0; k < 3; ++k) {
+          kb.n[k] = c.n[k];
+          kb.ss[k] = c.ss[k];
+          kb.ds[k] = c.ds[k];
+        }
+        fillRowCopy(kb, c, es, V, tile_bytes, kind == KernelKind::ROWCOPY_BULK);
+      } else {
+        // axis 0: contiguous in the source; axis 1: contiguous in the destination when there is one
+        int a1 = c.dstUnitAxis();
+        if (a1 <= 0) a1 = (c.nd > 1) ? 1 : -1;
+        int a2 = -1;
+        for (int k = 1; k < c.nd; ++k)
+          if (k != a1) a2 = k;
+        const int map[3] = {0, a1, a2};
+        for (int k = 0; k < 3; ++k) {
+          kb.n[k] = (map[k] >= 0) ? c.n[map[k]] : 1;
+          kb.ss[k] = (map[k] >= 0) ? c.ss[map[k]] : 0;
+          kb.ds[k] = (map[k] >= 0) ? c.ds[map[k]] : 0;
+        }
+        kb.tiles0 = static_cast<uint32_t>((kb.n[0] + 31) / 32);
+        kb.tiles1 = static_cast<uint32_t>((kb.n[1] + 31) / 32);
+        const int64_t tiles = static_cast<int64_t>(kb.tiles0) * kb.tiles1 * kb.n[2];
+        if (tiles > 0x7fffffff) THROW_NOT_SUPPORTED("box too large for one launch");
+        kb.tiles = static_cast<uint32_t>(tiles);
+      }
+      p.max_tiles = std::max(p.max_tiles, kb.tiles);
+    }
+    if (static_cast<uint64_t>(p.nboxes) * p.max_tiles > 0xffffffffull) THROW_NOT_SUPPORTED("launch too large");
+    out.push_back(pl);
+  }
+  return out;
+}
+
+int chooseGrid(int requested, int dflt, int resident, uint64_t total_slots, int balance) {
+  int grid = requested > 0 ? requested : dflt;
+  if (grid > resident) grid = resident;
+  if (static_cast<uint64_t>(grid) > total_slots) grid = static_cast<int>(total_slots);
+  if (grid < 1) return 1; // still runs the handshake when this rank has nothing to move
+  if (balance && total_slots > static_cast<uint64_t>(grid)) {
+    // rounds(g) = ceil(slots / g); utilisation of a launch = slots / (g * rounds(g)). Among the counts within 20 % of
+    // the chosen one take the best utilisation: the slowest CTA sets the launch time, and a last round that occupies a
+    // handful of CTAs costs a whole tile time (a 512^3 complex64 pencil is only 11 rounds of 32 KiB tiles).
+    int best = grid;
+    double best_u = 0.0;
+    for (int g = grid; g >= std::max(1, grid - grid / 5); --g) {
+      const uint64_t rounds = (total_slots + g - 1) / g;
+      const double u = static_cast<double>(total_slots) / (static_cast<double>(g) * static_cast<double>(rounds));
+      if (u > best_u + 1e-12) {
+        best_u = u;
+        best = g;
+      }
+    }
+    grid = best;
+  }
+  return grid;
+}
+
+} // namespace cdb

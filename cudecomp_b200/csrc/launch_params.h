@@ -1,0 +1,45 @@
+// From transfer boxes to kernel launch parameters: kernel selection, vector width, tiling. Pure host arithmetic on
+// whatever base pointers it is given, so the same code prepares real launches (engine.cc) and the launches that the
+// host-side emulator under tests/host_emu/ walks on numpy buffers.
+#ifndef CUDECOMP_B200_LAUNCH_PARAMS_H
+#define CUDECOMP_B200_LAUNCH_PARAMS_H
+
+#include <vector>
+
+#include "kernels.h"
+#include "plan.h"
+
+namespace cdb {
+
+struct LaunchBox {
+  BoxDesc d;
+  const char* src_base;
+  char* dst_base;
+};
+
+// Per-descriptor schedule knobs (cudecompB200SetSchedule / SetKernelVariant); the autotuner sweeps them.
+struct LaunchTuning {
+  int tile_bytes = 0;     // bytes of a ROWCOPY tile (0: kDefaultTileBytes); power of two in [4 KiB, 256 KiB]
+  int peer_order = 0;     // CopyParams::peer_order
+  int kernel_variant = 0; // 1: TMA bulk row copy where every row is 16-byte aligned and at least 2 KiB long
+};
+
+constexpr int kDefaultTileBytes = 32768;
+constexpr int kMinTileBytes = 4096;
+constexpr int kMaxTileBytes = 262144;
+
+struct PreparedLaunch {
+  KernelKind kind;
+  CopyParams params; // sync block zeroed: the caller fills it in
+};
+
+// Splits `boxes` (all of element size `es`) into launches of at most kMaxBoxes boxes. Empty boxes are dropped; the
+// result always holds at least one launch (possibly with nboxes == 0) because a launch also carries the handshake.
+// `me` / `comm_size`: this rank's index in the communicator the boxes' `peer` fields refer to; only used to order the
+// boxes for peer_order == 1 (self first, then me+1, me+2, ... cyclically). Pass comm_size <= 1 to keep the given order.
+std::vector<PreparedLaunch> prepareLaunches(const std::vector<LaunchBox>& boxes, int es, const LaunchTuning& tuning, int me,
+                                            int comm_size);
+
+} // namespace cdb
+
+#endif

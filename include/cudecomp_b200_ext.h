@@ -40,6 +40,15 @@ cudecompResult_t cudecompB200SetTuning(cudecompHandle_t handle, cudecompGridDesc
  * kernel is not yet confirmed on hardware). */
 cudecompResult_t cudecompB200SetKernelVariant(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t variant);
 
+/* Launch schedule of the copy kernels. tile_bytes: size of a row-copy tile, 0 (= 32 KiB) or a power of two in
+ * [4096, 262144] -- small grids want small tiles (more grid-stride rounds, shorter tail). peer_order: 0 = consecutive
+ * tiles go to different peers for the whole launch ("one-shot"), 1 = the GPU works through its peers one after the
+ * other, me+1 first ("pairwise rounds"; the local share stays interleaved). balance_grid != 0: the CTA count is reduced
+ * by up to 20 % to the value whose last grid-stride round is fullest. Also CUDECOMP_B200_TILE_BYTES,
+ * CUDECOMP_B200_PEER_ORDER=pairwise, CUDECOMP_B200_BALANCE_GRID=1. Any value gives identical results. */
+cudecompResult_t cudecompB200SetSchedule(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t tile_bytes,
+                                         int32_t peer_order, int32_t balance_grid);
+
 /* Chunked schedule of staged transposes (in-place calls, NVSHMEM-family backends, non-exportable outputs): the pencil
  * is pushed in `nchunks` chunks and unpacking overlaps the next chunk's push (csrc/plan.h PipelinedPlan). 0 or 1 = off
  * (default; also settable for all descriptors with CUDECOMP_B200_PIPELINE_CHUNKS). Same value on every rank.

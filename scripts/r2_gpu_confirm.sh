@@ -1,0 +1,57 @@
+# usage: gpurun [--gpus N] -- 'bash scripts/r2_gpu_confirm.sh N'
+# First GPU call of the next round: confirms on hardware everything that was written after the round-1 GPU budget was
+# spent (the tests/test_zz_* files report XPASS when the code works), then measures the opt-in schedules so that their
+# defaults can be decided from numbers. Everything lands in gpurun_out/r2_*.{log,json}; copy what matters to profiles/.
+mkdir -p gpurun_out
+N=${1:-1}
+OUT=gpurun_out
+echo "== unconfirmed code paths (XPASS = confirmed)"
+timeout 1500 python -m pytest tests/test_zz_api_contract_gpu.py tests/test_zz_perf_report_gpu.py tests/test_zz_pipeline_gpu.py \
+  tests/test_zz_ref_benchmark_gpu.py tests/test_zz_schedule_gpu.py -q -m gpu -rxX -p no:cacheprovider > $OUT/r2_zz_tests.log 2>&1
+tail -40 $OUT/r2_zz_tests.log
+
+i=0
+bench() { # label, extra args...
+  label=$1; shift
+  i=$((i+1))
+  if [ "$N" = 1 ]; then
+    timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline "$@" > $OUT/r2_n${N}_$label.log 2>&1
+  else
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+      --master-port $((29500+i*10)) bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline "$@" > $OUT/r2_n${N}_$label.log 2>&1
+  fi
+  grep '"metric"' $OUT/r2_n${N}_$label.log | tee $OUT/r2_n${N}_$label.json | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); r = d['roofline']
+    print('$label:', round(d['ms_per_step'], 3), 'ms/step;', d['path'], {k: round(v, 3) for k, v in r['per_op_ms'].items()},
+          r['bound'], round(r['achieved'], 1), 'GB/s frac', round(r['frac'], 4))" || tail -5 $OUT/r2_n${N}_$label.log
+}
+
+echo "== default schedules, N=$N"
+bench default --no-e2e
+bench inplace --no-e2e --inplace
+echo "== chunked in-place schedule (cudecompB200SetPipelineChunks)"
+for k in 2 4 8 16; do bench inplace_chunks$k --no-e2e --inplace --chunks $k; done
+echo "== TMA bulk row copy (cudecompB200SetKernelVariant)"
+bench bulk --no-e2e --bulk
+bench bulk_inplace_chunks8 --no-e2e --bulk --inplace --chunks 8
+echo "== tile size / peer order / balanced grid (cudecompB200SetSchedule)"
+for t in 16384 65536; do bench tile$t --no-e2e --tile-bytes $t; done
+bench pairwise --no-e2e --peer-order 1
+bench balanced --no-e2e --balance-grid 1
+echo "== 512^3 complex64 (BASELINE config 2): handshake- and tail-sensitive"
+bench c64_512 --no-e2e --grid 512 --dtype float_complex
+for t in 8192 16384; do bench c64_512_tile$t --no-e2e --grid 512 --dtype float_complex --tile-bytes $t; done
+bench c64_512_balanced --no-e2e --grid 512 --dtype float_complex --balance-grid 1
+bench c64_512_balanced_tile16k --no-e2e --grid 512 --dtype float_complex --balance-grid 1 --tile-bytes 16384
+
+if [ "$N" = 1 ]; then
+  echo "== ncu: launch list and one full capture of the transpose (permuting) kernel, axis-contiguous layout"
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/r2_n1_launches_ac.csv \
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --axis-contiguous > $OUT/r2_n1_ncu_ac.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:transposeKernel -c 1 -o $OUT/r2_n1_transpose_full \
+    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --axis-contiguous > $OUT/r2_n1_ncu_ac_full.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:rowCopyBulkKernel -c 1 -o $OUT/r2_n1_bulk_full \
+    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --bulk > $OUT/r2_n1_ncu_bulk_full.log 2>&1
+fi
