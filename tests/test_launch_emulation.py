@@ -1,0 +1,268 @@
+"""The copy kernels' index arithmetic, checked without a GPU.
+
+tests/host_emu walks every launch the way the device does -- launches prepared by the product's own host code
+(csrc/launch_params.cc), slots and tiles decoded by the very functions the kernels are compiled from (csrc/tiling.h),
+warps and lanes restated from csrc/kernels.cu -- on numpy buffers, with every access checked for alignment and bounds.
+For random decompositions, element sizes, buffer alignments, tile sizes, slot orders, kernel variants and grid sizes
+the outcome of all ranks' launches must equal the oracle byte for byte, and every destination byte must be written
+exactly once. This covers what the -m gpu parity tests cover for the default schedule, and it is the only pre-hardware
+check of the opt-in schedules (pairwise slot order, other tile sizes, the TMA bulk variant's 16-byte rules).
+"""
+import os
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+from cudecomp_b200 import capi as cd
+from oracle import oracle as orc
+from tests import host_emu as emu
+from tests.test_planner_properties import OPS, decompositions, make_config, make_oracle
+
+EXAMPLES = int(os.environ.get("CDB_HYPOTHESIS_EXAMPLES", "150"))
+DT = {4: np.int32, 8: np.int64, 16: np.complex128}
+
+
+def rand_fill(arr, rng):
+    if arr.dtype == np.complex128:
+        arr[:] = rng.integers(1, 1 << 30, arr.size) + 1j * rng.integers(1, 1 << 30, arr.size)
+    else:
+        arr[:] = rng.integers(1, 1 << 30, arr.size)
+
+
+@st.composite
+def schedules(draw):
+    return dict(es=draw(st.sampled_from([4, 8, 16])), tile_bytes=draw(st.sampled_from([0, 4096, 8192, 16384, 65536])),
+                peer_order=draw(st.sampled_from([0, 1])), kernel_variant=draw(st.sampled_from([0, 1])),
+                grid=draw(st.sampled_from([0, 1, 3, 7, 64])), threads=draw(st.sampled_from([256, 128, 64])),
+                misalign=draw(st.sampled_from([0, 0, 1, 2, 3])))
+
+
+@st.composite
+def long_row_decompositions(draw):
+    """One long axis (rows of several KiB: the warp-per-piece path, rows cut into segments, the bulk variant), the
+    other two short; at most 4 ranks so that the examples stay small."""
+    d = draw(decompositions())
+    d["pdims"] = list(draw(st.sampled_from([(1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (1, 4), (4, 1)])))
+    k = draw(st.integers(0, 2))
+    d["gdims"] = [draw(st.integers(1, 5)) for _ in range(3)]
+    d["gdims"][k] = draw(st.sampled_from([96, 128, 250, 256, 515, 640, 1030]))
+    d["gdims_dist"] = None
+    return d
+
+
+def group_index(plans):
+    """communicator index of a destination rank = its position among the destinations of the push boxes"""
+    world = sorted({b["peer_rank"] for b in plans if not b["is_unpack"]})
+    return {w: i for i, w in enumerate(world)}
+
+
+def emulate(boxes, src_of, dst_of, legal, s, me=-1, comm=0, peer_index=None):
+    if not boxes:
+        return dict(bytes_written=0, kinds=0, launches=0)
+    return emu.run_boxes(boxes, [src_of(b) for b in boxes], [dst_of(b) for b in boxes], s["es"], legal, me=me,
+                         comm_size=comm, peer_index=peer_index, tile_bytes=s["tile_bytes"], peer_order=s["peer_order"],
+                         kernel_variant=s["kernel_variant"], grid=s["grid"], threads=s["threads"])
+
+
+@settings(max_examples=EXAMPLES, deadline=None, suppress_health_check=list(HealthCheck))
+@given(decompositions(), schedules())
+def test_emulated_transposes_equal_oracle(d, s):
+    check_transposes(d, s)
+
+
+@settings(max_examples=EXAMPLES, deadline=None, suppress_health_check=list(HealthCheck))
+@given(long_row_decompositions(), schedules())
+def test_emulated_transposes_with_long_rows_equal_oracle(d, s):
+    check_transposes(d, s)
+
+
+def check_transposes(d, s):
+    cfg, o = make_config(d), make_oracle(d)
+    n = o.nranks
+    dt = DT[s["es"]]
+    off = s["misalign"] * s["es"]  # buffers start at a multiple of the element size past a 256-byte boundary
+    rng = np.random.default_rng(3)
+    for op, (ax, direction) in OPS.items():
+        a, b = orc.transpose_axes(op)
+        if o.has_empty_pencils(a) or o.has_empty_pencils(b):
+            continue
+        ha, hb, pa, pb = d["halos"][str(a)], d["halos"][str(b)], d["pads"][str(a)], d["pads"][str(b)]
+        ins = [emu.aligned_array(o.pencil_info(r, a, ha, pa).size, dt, off) for r in range(n)]
+        for x in ins:
+            rand_fill(x, rng)
+        want = [np.full(o.pencil_info(r, b, hb, pb).size, -3, dt) for r in range(n)]
+        o.transpose(op, ins, want, ha, hb, pa, pb)
+        for staged in (False, True):
+            plans = [cd.plan_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, staged) for r in range(n)]
+            outs = [emu.aligned_array(w.size, dt, off, -3) for w in want]
+            works = [emu.aligned_array(max(o.transpose_workspace_size(), 1), dt, 0, -9) for _ in range(n)]
+            legal = ins + outs + works
+            moved = 0
+            for r in range(n):
+                push = [bx for bx in plans[r] if not bx["is_unpack"]]
+                gi = group_index(plans[r])
+                st_ = emulate(push, lambda bx: ins[r], lambda bx: (works if staged else outs)[bx["peer_rank"]], legal, s,
+                              me=gi[r], comm=len(gi), peer_index=[gi[bx["peer_rank"]] for bx in push])
+                moved += st_["bytes_written"]
+                assert st_["bytes_written"] == sum(int(np.prod(bx["extent"])) for bx in push) * s["es"], (d, s, op, r)
+            if staged:
+                for r in range(n):
+                    unpack = [bx for bx in plans[r] if bx["is_unpack"]]
+                    st_ = emulate(unpack, lambda bx: works[r], lambda bx: outs[r], legal, s)
+                    assert st_["bytes_written"] == sum(int(np.prod(bx["extent"])) for bx in unpack) * s["es"]
+            assert moved == sum(o.pencil_info(r, a).size for r in range(n)) * s["es"]  # every interior cell exactly once
+            for r in range(n):
+                assert np.array_equal(outs[r], want[r]), (d, s, op, staged, r)
+
+
+@settings(max_examples=EXAMPLES, deadline=None, suppress_health_check=list(HealthCheck))
+@given(decompositions(), schedules(), st.lists(st.integers(0, 3), min_size=3, max_size=3),
+       st.lists(st.booleans(), min_size=3, max_size=3), st.lists(st.integers(0, 2), min_size=3, max_size=3))
+def test_emulated_halos_equal_oracle(d, s, halo, periods, padding):
+    cfg, o = make_config(d), make_oracle(d)
+    n = o.nranks
+    dt = DT[s["es"]]
+    rng = np.random.default_rng(13)
+    for ax in range(3):
+        if o.has_empty_pencils(ax):
+            continue
+        data = [emu.aligned_array(o.pencil_info(r, ax, halo, padding).size, dt, s["misalign"] * s["es"]) for r in range(n)]
+        for x in data:
+            rand_fill(x, rng)
+        for staged in (False, True):
+            mine = [emu.aligned_array(x.size, dt, s["misalign"] * s["es"], 0) for x in data]
+            for m, x in zip(mine, data):
+                m[:] = x
+            ref = [x.copy() for x in data]
+            for dim in range(3):
+                try:
+                    o.halo(ax, dim, ref, halo, periods, padding)
+                except RuntimeError:
+                    break  # halo wider than a slab: covered by test_planner_properties
+                plans = [cd.plan_halo_boxes(cfg, r, ax, dim, halo, periods, padding, staged) for r in range(n)]
+                works = [emu.aligned_array(max(o.halo_workspace_size(r, ax, halo), 1), dt, 0, -9) for r in range(n)]
+                snap = [emu.aligned_array(x.size, dt, s["misalign"] * s["es"], 0) for x in mine]
+                for sn, m in zip(snap, mine):
+                    sn[:] = m
+                legal = mine + works + snap
+                for r in range(n):
+                    push = [bx for bx in plans[r] if not bx["is_unpack"]]
+                    emulate(push, lambda bx: snap[r], lambda bx: (works if staged else mine)[bx["peer_rank"]], legal, s)
+                if staged:
+                    for r in range(n):
+                        unpack = [bx for bx in plans[r] if bx["is_unpack"]]
+                        emulate(unpack, lambda bx: works[r], lambda bx: mine[r], legal, s)
+                for r in range(n):
+                    assert np.array_equal(mine[r], ref[r]), (d, s, ax, dim, staged, r, halo, periods, padding)
+
+
+@settings(max_examples=max(EXAMPLES // 3, 20), deadline=None, suppress_health_check=list(HealthCheck))
+@given(decompositions(), schedules(), st.sampled_from([2, 3, 4, 8]), st.booleans())
+def test_emulated_pipelined_schedule_equals_oracle(d, s, K, inplace):
+    """The chunked schedule executed step by step (engine.cc runPipelinedStaged): push launches of step k, then the
+    unpack launches of step k, every launch through the emulator."""
+    cfg, o = make_config(d), make_oracle(d)
+    n = o.nranks
+    dt = DT[s["es"]]
+    for op, (ax, direction) in OPS.items():
+        a, b = orc.transpose_axes(op)
+        if o.has_empty_pencils(a) or o.has_empty_pencils(b):
+            continue
+        ha, hb, pa, pb = d["halos"][str(a)], d["halos"][str(b)], d["pads"][str(a)], d["pads"][str(b)]
+        plans = [cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, inplace, K) for r in range(n)]
+        if not any(plans):
+            continue
+        rng = np.random.default_rng(5)
+        sizes = [max(o.pencil_info(r, a, ha, pa).size, o.pencil_info(r, b, hb, pb).size) for r in range(n)]
+        bufs = [emu.aligned_array(sizes[r], dt, 0, -3) for r in range(n)]
+        for r in range(n):
+            rand_fill(bufs[r][:o.pencil_info(r, a, ha, pa).size], rng)
+        ref_in = [x.copy() for x in bufs]
+        ref_out = ref_in if inplace else [np.full(sizes[r], -3, dt) for r in range(n)]
+        o.transpose(op, ref_in, ref_out, ha, hb, pa, pb)
+        outs = bufs if inplace else [emu.aligned_array(sizes[r], dt, 0, -3) for r in range(n)]
+        works = [emu.aligned_array(max(o.transpose_workspace_size(), 1), dt, 0, -9) for _ in range(n)]
+        legal = bufs + outs + works
+        for step in range(K):
+            for r in range(n):
+                push = [bx for bx in plans[r] if bx["step"] == step and not bx["is_unpack"]]
+                gi = group_index(plans[r])
+                emulate(push, lambda bx: bufs[r], lambda bx: works[bx["peer_rank"]], legal, s, me=gi.get(r, -1), comm=len(gi),
+                        peer_index=[gi[bx["peer_rank"]] for bx in push])
+            for r in range(n):
+                unpack = [bx for bx in plans[r] if bx["step"] == step and bx["is_unpack"]]
+                emulate(unpack, lambda bx: works[r], lambda bx: outs[r], legal, s)
+        for r in range(n):
+            assert np.array_equal(outs[r], ref_out[r]), (d, s, op, K, inplace, r)
+
+
+def test_kernel_selection_and_vector_width():
+    """Default-layout transposes are row copies at the widest vector the alignment allows; differing memory orders go
+    through the tiled transpose kernel; the bulk variant only takes over for 16-byte aligned rows of at least 2 KiB."""
+    d = dict(gdims=[256, 8, 6], pdims=[2, 1], axis_contiguous=[False] * 3, mem_order=None, gdims_dist=None, col_major=False,
+             halos={str(a): [0, 0, 0] for a in range(3)}, pads={str(a): [0, 0, 0] for a in range(3)})
+    cfg, o = make_config(d), make_oracle(d)
+
+    def run(es, variant, misalign=0, dd=d, cfg_=cfg, o_=o):
+        dt = DT[es]
+        ins = [emu.aligned_array(o_.pencil_info(r, 0).size, dt, misalign) for r in range(2)]
+        outs = [emu.aligned_array(o_.pencil_info(r, 1).size, dt, misalign) for r in range(2)]
+        push = cd.plan_transpose_boxes(cfg_, 0, 0, 1)
+        return emu.run_boxes(push, [ins[0]] * len(push), [outs[bx["peer_rank"]] for bx in push], es, ins + outs,
+                             kernel_variant=variant, me=0, comm_size=2, peer_index=[0, 1])
+
+    st16 = run(16, 0)
+    assert st16["kinds"] == 1 and st16["vec"] == 16
+    assert run(4, 0)["vec"] == 16          # 128 floats per row: still 16-byte vectors
+    assert run(8, 0, misalign=8)["vec"] == 8  # buffers only 8-byte aligned
+    assert run(4, 0, misalign=4)["vec"] == 4
+    assert run(16, 1)["kinds"] == 4        # rows of 128 x 16 B = 2 KiB: TMA bulk
+    assert run(8, 1)["kinds"] == 1         # 1 KiB rows: stays SIMT
+    assert run(16, 1)["accesses"] == 2 * 4 * 6   # one bulk copy per row segment: 2 peers x (4 x 6) rows of my pencil
+    # axis-contiguous layouts permute: the tiled transpose kernel
+    d2 = dict(d, axis_contiguous=[True] * 3)
+    cfg2, o2 = make_config(d2), make_oracle(d2)
+    assert run(8, 0, dd=d2, cfg_=cfg2, o_=o2)["kinds"] == 2
+
+
+def test_slot_orders_are_permutations():
+    import ctypes
+    lib = emu.lib()
+    for nboxes, max_tiles in [(1, 5), (2, 7), (4, 1), (4, 33), (8, 9), (16, 3)]:
+        for order in (0, 1):
+            seen = set()
+            for t in range(nboxes * max_tiles):
+                b, j = ctypes.c_uint32(), ctypes.c_uint32()
+                lib.cdb_emu_slot(ctypes.c_uint32(t), ctypes.c_uint32(nboxes), ctypes.c_uint32(max_tiles),
+                                 ctypes.c_uint32(order), ctypes.byref(b), ctypes.byref(j))
+                assert b.value < nboxes and j.value < max_tiles
+                seen.add((b.value, j.value))
+            assert len(seen) == nboxes * max_tiles
+    # pairwise: between two local slots the remote slots walk one peer after the other
+    nboxes, max_tiles = 4, 30
+    order = []
+    for t in range(nboxes * max_tiles):
+        b, j = ctypes.c_uint32(), ctypes.c_uint32()
+        lib.cdb_emu_slot(ctypes.c_uint32(t), ctypes.c_uint32(nboxes), ctypes.c_uint32(max_tiles), ctypes.c_uint32(1),
+                         ctypes.byref(b), ctypes.byref(j))
+        if b.value:
+            order.append(b.value)
+    assert order == sorted(order) and order.count(1) == order.count(2) == order.count(3) == max_tiles
+
+
+def test_balanced_grid():
+    g = emu.lib().cdb_emu_choose_grid
+    assert g(0, 370, 444, 4096, 0) == 370                 # default: 2.5 CTAs per SM
+    assert g(0, 370, 444, 100, 0) == 100                  # never more CTAs than slots
+    assert g(1000, 370, 444, 1 << 20, 0) == 444           # capped by residency
+    assert g(0, 370, 444, 0, 0) == 1                      # an empty launch still handshakes
+    b = g(0, 370, 444, 4096, 1)                           # 4096 slots: 12 full rounds of 342 CTAs instead of 11.07 of 370
+    assert 296 <= b <= 370 and -(-4096 // b) * b - 4096 < 10
+    assert g(0, 370, 444, 370 * 50, 1) == 370             # already even: unchanged
+    for slots in (371, 1000, 4097, 65536, 99991):
+        b = g(0, 370, 444, slots, 1)
+        assert 296 <= b <= 370
+        util = lambda c: slots / (c * -(-slots // c))
+        assert util(b) >= util(370) - 1e-12
