@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--bulk", action="store_true", help="TMA bulk row-copy variant (experimental)")
     ap.add_argument("--chunks", type=int, default=0, help="chunked schedule of staged transposes (experimental)")
+    ap.add_argument("--tile-bytes", type=int, default=0, help="row-copy tile size (0 = 32 KiB)")
+    ap.add_argument("--peer-order", type=int, default=0, help="0 one-shot interleaved, 1 pairwise rounds")
+    ap.add_argument("--balance-grid", type=int, default=0, help="1: CTA count with the fullest last grid-stride round")
     return ap.parse_args()
 
 
@@ -227,6 +230,8 @@ def run_native(args, rank, world, local_rank):
         cd.check(cd.set_kernel_variant(handle, gd, 1))
     if args.chunks:
         cd.check(cd.set_pipeline_chunks(handle, gd, args.chunks))
+    if args.tile_bytes or args.peer_order or args.balance_grid:
+        cd.check(cd.set_schedule(handle, gd, args.tile_bytes, args.peer_order, bool(args.balance_grid)))
 
     sizes = [cd.cudecompGetPencilInfo(handle, gd, ax)[1].size for ax in range(3)]
     S = sizes[0] * es  # bytes of this rank's pencil (equal for the three orientations on even grids)

@@ -194,6 +194,7 @@ _sig("cudecompB200SetTuning", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_
 _sig("cudecompB200CheckErrors", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t])
 _sig("cudecompB200SetPipelineChunks", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32])
 _sig("cudecompB200SetKernelVariant", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32])
+_sig("cudecompB200SetSchedule", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32, _i32, _i32])
 _sig("cudecompB200DescribeTransposeBoxes", _i32,
      [cudecompHandle_t, cudecompGridDesc_t, _i32, _i32, _i32p, _i32p, _i32p, _i32p, _i32, _P(cudecompB200Box_t), _i32])
 _sig("cudecompB200DescribeHaloBoxes", _i32,
@@ -445,6 +446,10 @@ def set_tuning(handle, grid_desc, grid_ctas=0, force_staged=False):
 
 def set_kernel_variant(handle, grid_desc, variant):
     return lib.cudecompB200SetKernelVariant(handle, grid_desc, int(variant))
+
+
+def set_schedule(handle, grid_desc, tile_bytes=0, peer_order=0, balance_grid=False):
+    return lib.cudecompB200SetSchedule(handle, grid_desc, int(tile_bytes), int(peer_order), 1 if balance_grid else 0)
 
 
 def set_pipeline_chunks(handle, grid_desc, nchunks):

@@ -189,3 +189,20 @@ def test_product_fails_loudly_without_gpu(handle):
     assert cd.cudecompTransposeXToY(handle, gd, addr, addr + 4096, addr, cd.CUDECOMP_FLOAT) == cd.CUDECOMP_RESULT_CUDA_ERROR
     assert cd.cudecompMalloc(handle, gd, 1024)[0] == cd.CUDECOMP_RESULT_CUDA_ERROR
     cd.cudecompGridDescDestroy(handle, gd)
+
+
+def test_schedule_knobs_validate_their_arguments(handle):
+    res, gd = cd.cudecompGridDescCreate(handle, _config())
+    assert res == 0
+    INV = cd.CUDECOMP_RESULT_INVALID_USAGE
+    assert cd.set_schedule(handle, gd, 0, 0, False) == 0
+    assert cd.set_schedule(handle, gd, 16384, 1, True) == 0
+    assert cd.set_schedule(handle, gd, 3000, 0, False) == INV      # not a power of two
+    assert cd.set_schedule(handle, gd, 2048, 0, False) == INV      # below 4 KiB
+    assert cd.set_schedule(handle, gd, 1 << 20, 0, False) == INV   # above 256 KiB
+    assert cd.set_schedule(handle, gd, 0, 2, False) == INV
+    assert cd.set_schedule(None, gd, 0, 0, False) == INV
+    assert cd.set_kernel_variant(handle, gd, 2) == INV
+    assert cd.set_pipeline_chunks(handle, gd, 65) == INV
+    assert cd.set_pipeline_chunks(handle, gd, 8) == 0
+    cd.cudecompGridDescDestroy(handle, gd)

@@ -1,0 +1,39 @@
+"""Opt-in launch schedules on the GPU (cudecompB200SetSchedule): tile sizes, the pairwise slot order and the balanced
+grid must give byte-identical results to the default schedule. Their index arithmetic is property-tested on the host
+(tests/test_launch_emulation.py walks the same launches with the kernels' own decode functions); the device run was
+written after the round-1 GPU budget was spent, hence xfail(strict=False): an XPASS is the hardware confirmation."""
+import pytest
+
+from tests._launcher import run_ranks
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="device execution not yet confirmed on hardware")]
+
+BASE = dict(kind="transpose", ops=["XY", "YZ", "ZY", "YX"])
+CASES = [
+    dict(BASE, name="Pairwise_oop_2x2_c128", gdims=[64, 40, 48], pdims=[2, 2], dtype="double_complex", out_of_place=True,
+         peer_order=1),
+    dict(BASE, name="Pairwise_oop_1x4_uneven_float", gdims=[31, 30, 29], pdims=[1, 4], dtype="float", out_of_place=True,
+         peer_order=1),
+    dict(BASE, name="Pairwise_inplace_4x1_axis_contiguous", gdims=[32, 40, 48], pdims=[4, 1], dtype="double",
+         axis_contiguous=[True] * 3, peer_order=1),
+    dict(BASE, name="Tile4k_oop_2x2_long_rows", gdims=[1030, 12, 10], pdims=[2, 2], dtype="double_complex",
+         out_of_place=True, tile_bytes=4096),
+    dict(BASE, name="Tile64k_balanced_inplace_2x2", gdims=[96, 40, 48], pdims=[2, 2], dtype="float_complex",
+         tile_bytes=65536, balance_grid=1),
+    dict(BASE, name="Pairwise_tile8k_balanced_halo_padding", gdims=[48, 32, 40], pdims=[2, 2], dtype="double",
+         out_of_place=True, peer_order=1, tile_bytes=8192, balance_grid=1,
+         halos={"0": [1, 1, 1], "1": [1, 1, 1], "2": [1, 1, 1]}, pads={"0": [1, 0, 0], "1": [0, 1, 0], "2": [0, 0, 2]}),
+    dict(BASE, name="Pairwise_bulk_oop_2x2", gdims=[256, 24, 20], pdims=[2, 2], dtype="double_complex", out_of_place=True,
+         peer_order=1, kernel_variant=1),
+]
+
+
+@pytest.fixture(scope="module")
+def schedule_results():
+    return run_ranks(4, "gpu", CASES, timeout=900)[0]
+
+
+@pytest.mark.parametrize("i", range(len(CASES)), ids=[c["name"] for c in CASES])
+def test_opt_in_schedules(schedule_results, i):
+    bad = ["rank %d: %s" % (r, schedule_results[r][i].get("msg")) for r in range(4) if not schedule_results[r][i]["ok"]]
+    assert not bad, "\n".join(bad)
