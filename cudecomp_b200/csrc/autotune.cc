@@ -19,6 +19,7 @@
 
 #include "engine.h"
 #include "errors.h"
+#include "launch_params.h"
 
 namespace cdb {
 
@@ -196,6 +197,77 @@ struct Events {
 
 const int kOps[4][2] = {{0, 1}, {1, 1}, {2, -1}, {1, -1}}; // XY, YZ, ZY, YX as (ax, dir)
 
+// What is swept per (process grid, schedule family) besides the reference's dimensions: the launch schedule of the one
+// engine (BASELINE north star: "tile shape / CTA count / one-shot-vs-pairwise").
+struct Schedule {
+  int ctas = 0;       // CTAs per launch (0: library default)
+  int tile_bytes = 0; // row-copy tile (0: 32 KiB)
+  int peer_order = 0; // 0 one-shot interleaved, 1 pairwise rounds
+  int balance = 0;    // balanced grid
+  int chunks = 0;     // chunked staged schedule (in-place / staged calls)
+  int variant = 0;    // 1: TMA bulk row copy
+};
+
+void applySchedule(cudecompGridDesc_t gd, const Schedule& s) {
+  gd->grid_ctas = s.ctas;
+  gd->tile_bytes = s.tile_bytes;
+  gd->peer_order = s.peer_order;
+  gd->balance_grid = s.balance;
+  gd->pipeline_chunks = s.chunks;
+  gd->kernel_variant = s.variant;
+}
+
+Schedule currentSchedule(const cudecompGridDesc_t gd) {
+  Schedule s;
+  s.ctas = gd->grid_ctas;
+  s.tile_bytes = gd->tile_bytes;
+  s.peer_order = gd->peer_order;
+  s.balance = gd->balance_grid;
+  s.chunks = gd->pipeline_chunks;
+  s.variant = gd->kernel_variant;
+  return s;
+}
+
+std::string describeSchedule(const Schedule& s) {
+  std::string d = "CTAs: " + std::to_string(s.ctas) + ", tile: " + std::to_string(s.tile_bytes ? s.tile_bytes : kDefaultTileBytes) +
+                  ", order: " + (s.peer_order ? "pairwise" : "one-shot");
+  if (s.balance) d += ", balanced grid";
+  if (s.chunks > 1) d += ", chunks: " + std::to_string(s.chunks);
+  if (s.variant) d += ", TMA bulk";
+  return d;
+}
+
+// CUDECOMP_B200_AUTOTUNE_SCHEDULES: which schedule dimensions the second tuning phase explores on the winning
+// (grid, family): comma list of tile, order, balance, chunks, bulk, or "all". The CTA count is always swept (phase 1).
+// Default: none -- the dimensions below were added after the round-1 hardware budget was spent and join the default
+// sweep once confirmed on hardware.
+struct ScheduleDims {
+  bool tile = false, order = false, balance = false, chunks = false, bulk = false;
+};
+
+ScheduleDims scheduleDimsFromEnvironment() {
+  ScheduleDims d;
+  const char* v = std::getenv("CUDECOMP_B200_AUTOTUNE_SCHEDULES");
+  if (!v) return d;
+  const std::string s(v);
+  size_t start = 0;
+  while (start <= s.size()) {
+    size_t end = s.find(',', start);
+    if (end == std::string::npos) end = s.size();
+    const std::string name = s.substr(start, end - start);
+    if (name == "all") d.tile = d.order = d.balance = d.chunks = d.bulk = true;
+    else if (name == "tile") d.tile = true;
+    else if (name == "order") d.order = true;
+    else if (name == "balance") d.balance = true;
+    else if (name == "chunks") d.chunks = true;
+    else if (name == "bulk") d.bulk = true;
+    else if (!name.empty())
+      THROW_INVALID_USAGE("CUDECOMP_B200_AUTOTUNE_SCHEDULES contains unknown schedule dimension '" + name + "'");
+    start = end + 1;
+  }
+  return d;
+}
+
 void autotuneTransposes(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecompGridDescAutotuneOptions_t* o,
                         bool tune_pdims, bool tune_backend) {
   const double t_start = MPI_Wtime();
@@ -244,7 +316,8 @@ void autotuneTransposes(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecom
   double t_best = std::numeric_limits<double>::max();
   std::array<int32_t, 2> best_grid{0, 0};
   int best_backend = backends[0];
-  int best_ctas = 0;
+  const Schedule saved_schedule = currentSchedule(gd);
+  Schedule best_schedule = saved_schedule;
   bool valid = false;
 
   if (!h->have_device) {
@@ -269,9 +342,81 @@ void autotuneTransposes(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecom
     }
     cudaStream_t stream = 0;
     Events ev(5);
-    const int saved_ctas = gd->grid_ctas;
     const bool saved_staged = gd->force_staged;
 
+    // Times the enabled operations on the geometry / backend / schedule currently set on `gd` with the reference's
+    // protocol and prints the candidate block. Returns the rank-averaged weighted time, or a negative value when the
+    // candidate was abandoned after its first trial (skip_threshold). Collective.
+    auto timeCandidate = [&](const std::array<int32_t, 2>& p, const Schedule& sched) -> double {
+      applySchedule(gd, sched);
+      auto runOp = [&](int op) {
+        void* in = data.p;
+        void* out = o->transpose_use_inplace_buffers[op] ? data.p : data2.p;
+        runTranspose(h, gd, kOps[op][0], kOps[op][1], in, out, work.p, o->dtype, o->transpose_input_halo_extents[op],
+                     o->transpose_output_halo_extents[op], o->transpose_input_padding[op],
+                     o->transpose_output_padding[op], stream);
+      };
+      for (int w = 0; w < o->n_warmup_trials; ++w)
+        for (int op = 0; op < 4; ++op)
+          if (o->transpose_op_weights[op] != 0.0) runOp(op);
+      CHECK_CUDA(cudaStreamSynchronize(stream));
+
+      std::vector<double> total, total_w;
+      std::vector<double> per_op[4];
+      bool skipped = false;
+      for (int t = 0; t < o->n_trials; ++t) {
+        CHECK_CUDA(cudaEventRecord(ev.ev[0], stream));
+        for (int op = 0; op < 4; ++op) {
+          if (o->transpose_op_weights[op] != 0.0) runOp(op);
+          CHECK_CUDA(cudaEventRecord(ev.ev[op + 1], stream));
+        }
+        CHECK_CUDA(cudaStreamSynchronize(stream));
+        double tt = 0, tw = 0;
+        for (int op = 0; op < 4; ++op) {
+          float ms = 0;
+          CHECK_CUDA(cudaEventElapsedTime(&ms, ev.ev[op], ev.ev[op + 1]));
+          per_op[op].push_back(ms);
+          tt += ms;
+          tw += ms * o->transpose_op_weights[op];
+        }
+        total.push_back(tt);
+        total_w.push_back(tw);
+        if (t == 0 && o->skip_threshold > 0.0) {
+          // agree across ranks whether this configuration is hopeless (reference src/autotune.cc:578-602)
+          double first = tw;
+          allreduceF64(*h->comm, &first, 1, ReduceOp::SUM);
+          first /= h->nranks;
+          if (o->skip_threshold * first > t_best) {
+            skipped = true;
+            break;
+          }
+        }
+      }
+      const std::string desc = describeSchedule(sched);
+      if (skipped) {
+        if (h->rank == 0)
+          std::printf("CUDECOMP:\tgrid: %d x %d, backend: %s, %s \nCUDECOMP:\t(skipped) \n", p[0], p[1],
+                      cudecompTransposeCommBackendToString(gd->config.transpose_comm_backend), desc.c_str());
+        return -1.0;
+      }
+      Stats st = reduceTimes(h, total), sw = reduceTimes(h, total_w);
+      Stats so[4];
+      for (int op = 0; op < 4; ++op) so[op] = reduceTimes(h, per_op[op]);
+      if (h->rank == 0) {
+        std::printf("CUDECOMP:\tgrid: %d x %d, backend: %s, %s \n"
+                    "CUDECOMP:\tTotal time min/max/avg/std [ms]: %f/%f/%f/%f\n"
+                    "CUDECOMP:\t           min/max/avg/std [ms]: %f/%f/%f/%f (weighted)\n",
+                    p[0], p[1], cudecompTransposeCommBackendToString(gd->config.transpose_comm_backend), desc.c_str(), st.min,
+                    st.max, st.avg, st.std, sw.min, sw.max, sw.avg, sw.std);
+        const char* names[4] = {"XY", "YZ", "ZY", "YX"};
+        for (int op = 0; op < 4; ++op)
+          std::printf("CUDECOMP:\tTranspose%s time min/max/avg/std [ms]: %f/%f/%f/%f%s\n", names[op], so[op].min, so[op].max,
+                      so[op].avg, so[op].std, o->transpose_op_weights[op] == 0.0 ? " (skipped)" : "");
+      }
+      return sw.avg;
+    };
+
+    // ---- phase 1 (reference protocol): process grid x schedule family x CTA count
     for (auto& p : grids) {
       if (!gridUsable(gd, p, o->allow_uneven_decompositions)) continue;
       valid = true;
@@ -281,88 +426,85 @@ void autotuneTransposes(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecom
       for (int backend : backends) {
         gd->config.transpose_comm_backend = static_cast<cudecompTransposeCommBackend_t>(backend);
         gd->force_staged = backendIsStaged(backend);
-        // CTA counts to try: everything resident, and one / two CTAs per SM
-        std::vector<int> cta_list = {0};
+        // CTA counts to try: the library default, and two / one CTAs per SM
+        std::vector<int> cta_list = {saved_schedule.ctas};
         if (tune_backend && h->sm_count > 0) {
-          cta_list.push_back(2 * h->sm_count);
-          cta_list.push_back(h->sm_count);
+          cta_list = {0, 2 * h->sm_count, h->sm_count};
         }
         for (int ctas : cta_list) {
-          gd->grid_ctas = ctas;
-          auto runOp = [&](int op) {
-            void* in = data.p;
-            void* out = o->transpose_use_inplace_buffers[op] ? data.p : data2.p;
-            runTranspose(h, gd, kOps[op][0], kOps[op][1], in, out, work.p, o->dtype,
-                         o->transpose_input_halo_extents[op], o->transpose_output_halo_extents[op],
-                         o->transpose_input_padding[op], o->transpose_output_padding[op], stream);
-          };
-          for (int w = 0; w < o->n_warmup_trials; ++w)
-            for (int op = 0; op < 4; ++op)
-              if (o->transpose_op_weights[op] != 0.0) runOp(op);
-          CHECK_CUDA(cudaStreamSynchronize(stream));
-
-          std::vector<double> total, total_w;
-          std::vector<double> per_op[4];
-          bool skipped = false;
-          for (int t = 0; t < o->n_trials; ++t) {
-            CHECK_CUDA(cudaEventRecord(ev.ev[0], stream));
-            for (int op = 0; op < 4; ++op) {
-              if (o->transpose_op_weights[op] != 0.0) runOp(op);
-              CHECK_CUDA(cudaEventRecord(ev.ev[op + 1], stream));
-            }
-            CHECK_CUDA(cudaStreamSynchronize(stream));
-            double tt = 0, tw = 0;
-            for (int op = 0; op < 4; ++op) {
-              float ms = 0;
-              CHECK_CUDA(cudaEventElapsedTime(&ms, ev.ev[op], ev.ev[op + 1]));
-              per_op[op].push_back(ms);
-              tt += ms;
-              tw += ms * o->transpose_op_weights[op];
-            }
-            total.push_back(tt);
-            total_w.push_back(tw);
-            if (t == 0 && o->skip_threshold > 0.0) {
-              // agree across ranks whether this configuration is hopeless (reference src/autotune.cc:578-602)
-              double first = tw;
-              allreduceF64(*h->comm, &first, 1, ReduceOp::SUM);
-              first /= h->nranks;
-              if (o->skip_threshold * first > t_best) {
-                skipped = true;
-                break;
-              }
-            }
-          }
-          if (skipped) {
-            if (h->rank == 0)
-              std::printf("CUDECOMP:\tgrid: %d x %d, backend: %s, CTAs: %d \nCUDECOMP:\t(skipped) \n", p[0], p[1],
-                          cudecompTransposeCommBackendToString(gd->config.transpose_comm_backend), ctas);
-            continue;
-          }
-          Stats st = reduceTimes(h, total), sw = reduceTimes(h, total_w);
-          Stats so[4];
-          for (int op = 0; op < 4; ++op) so[op] = reduceTimes(h, per_op[op]);
-          if (h->rank == 0) {
-            std::printf("CUDECOMP:\tgrid: %d x %d, backend: %s, CTAs: %d \n"
-                        "CUDECOMP:\tTotal time min/max/avg/std [ms]: %f/%f/%f/%f\n"
-                        "CUDECOMP:\t           min/max/avg/std [ms]: %f/%f/%f/%f (weighted)\n",
-                        p[0], p[1], cudecompTransposeCommBackendToString(gd->config.transpose_comm_backend), ctas,
-                        st.min, st.max, st.avg, st.std, sw.min, sw.max, sw.avg, sw.std);
-            const char* names[4] = {"XY", "YZ", "ZY", "YX"};
-            for (int op = 0; op < 4; ++op)
-              std::printf("CUDECOMP:\tTranspose%s time min/max/avg/std [ms]: %f/%f/%f/%f%s\n", names[op], so[op].min,
-                          so[op].max, so[op].avg, so[op].std,
-                          o->transpose_op_weights[op] == 0.0 ? " (skipped)" : "");
-          }
-          if (sw.avg < t_best) {
-            t_best = sw.avg;
+          Schedule sched = saved_schedule;
+          sched.ctas = ctas;
+          const double t = timeCandidate(p, sched);
+          if (t >= 0 && t < t_best) {
+            t_best = t;
             best_grid = p;
             best_backend = backend;
-            best_ctas = ctas;
+            best_schedule = sched;
           }
         }
       }
     }
-    gd->grid_ctas = saved_ctas;
+
+    // ---- phase 2: the launch schedule of the winner, one dimension after the other (greedy); an alternative is kept
+    // when it is faster than everything seen so far
+    const ScheduleDims dims = scheduleDimsFromEnvironment();
+    if (valid && tune_backend && t_best < std::numeric_limits<double>::max() &&
+        (dims.tile || dims.order || dims.balance || dims.chunks || dims.bulk)) {
+      setGeometry(gd, best_grid);
+      if (gd->mbox.valid()) gd->mbox.reset(*h->comm);
+      gd->config.transpose_comm_backend = static_cast<cudecompTransposeCommBackend_t>(best_backend);
+      gd->force_staged = backendIsStaged(best_backend);
+      bool any_inplace = false;
+      for (int op = 0; op < 4; ++op)
+        if (o->transpose_op_weights[op] != 0.0 && o->transpose_use_inplace_buffers[op]) any_inplace = true;
+      std::vector<Schedule> alternatives;
+      auto tryAlternatives = [&]() {
+        for (const Schedule& alt : alternatives) {
+          const double t = timeCandidate(best_grid, alt);
+          if (t >= 0 && t < t_best) {
+            t_best = t;
+            best_schedule = alt;
+          }
+        }
+        alternatives.clear();
+      };
+      if (dims.tile) {
+        for (int tb : {16384, 65536}) {
+          Schedule a = best_schedule;
+          a.tile_bytes = tb;
+          alternatives.push_back(a);
+        }
+        tryAlternatives();
+      }
+      if (dims.order) {
+        Schedule a = best_schedule;
+        a.peer_order = 1;
+        alternatives.push_back(a);
+        tryAlternatives();
+      }
+      if (dims.balance) {
+        Schedule a = best_schedule;
+        a.balance = 1;
+        alternatives.push_back(a);
+        tryAlternatives();
+      }
+      if (dims.chunks && (any_inplace || backendIsStaged(best_backend))) {
+        for (int k : {4, 8}) {
+          Schedule a = best_schedule;
+          a.chunks = k;
+          alternatives.push_back(a);
+        }
+        tryAlternatives();
+      }
+      if (dims.bulk) {
+        Schedule a = best_schedule;
+        a.variant = 1;
+        alternatives.push_back(a);
+        tryAlternatives();
+      }
+    }
+
+    applySchedule(gd, saved_schedule);
     gd->force_staged = saved_staged;
     CHECK_CUDA(cudaDeviceSynchronize());
     // our device buffers are about to be freed: every peer drops its imports of them first
@@ -375,12 +517,14 @@ void autotuneTransposes(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecom
   gd->config.pdims[0] = best_grid[0];
   gd->config.pdims[1] = best_grid[1];
   gd->config.transpose_comm_backend = static_cast<cudecompTransposeCommBackend_t>(best_backend);
-  if (tune_backend) gd->grid_ctas = best_ctas;
+  if (tune_backend) applySchedule(gd, best_schedule);
   gd->force_staged = false;
-  if (h->rank == 0)
+  if (h->rank == 0) {
     std::printf("CUDECOMP: SELECTED: grid: %d x %d, backend: %s, Avg. time (weighted) [ms]: %f\n", best_grid[0],
                 best_grid[1], cudecompTransposeCommBackendToString(gd->config.transpose_comm_backend),
                 h->have_device ? t_best : 0.0);
+    if (tune_backend && h->have_device) std::printf("CUDECOMP: SELECTED schedule: %s\n", describeSchedule(best_schedule).c_str());
+  }
   barrier(*h->comm);
   if (h->rank == 0) std::printf("CUDECOMP: transpose autotuning time [s]: %f\n", MPI_Wtime() - t_start);
 }

@@ -55,3 +55,13 @@ if [ "$N" = 1 ]; then
   ncu --set full --clock-control none --import-source on -k regex:rowCopyBulkKernel -c 1 -o $OUT/r2_n1_bulk_full \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --bulk > $OUT/r2_n1_ncu_bulk_full.log 2>&1
 fi
+
+if [ "$N" != 1 ]; then
+  echo "== autotune 768^3 with the schedule dimensions in the sweep (CUDECOMP_B200_AUTOTUNE_SCHEDULES=all)"
+  CUDECOMP_B200_AUTOTUNE_SCHEDULES=all timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N \
+    --master-addr 127.0.0.1 --master-port 29990 scripts/autotune_bench.py --grid 768 --backend > $OUT/r2_n${N}_autotune_all.log 2>&1
+  grep -E "SELECTED|\"autotune\"" $OUT/r2_n${N}_autotune_all.log
+  CUDECOMP_B200_AUTOTUNE_SCHEDULES=all timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N \
+    --master-addr 127.0.0.1 --master-port 29980 scripts/autotune_bench.py --grid 768 --backend --inplace > $OUT/r2_n${N}_autotune_all_inplace.log 2>&1
+  grep -E "SELECTED|\"autotune\"" $OUT/r2_n${N}_autotune_all_inplace.log
+fi
