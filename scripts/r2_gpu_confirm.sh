@@ -7,7 +7,7 @@ N=${1:-1}
 OUT=gpurun_out
 echo "== unconfirmed code paths (XPASS = confirmed)"
 timeout 1500 python -m pytest tests/test_zz_api_contract_gpu.py tests/test_zz_perf_report_gpu.py tests/test_zz_pipeline_gpu.py \
-  tests/test_zz_ref_benchmark_gpu.py tests/test_zz_schedule_gpu.py -q -m gpu -rxX -p no:cacheprovider > $OUT/r2_zz_tests.log 2>&1
+  tests/test_zz_ref_benchmark_gpu.py tests/test_zz_schedule_gpu.py tests/test_zz_nccl_crosscheck_gpu.py -q -m gpu -rxX -p no:cacheprovider > $OUT/r2_zz_tests.log 2>&1
 tail -40 $OUT/r2_zz_tests.log
 
 i=0
@@ -64,4 +64,16 @@ if [ "$N" != 1 ]; then
   CUDECOMP_B200_AUTOTUNE_SCHEDULES=all timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N \
     --master-addr 127.0.0.1 --master-port 29980 scripts/autotune_bench.py --grid 768 --backend --inplace > $OUT/r2_n${N}_autotune_all_inplace.log 2>&1
   grep -E "SELECTED|\"autotune\"" $OUT/r2_n${N}_autotune_all_inplace.log
+fi
+
+if [ "$N" != 1 ]; then
+  echo "== GPU-side baseline: the reference's NCCL arm restated (pack + NCCL all-to-all + unpack), same metric"
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29970 \
+    bench/nccl_restated.py --grid 1024 --out $OUT/r2_n${N}_nccl_restated.json > $OUT/r2_n${N}_nccl_restated.log 2>&1
+  grep '^{' $OUT/r2_n${N}_nccl_restated.log || tail -5 $OUT/r2_n${N}_nccl_restated.log
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29960 \
+    bench/nccl_restated.py --grid 512 --dtype float_complex > $OUT/r2_n${N}_nccl_restated_512.log 2>&1
+  grep '^{' $OUT/r2_n${N}_nccl_restated_512.log || tail -5 $OUT/r2_n${N}_nccl_restated_512.log
+  timeout 900 python -m pytest tests/test_zz_nccl_crosscheck_gpu.py -q -m gpu -rxXs -p no:cacheprovider > $OUT/r2_n${N}_nccl_crosscheck.log 2>&1
+  tail -5 $OUT/r2_n${N}_nccl_crosscheck.log
 fi

@@ -420,6 +420,73 @@ def shim_battery(rank, nranks):
     return out
 
 
+_restated = None
+
+
+def nccl_crosscheck_case(gpu, handle, rank, case):
+    """The library against the reference's NCCL arm restated with torch ops + NCCL all-to-all (bench/nccl_restated.py):
+    same seeded input, every op of the chain compared byte for byte. Needs one GPU per rank."""
+    global _restated
+    import importlib.util
+    torch = gpu.torch
+    import torch.distributed as dist
+    nranks = int(os.environ["WORLD_SIZE"])
+    if torch.cuda.device_count() < nranks:
+        return dict(ok=True, skipped=True, msg="needs %d GPUs (NCCL cannot share a device between ranks)" % nranks)
+    if _restated is None:
+        spec = importlib.util.spec_from_file_location("nccl_restated", os.path.join(ROOT, "bench", "nccl_restated.py"))
+        _restated = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_restated)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", rank=rank, world_size=nranks, device_id=torch.device("cuda", gpu.dev))
+    dt_enum, np_dtype = DTYPES[case.get("dtype", "double")]
+    es = np.dtype(np_dtype).itemsize
+    cfg = make_config(case)
+    res, gd = cd.cudecompGridDescCreate(handle, cfg)
+    cd.check(res, "cudecompGridDescCreate")
+    out = dict(ok=True, msg="", paths=[])
+    work_ptr = 0
+    try:
+        geom = _restated.Geometry(case["gdims"], case["pdims"], case.get("axis_contiguous") or [False] * 3,
+                                  case.get("mem_order"), case.get("gdims_dist"))
+        rt = _restated.RestatedTranspose(geom, rank)
+        rt.create_groups()
+        sizes = [cd.cudecompGetPencilInfo(handle, gd, ax)[1].size for ax in range(3)]
+        for ax in range(3):
+            if sizes[ax] != _restated._prod(geom.torch_shape(rank, ax)):
+                return dict(ok=False, msg="pencil size mismatch on axis %d" % ax)
+        n = max(sizes)
+        res, wsize = cd.cudecompGetTransposeWorkspaceSize(handle, gd)
+        cd.check(res)
+        res, work_ptr = cd.cudecompMalloc(handle, gd, wsize * es)
+        cd.check(res, "cudecompMalloc")
+        tdt = {np.float32: torch.float32, np.float64: torch.float64, np.complex64: torch.complex64,
+               np.complex128: torch.complex128}[np_dtype]
+        host = np.zeros(n, np_dtype)
+        host[:sizes[0]] = seeded(sizes[0], np_dtype, 4242 + rank)
+        mine_in = torch.from_numpy(host.copy()).cuda(gpu.dev)
+        ref_in = mine_in.clone()
+        mine_out, ref_out = torch.zeros_like(mine_in), torch.zeros_like(mine_in)
+        send, recv = torch.zeros(n, dtype=tdt, device=mine_in.device), torch.zeros(n, dtype=tdt, device=mine_in.device)
+        for op in case.get("ops", OPS):
+            b = orc.transpose_axes(op)[1]
+            res = cd.TRANSPOSES[op](handle, gd, mine_in, mine_out, work_ptr, dt_enum, None, None, None, None, None)
+            if res != 0:
+                return dict(ok=False, msg="%s returned %d" % (op, res))
+            rt.transpose(op, ref_in, ref_out, send, recv)
+            torch.cuda.synchronize()
+            out["paths"].append(cd.last_path(handle, gd))
+            if not torch.equal(mine_out[:sizes[b]].view(torch.uint8), ref_out[:sizes[b]].view(torch.uint8)):
+                return dict(ok=False, msg="%s: differs from the restated NCCL arm" % op)
+            mine_in, mine_out = mine_out, mine_in
+            ref_in, ref_out = ref_out, ref_in
+    finally:
+        if work_ptr:
+            cd.cudecompFree(handle, gd, work_ptr)
+        cd.cudecompGridDescDestroy(handle, gd)
+    return out
+
+
 def mailbox_selftest(handle, case):
     return dict(ok=cd.lib.cudecompB200SelfTestMailbox(handle, case.get("iterations", 2000), case.get("seed", 1)) == 0)
 
@@ -451,6 +518,8 @@ def main():
                 results.append(_api_battery.run(handle, rank, case["name"], payload["mode"] == "api_gpu"))
             elif case["kind"] == "halo":
                 results.append(halo_case(gpu, handle, rank, case))
+            elif case["kind"] == "nccl_crosscheck":
+                results.append(nccl_crosscheck_case(gpu, handle, rank, case))
             elif case["kind"] == "autotune":
                 results.append(autotune_case(gpu, handle, rank, case))
             else:
@@ -473,6 +542,10 @@ def main():
         dist.destroy_process_group()
     with open(os.path.join(out_dir, "rank%d.json" % rank), "w") as f:
         json.dump(results, f)
+    if payload["mode"] == "gpu":
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
     cd.cudecompFinalize(handle)
     cd.MPI_Finalize()
 
