@@ -15,6 +15,7 @@
 #include "kernels.h"
 
 #include <atomic>
+#include <cstring>
 
 #include "tiling.h"
 
@@ -357,26 +358,26 @@ KernelFn pickKernel(KernelKind kind, int size, uint32_t peer_order = 0) {
 
 } // namespace
 
-int maxResidentCtas(KernelKind kind, int size, int threads) {
-  static int cache[2][3] = {{0, 0, 0}, {0, 0, 0}};
+int maxResidentCtas(KernelKind kind, int size, int threads, uint32_t peer_order) {
+  static int cache[2][2][3] = {};
   static int cache_dev = -1;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (dev != cache_dev) {
-    for (auto& row : cache)
-      for (int& v : row) v = 0;
+    std::memset(cache, 0, sizeof(cache));
     cache_dev = dev;
   }
   if (kind == KernelKind::ROWCOPY_BULK) return 0; // not used: launchBulk sizes its own grid
+  const int oi = peer_order ? 1 : 0;
   const int ki = (kind == KernelKind::ROWCOPY) ? 0 : 1;
   const int si = (size == 16) ? 2 : (size == 8 ? 1 : 0);
-  if (threads == 256 && cache[ki][si] > 0) return cache[ki][si];
-  KernelFn fn = pickKernel(kind, size);
+  if (threads == 256 && cache[oi][ki][si] > 0) return cache[oi][ki][si];
+  KernelFn fn = pickKernel(kind, size, peer_order);
   int per_sm = 0, sms = 0;
   if (!fn || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
   const int total = per_sm * sms;
-  if (threads == 256) cache[ki][si] = total;
+  if (threads == 256) cache[oi][ki][si] = total;
   return total;
 }
 
@@ -405,7 +406,7 @@ cudaError_t launchCopy(KernelKind kind, const CopyParams& p, const LaunchConfig&
   KernelFn fn = pickKernel(kind, size, p.peer_order);
   if (!fn) return cudaErrorInvalidValue;
   const uint64_t total = static_cast<uint64_t>(p.nboxes) * p.max_tiles;
-  const int resident = maxResidentCtas(kind, size, cfg.threads);
+  const int resident = maxResidentCtas(kind, size, cfg.threads, p.peer_order);
   if (resident <= 0) return cudaErrorInvalidDevice;
   // Measured on B200 (profiles/r1_n1_cta_sweep.txt): HBM streams best with a moderate number of CTAs in flight;
   // filling every resident slot costs 6-8 % of copy bandwidth. 2.5 CTAs/SM for the row copy, 4/SM for the

@@ -90,7 +90,7 @@ int chooseGrid(int requested, int dflt, int resident, uint64_t total_slots, int 
 cudaError_t launchCopy(KernelKind kind, const CopyParams& p, const LaunchConfig& cfg, cudaStream_t stream);
 
 // Upper bound on co-resident CTAs of the given kernel on the current device.
-int maxResidentCtas(KernelKind kind, int vec_or_elem_size, int threads);
+int maxResidentCtas(KernelKind kind, int vec_or_elem_size, int threads, uint32_t peer_order = 0);
 
 // counts launches issued through launchCopy (bench.py reports it as gpu_launches)
 uint64_t launchCount();
