@@ -9,6 +9,11 @@ Sources (all in /root/reference/tests/ctest/api_tests.cc):
   * expectShiftedRanks(...) calls                         (:1386-1408) -- per-rank neighbour tables
   * dtype sizes (:449-459) and backend names (:467-493)
 The parser reads the C++ initialiser lists; nothing is typed by hand.
+
+Also writes abi_golden.json: the reference's public ABI as read from ITS include/cudecomp.h and cudecomp_version.h by
+tests/golden/abi_parse.py (enumerators and values, struct members, magics / versions, the 24 prototypes and the 5
+header-inline wrappers reduced to return and parameter types) plus the C names its Fortran module binds
+(src/cudecomp_m.cuf). tests/test_abi_golden.py holds this repo's header and library against it.
 """
 import json
 import os
@@ -92,6 +97,17 @@ def main():
     path = os.path.join(OUT, "api_golden.json")
     with open(path, "w") as f:
         json.dump(golden, f, indent=1, sort_keys=True)
+    print("wrote", path)
+
+    sys.path.insert(0, OUT)
+    from abi_parse import fortran_bindings, parse_header
+    abi = parse_header(open("/root/reference/include/cudecomp.h").read())
+    abi["defines"].update(parse_header(open("/root/reference/include/cudecomp_version.h").read())["defines"])
+    abi["fortran_bindings"] = fortran_bindings(open("/root/reference/src/cudecomp_m.cuf").read())
+    abi["source"] = "reference include/cudecomp.h, include/cudecomp_version.h, src/cudecomp_m.cuf (v0.7.0)"
+    path = os.path.join(OUT, "abi_golden.json")
+    with open(path, "w") as f:
+        json.dump(abi, f, indent=1, sort_keys=True)
     print("wrote", path)
 
 
