@@ -225,13 +225,7 @@ extern "C" {
 
 // ------------------------------------------------------------------------------------------------ lifecycle
 
-cudecompResult_t cudecompInit(cudecompHandle_t* handle_in, MPI_Comm mpi_comm) {
-  cudecompHandle_t h = nullptr;
-  API_TRY
-  if (!handle_in) THROW_INVALID_USAGE("handle argument cannot be null");
-  CommPtr parent = commFromHandle(static_cast<int>(mpi_comm));
-  if (!parent) THROW_INVALID_USAGE("invalid communicator");
-  h = new cudecompHandle;
+static void initHandle(cudecompHandle_t h, const CommPtr& parent) {
   h->comm = dup(*parent); // private copy: library traffic never interleaves with the caller's collectives
   h->rank = h->comm->rank();
   h->nranks = h->comm->size();
@@ -257,8 +251,42 @@ cudecompResult_t cudecompInit(cudecompHandle_t* handle_in, MPI_Comm mpi_comm) {
   h->spin_timeout_ns = static_cast<uint64_t>(spin_s * 1e9);
   h->token = sharedToken(*h->comm);
   h->initialized = true;
+}
+
+cudecompResult_t cudecompInit(cudecompHandle_t* handle_in, MPI_Comm mpi_comm) {
+  cudecompHandle_t h = nullptr;
+  API_TRY
+  if (!handle_in) THROW_INVALID_USAGE("handle argument cannot be null");
+  CommPtr parent = commFromHandle(static_cast<int>(mpi_comm));
+  if (!parent) THROW_INVALID_USAGE("invalid communicator");
+  h = new cudecompHandle;
+  initHandle(h, parent);
   *handle_in = h;
   API_CATCH(delete h)
+}
+
+// For applications that run on a real MPI (include/cudecomp_b200_mpi.h): the caller says who it is and where rank 0
+// listens; the library builds its own control-plane mesh among exactly these processes. No MPI type crosses the ABI.
+cudecompResult_t cudecompB200InitBootstrap(cudecompHandle_t* handle_in, int32_t rank, int32_t nranks, const char* root_addr,
+                                           int32_t root_port) {
+  cudecompHandle_t h = nullptr;
+  API_TRY
+  if (!handle_in) THROW_INVALID_USAGE("handle argument cannot be null");
+  if (nranks < 1 || rank < 0 || rank >= nranks) THROW_INVALID_USAGE("rank / nranks are invalid");
+  if (nranks > 1 && (!root_addr || !*root_addr || root_port <= 0 || root_port > 65535))
+    THROW_INVALID_USAGE("root_addr / root_port are invalid");
+  worldInitExplicit(rank, nranks, root_addr ? root_addr : "127.0.0.1", root_port);
+  h = new cudecompHandle;
+  initHandle(h, worldComm());
+  *handle_in = h;
+  API_CATCH(delete h)
+}
+
+cudecompResult_t cudecompB200PickBootstrapPort(int32_t* port) {
+  API_TRY
+  if (!port) THROW_INVALID_USAGE("port argument cannot be null");
+  *port = pickFreePort();
+  API_CATCH()
 }
 
 cudecompResult_t cudecompInit_F(cudecompHandle_t* handle_in, MPI_Fint mpi_comm_f) {

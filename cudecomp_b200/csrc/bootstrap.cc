@@ -182,21 +182,33 @@ CommPtr selfComm() { return g_world.self; }
 
 void worldInit() {
   if (g_world.initialized) return;
+  const int rank = envInt("RANK", envInt("OMPI_COMM_WORLD_RANK", envInt("PMI_RANK", 0)));
+  const int size = envInt("WORLD_SIZE", envInt("OMPI_COMM_WORLD_SIZE", envInt("PMI_SIZE", 1)));
+  const char* addr_env = std::getenv("CUDECOMP_B200_BOOTSTRAP_ADDR");
+  if (!addr_env) addr_env = std::getenv("MASTER_ADDR");
+  int port = envInt("CUDECOMP_B200_BOOTSTRAP_PORT", 0);
+  if (port == 0) port = envInt("MASTER_PORT", 29616) + 1;
+  worldInitExplicit(rank, size, addr_env ? addr_env : "127.0.0.1", port);
+}
+
+void worldInitExplicit(int rank, int size, const std::string& addr, int port) {
+  if (g_world.initialized) {
+    if (g_world.rank != rank || g_world.size != size) {
+      errno = 0;
+      fail("the process mesh already exists with a different rank / size");
+    }
+    return;
+  }
   World& w = g_world;
-  w.rank = envInt("RANK", envInt("OMPI_COMM_WORLD_RANK", envInt("PMI_RANK", 0)));
-  w.size = envInt("WORLD_SIZE", envInt("OMPI_COMM_WORLD_SIZE", envInt("PMI_SIZE", 1)));
+  w.rank = rank;
+  w.size = size;
   if (w.size < 1 || w.rank < 0 || w.rank >= w.size) {
     errno = 0;
-    fail("invalid RANK/WORLD_SIZE environment");
+    fail("invalid rank / size (RANK, WORLD_SIZE)");
   }
   w.fds.assign(w.size, -1);
 
   if (w.size > 1) {
-    const char* addr_env = std::getenv("CUDECOMP_B200_BOOTSTRAP_ADDR");
-    if (!addr_env) addr_env = std::getenv("MASTER_ADDR");
-    std::string addr = addr_env ? addr_env : "127.0.0.1";
-    int port = envInt("CUDECOMP_B200_BOOTSTRAP_PORT", 0);
-    if (port == 0) port = envInt("MASTER_PORT", 29616) + 1;
     double timeout_s = envInt("CUDECOMP_B200_BOOTSTRAP_TIMEOUT", 120);
 
     int my_port = 0;
@@ -261,6 +273,13 @@ void worldInit() {
   w.self->me = 0;
   w.initialized = true;
   barrier(*w.world);
+}
+
+int pickFreePort() {
+  int port = 0;
+  int fd = listenOn("", 0, &port);
+  ::close(fd);
+  return port;
 }
 
 void worldFinalize() {

@@ -36,6 +36,11 @@ struct Comm {
 using CommPtr = std::shared_ptr<Comm>;
 
 void worldInit();     // idempotent; reads the environment and builds the mesh
+// Same with the rendezvous given explicitly (an application that has a real MPI: cudecompB200InitBootstrap): rank 0
+// listens on `port`, everybody else dials `addr`:`port`.
+void worldInitExplicit(int rank, int size, const std::string& addr, int port);
+// A TCP port that was free a moment ago (rank 0 of an explicit rendezvous picks one and broadcasts it).
+int pickFreePort();
 void worldFinalize(); // closes the mesh
 bool worldInitialized();
 int worldRank();

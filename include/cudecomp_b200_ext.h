@@ -24,6 +24,15 @@ typedef struct {
   int64_t dst_stride[3];
 } cudecompB200Box_t;
 
+/* Handle creation without an MPI type in the signature, for applications that run on a real MPI (see
+ * cudecomp_b200_mpi.h, which wraps these two behind the application's own cudecompInit(&handle, comm) call): this
+ * process is `rank` of `nranks`, rank 0 listens on root_addr:root_port (root_addr as every rank can reach it). The
+ * library builds its control-plane mesh among exactly these processes. Collective. */
+cudecompResult_t cudecompB200InitBootstrap(cudecompHandle_t* handle, int32_t rank, int32_t nranks, const char* root_addr,
+                                           int32_t root_port);
+/* A TCP port that is free on this host right now (rank 0 picks one and broadcasts it with its own MPI). */
+cudecompResult_t cudecompB200PickBootstrapPort(int32_t* port);
+
 /* Number of copy kernels this process has launched so far. */
 cudecompResult_t cudecompB200GetLaunchCount(uint64_t* count);
 

@@ -19,3 +19,40 @@ def test_plain_c_caller_compiles_links_and_runs(tmp_path):
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE")}
     run = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
     assert run.returncode == 0 and "C caller OK" in run.stdout, run.stdout + run.stderr
+
+
+def test_real_mpi_application_through_the_adapter(tmp_path):
+    """An unmodified cuDecomp application on a 'real' MPI whose MPI_Comm is a pointer (tests/c_caller/mock_mpi, Open MPI's
+    convention): compiled with -include cudecomp_b200_mpi.h against ITS mpi.h, linked with libcudecomp_realmpi.so, run on
+    2 ranks. The library must not export any MPI_* symbol in this flavour, and the ranks must find each other through the
+    rendezvous the adapter broadcasts with the application's MPI."""
+    import sys
+    from tests._launcher import free_port  # noqa: F401  (keeps the helper imported for parity with the other tests)
+    lib_dir = os.path.join(ROOT, "cudecomp_b200", "lib")
+    real = os.path.join(lib_dir, "libcudecomp_realmpi.so")
+    assert os.path.exists(real)
+    syms = subprocess.run(["nm", "-D", "--defined-only", real], capture_output=True, text=True).stdout.split("\n")
+    exported = [l.split()[-1] for l in syms if l.strip()]
+    assert exported and all(s.startswith("cudecomp") for s in exported), [s for s in exported if not s.startswith("cudecomp")]
+    assert "cudecompB200InitBootstrap" in exported and "cudecompTransposeXToY" in exported
+
+    exe = str(tmp_path / "realmpi_usage")
+    cc = os.path.join(ROOT, "tests", "c_caller")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = ["gcc", "-std=c11", "-Wall", "-Werror", "-D_DEFAULT_SOURCE", "-I" + os.path.join(cc, "mock_mpi"),
+           "-I" + os.path.join(ROOT, "include"), "-I" + cuda_inc, "-include", "cudecomp_b200_mpi.h",
+           os.path.join(cc, "realmpi_usage.c"), os.path.join(cc, "mock_mpi", "mock_mpi.c"), "-L" + lib_dir,
+           "-lcudecomp_realmpi", "-Wl,-rpath," + lib_dir, "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    for nranks in (1, 2):
+        d = tmp_path / ("run%d" % nranks)
+        d.mkdir()
+        procs = []
+        for r in range(nranks):
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+            env.update(MOCK_MPI_RANK=str(r), MOCK_MPI_SIZE=str(nranks), MOCK_MPI_DIR=str(d))
+            procs.append(subprocess.Popen([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        for r, p in enumerate(procs):
+            out, _ = p.communicate(timeout=120)
+            assert p.returncode == 0 and "real-MPI caller OK rank %d of %d" % (r, nranks) in out, out
