@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--axis-contiguous", action="store_true")
     ap.add_argument("--pdims", default=None, help="override process grid, e.g. 2x4")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--staged", action="store_true", help="force the workspace-staged schedule")
     ap.add_argument("--ctas", type=int, default=0)
@@ -180,6 +181,32 @@ def workload_config(args, pd, sample=None):
     return c
 
 
+def bind_near_gpu(torch, local_rank):
+    """Pin this process to the cores next to its GPU before any pinned host memory is allocated, so that the staging
+    buffers of the end-to-end leg land on the GPU's NUMA node (what the reference's launch scripts do with numactl).
+    Returns a short description for the JSON line; does nothing when the topology is not exposed."""
+    try:
+        prop = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        with open(base + "/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa node not exposed"
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "numa node %d has no usable cores" % node
+        os.sched_setaffinity(0, cpus)
+        return "bound to %d cores of numa node %d" % (len(cpus), node)
+    except Exception as e:  # noqa: BLE001 -- best effort, never fatal
+        return "not bound (%s)" % type(e).__name__
+
+
 # -------------------------------------------------------------------------------------------------- native arm
 def run_native(args, rank, world, local_rank):
     import numpy as np
@@ -187,8 +214,16 @@ def run_native(args, rank, world, local_rank):
     import torch.distributed as dist
     from cudecomp_b200 import capi as cd
 
+    # The CPU leg runs first, before this process narrows its affinity to the GPU's NUMA node: it gets every core the
+    # process was given (threads created later would inherit the narrowed mask).
+    cpu_first = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        pd0 = tuple(int(v) for v in args.pdims.split("x")) if args.pdims else GRID_BY_N.get(world, (1, world))
+        cpu_first = cpu_baseline(args, pd0)
+
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_near_gpu(torch, local_rank) if not args.no_numa_bind else "disabled"
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
@@ -337,7 +372,43 @@ def run_native(args, rank, world, local_rank):
         e2e_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
         e2e = {"value": world * 4.0 * S / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(S),
                "d2h_bytes_per_step": int(S), "ms_per_step": e2e_ms,
-               "pipelining": "%d device buffer sets; H2D, transposes and D2H on separate streams" % nslots}
+               "pipelining": "%d device buffer sets; H2D, transposes and D2H on separate streams" % nslots,
+               "host_binding": numa}
+
+        # What the host link gives this leg at best: the same pinned buffers copied with nothing else going on, one
+        # direction at a time and both at once (all ranks at the same time, like the leg itself). The end-to-end step
+        # cannot be shorter than S / duplex rate; the transposes are the remainder.
+        def copy_rate(do_h2d, do_d2h, reps=2):
+            x = slots[0][0]
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(stream)
+            s_h2d.wait_event(t0)
+            s_d2h.wait_event(t0)
+            for _ in range(reps):
+                if do_h2d:
+                    with torch.cuda.stream(s_h2d):
+                        x[:ne].copy_(h_in, non_blocking=True)
+                if do_d2h:
+                    with torch.cuda.stream(s_d2h):
+                        h_out.copy_(slots[-1][1][:ne], non_blocking=True)
+            ev_a, ev_b = torch.cuda.Event(), torch.cuda.Event()
+            ev_a.record(s_h2d)
+            ev_b.record(s_d2h)
+            stream.wait_event(ev_a)
+            stream.wait_event(ev_b)
+            t1.record(stream)
+            torch.cuda.synchronize()
+            ms = max_over_ranks(t0.elapsed_time(t1) / reps)
+            return S / (ms * 1e-3) / 1e9
+
+        try:
+            e2e["host_link"] = {"h2d_gbs_per_gpu": copy_rate(True, False), "d2h_gbs_per_gpu": copy_rate(False, True),
+                                "duplex_gbs_per_gpu_per_direction": copy_rate(True, True), "unit": "GB/s",
+                                "note": "pinned-memory copies of the same pencil, all ranks at once, nothing else running"}
+            e2e["host_link"]["floor_ms_per_step"] = S / (e2e["host_link"]["duplex_gbs_per_gpu_per_direction"] * 1e9) * 1e3
+        except Exception as e:  # noqa: BLE001 -- the probe is context, never a reason to lose the bench line
+            e2e["host_link"] = {"error": repr(e)}
         del h_in, h_out, slots
 
     hbm_peak, peak_src = peaks()
@@ -373,8 +444,8 @@ def run_native(args, rank, world, local_rank):
                         "hbm_view": {k: hbm_view[k] for k in ("achieved", "peak", "frac")}}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args, pd)
+    if cpu_first is not None:
+        cpu = cpu_first
 
     if rank == 0:
         line = {"metric": "effective transpose GB/s (4*S/t round trip, whole job)", "value": value, "unit": "GB/s",
