@@ -7,7 +7,7 @@ N=${1:-1}
 OUT=gpurun_out
 echo "== unconfirmed code paths (XPASS = confirmed)"
 timeout 1500 python -m pytest tests/test_zz_api_contract_gpu.py tests/test_zz_perf_report_gpu.py tests/test_zz_pipeline_gpu.py \
-  tests/test_zz_ref_benchmark_gpu.py tests/test_zz_schedule_gpu.py tests/test_zz_nccl_crosscheck_gpu.py -q -m gpu -rxX -p no:cacheprovider > $OUT/r2_zz_tests.log 2>&1
+  tests/test_zz_ref_benchmark_gpu.py tests/test_zz_ref_ctest_gpu.py tests/test_zz_schedule_gpu.py tests/test_zz_nccl_crosscheck_gpu.py -q -m gpu -rxX -p no:cacheprovider > $OUT/r2_zz_tests.log 2>&1
 tail -40 $OUT/r2_zz_tests.log
 
 i=0
