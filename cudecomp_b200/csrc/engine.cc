@@ -90,8 +90,8 @@ void launchBoxes(cudecompGridDesc_t gd, const std::vector<ResolvedBox>& boxes, i
   for (size_t l = 0; l < launches.size(); ++l) {
     CopyParams& p = launches[l].params;
     p.sync = sync;
-    p.sync.do_entry = (sync.npeers > 0 && l == 0) ? 1 : 0;
-    p.sync.do_exit = (sync.npeers > 0 && l + 1 == launches.size()) ? 1 : 0;
+    p.sync.do_entry = (sync.npeers > 0 && sync.do_entry && l == 0) ? 1 : 0;
+    p.sync.do_exit = (sync.npeers > 0 && sync.do_exit && l + 1 == launches.size()) ? 1 : 0;
     if (p.nboxes == 0 && sync.npeers == 0) continue;
     cudaError_t err = launchCopy(launches[l].kind, p, cfg, stream);
     if (err != cudaSuccess) THROW_CUDA_ERROR(std::string("kernel launch failed: ") + cudaGetErrorString(err));
@@ -161,7 +161,10 @@ bool runPipelinedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int d
   bool used_side = false;
   for (size_t s = 0; s < K; ++s) {
     if (s > 0) gd->epoch++; // the first step uses the epoch the call was given
-    const SyncParams sync = makeSync(gd, peers);
+    SyncParams sync = makeSync(gd, peers);
+    // Peers only have to be met on the way in once per call: after step 0 everybody is inside this operation and the
+    // chunks land in disjoint parts of the workspace. The way out is needed per step (unpack(s) reads what peers pushed).
+    if (s > 0) sync.do_entry = 0;
     std::vector<ResolvedBox> push, unpack;
     for (auto& b : pp.steps[s].push) {
       char* dst = (b.peer == pp.base.me) ? static_cast<char*>(work)
