@@ -114,13 +114,35 @@ void copyConfigToCaller(cudecompGridDescConfig_t* dst, int64_t struct_size, int3
 // ------------------------------------------------------------------------------------------------
 // argument checks (reference src/cudecomp.cc:136-207,445-481)
 
+// Live objects of this process. Callers hand back raw pointers; a pointer is only dereferenced after it has been found
+// here, so a stale handle or a grid descriptor that was already destroyed is an INVALID_USAGE error, not a read of
+// freed memory (the reference dereferences them, src/cudecomp.cc:136-207).
+std::set<cudecompHandle_t>& liveHandles() {
+  static std::set<cudecompHandle_t> s;
+  return s;
+}
+std::set<cudecompGridDesc_t>& liveGridDescs() {
+  static std::set<cudecompGridDesc_t> s;
+  return s;
+}
+
 void checkHandle(cudecompHandle_t h) {
-  if (!h || !h->initialized) THROW_INVALID_USAGE("invalid handle");
+  if (!h || !liveHandles().count(h) || !h->initialized) THROW_INVALID_USAGE("invalid handle");
 }
 void checkGridDesc(cudecompHandle_t h, cudecompGridDesc_t gd) {
-  if (!gd || !gd->initialized) THROW_INVALID_USAGE("invalid grid descriptor");
+  if (!gd || !liveGridDescs().count(gd) || !gd->initialized) THROW_INVALID_USAGE("invalid grid descriptor");
   if (gd->handle != h) THROW_INVALID_USAGE("grid descriptor belongs to a different handle");
 }
+// Enumerators arrive from C callers inside structs or as arguments and may hold any bit pattern; they are read through
+// their integer representation so that validating them is well defined (an out-of-range value must yield
+// INVALID_USAGE, not undefined behaviour on the load).
+template <typename E> int enumBits(const E& e) {
+  static_assert(sizeof(E) == sizeof(int), "cuDecomp enums are int-sized");
+  int v;
+  std::memcpy(&v, &e, sizeof(v));
+  return v;
+}
+
 void checkTransposeBackend(int b) {
   if (b < CUDECOMP_TRANSPOSE_COMM_MPI_P2P || b > CUDECOMP_TRANSPOSE_COMM_NVSHMEM_SM)
     THROW_INVALID_USAGE("unknown transpose communication type");
@@ -129,7 +151,8 @@ void checkHaloBackend(int b) {
   if (b < CUDECOMP_HALO_COMM_MPI || b > CUDECOMP_HALO_COMM_NVSHMEM_BLOCKING)
     THROW_INVALID_USAGE("unknown halo communication type");
 }
-void checkDataType(cudecompDataType_t d) {
+void checkDataType(const cudecompDataType_t& dtype) {
+  const int d = enumBits(dtype);
   if (d != CUDECOMP_FLOAT && d != CUDECOMP_DOUBLE && d != CUDECOMP_FLOAT_COMPLEX && d != CUDECOMP_DOUBLE_COMPLEX)
     THROW_INVALID_USAGE("unknown data type");
 }
@@ -138,9 +161,9 @@ void checkRankOrder(int r) {
 }
 
 void checkConfig(cudecompHandle_t h, const cudecompGridDescConfig_t* c, bool autotune_transpose, bool autotune_halo) {
-  if (!autotune_transpose) checkTransposeBackend(c->transpose_comm_backend);
-  if (!autotune_halo) checkHaloBackend(c->halo_comm_backend);
-  checkRankOrder(c->rank_order);
+  if (!autotune_transpose) checkTransposeBackend(enumBits(c->transpose_comm_backend));
+  if (!autotune_halo) checkHaloBackend(enumBits(c->halo_comm_backend));
+  checkRankOrder(enumBits(c->rank_order));
   if (c->pdims[0] < 0 || c->pdims[1] < 0) THROW_INVALID_USAGE("pdims values are invalid");
   const int64_t prod = static_cast<int64_t>(c->pdims[0]) * c->pdims[1];
   if (prod == 0) {
@@ -261,6 +284,7 @@ cudecompResult_t cudecompInit(cudecompHandle_t* handle_in, MPI_Comm mpi_comm) {
   if (!parent) THROW_INVALID_USAGE("invalid communicator");
   h = new cudecompHandle;
   initHandle(h, parent);
+  liveHandles().insert(h);
   *handle_in = h;
   API_CATCH(delete h)
 }
@@ -278,6 +302,7 @@ cudecompResult_t cudecompB200InitBootstrap(cudecompHandle_t* handle_in, int32_t 
   worldInitExplicit(rank, nranks, root_addr ? root_addr : "127.0.0.1", root_port);
   h = new cudecompHandle;
   initHandle(h, worldComm());
+  liveHandles().insert(h);
   *handle_in = h;
   API_CATCH(delete h)
 }
@@ -299,6 +324,7 @@ cudecompResult_t cudecompFinalize(cudecompHandle_t handle) {
   handle->peers.clear();
   if (handle->arena.valid()) handle->arena.destroy(handle->comm.get());
   handle->initialized = false;
+  liveHandles().erase(handle);
   delete handle;
   API_CATCH()
 }
@@ -327,7 +353,8 @@ cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudeco
     if (options->struct_size != options_struct_size || options->version != options_version)
       THROW_INVALID_USAGE("options metadata does not match the requested cuDecomp layout version");
     // rejected even when nothing is left to tune (reference src/cudecomp.cc:1201-1210)
-    if (options->grid_mode != CUDECOMP_AUTOTUNE_GRID_TRANSPOSE && options->grid_mode != CUDECOMP_AUTOTUNE_GRID_HALO)
+    if (enumBits(options->grid_mode) != CUDECOMP_AUTOTUNE_GRID_TRANSPOSE &&
+        enumBits(options->grid_mode) != CUDECOMP_AUTOTUNE_GRID_HALO)
       THROW_INVALID_USAGE("unknown value of autotune_grid_mode encountered.");
   }
   const bool autotune_transpose = options && options->autotune_transpose_backend;
@@ -385,9 +412,10 @@ cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudeco
   // samples taken from here on (autotuning trials are not part of the report, reference src/autotune.cc "reset")
   if (handle->perf.enabled && handle->have_device) gd->perf.reset(new PerfReport(handle->perf));
 
-  handle->live_grid_descs++;
-  *grid_desc_in = gd;
   copyConfigToCaller(config, config_struct_size, config_version, gd);
+  handle->live_grid_descs++;
+  liveGridDescs().insert(gd);
+  *grid_desc_in = gd;
   API_CATCH(if (gd) {
     destroyGridDescResources(gd, false);
     delete gd;
@@ -406,6 +434,7 @@ cudecompResult_t cudecompGridDescDestroy(cudecompHandle_t handle, cudecompGridDe
   destroyGridDescResources(grid_desc, true);
   grid_desc->initialized = false;
   handle->live_grid_descs--;
+  liveGridDescs().erase(grid_desc);
   delete grid_desc;
   API_CATCH()
 }
@@ -516,7 +545,7 @@ cudecompResult_t cudecompGetShiftedRank(cudecompHandle_t handle, cudecompGridDes
 }
 
 const char* cudecompTransposeCommBackendToString(cudecompTransposeCommBackend_t comm_backend) {
-  switch (comm_backend) {
+  switch (enumBits(comm_backend)) {
   case CUDECOMP_TRANSPOSE_COMM_NCCL: return "NCCL";
   case CUDECOMP_TRANSPOSE_COMM_NCCL_PL: return "NCCL (pipelined)";
   case CUDECOMP_TRANSPOSE_COMM_MPI_P2P: return "MPI_P2P";
@@ -530,7 +559,7 @@ const char* cudecompTransposeCommBackendToString(cudecompTransposeCommBackend_t 
 }
 
 const char* cudecompHaloCommBackendToString(cudecompHaloCommBackend_t comm_backend) {
-  switch (comm_backend) {
+  switch (enumBits(comm_backend)) {
   case CUDECOMP_HALO_COMM_NCCL: return "NCCL";
   case CUDECOMP_HALO_COMM_MPI: return "MPI";
   case CUDECOMP_HALO_COMM_MPI_BLOCKING: return "MPI (blocking)";

@@ -164,7 +164,10 @@ def test_single_rank_queries_and_config_roundtrip(handle):
     assert cd.cudecompUpdateHalosX(handle, gd, None, None, cd.CUDECOMP_FLOAT, (0, 0, 0), None, 0) == 0
     assert cd.cudecompUpdateHalosX(handle, gd, 8, 8, cd.CUDECOMP_FLOAT, (1, 0, 0), None, 5) == INV
     assert cd.cudecompGridDescDestroy(handle, gd) == 0
-    assert cd.cudecompGridDescDestroy(handle, gd) == INV or True  # destroyed descriptors are rejected or ignored
+    # a destroyed descriptor is recognised as stale (never dereferenced): every entry point rejects it
+    assert cd.cudecompGridDescDestroy(handle, gd) == INV
+    assert cd.cudecompGetPencilInfo(handle, gd, 0)[0] == INV
+    assert cd.cudecompGetTransposeWorkspaceSize(handle, gd)[0] == INV
 
 
 def test_empty_pencils_not_supported(handle):
