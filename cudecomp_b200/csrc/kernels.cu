@@ -265,6 +265,10 @@ __device__ __forceinline__ void store(void* g, const void* smem, uint32_t bytes)
 __global__ void __launch_bounds__(32) rowCopyBulkKernel(const __grid_constant__ CopyParams p) {
   extern __shared__ __align__(128) unsigned char bulk_smem[];
   __shared__ uint64_t full[kBulkStages];
+  // destination and size of what each stage holds (only the driving thread touches them; shared memory instead of a
+  // dynamically indexed local array)
+  __shared__ char* dst_of[kBulkStages];
+  __shared__ uint32_t bytes_of[kBulkStages];
   syncEntry(p.sync);
 
   if (threadIdx.x == 0) {
@@ -290,8 +294,6 @@ __global__ void __launch_bounds__(32) rowCopyBulkKernel(const __grid_constant__ 
 
     uint32_t t_load = blockIdx.x;   // next tile to look at for loading
     uint32_t n_loaded = 0, n_stored = 0;
-    char* dst_of[kBulkStages];
-    uint32_t bytes_of[kBulkStages];
     auto issueLoad = [&]() -> bool {
       while (t_load < total) {
         const char* src;
