@@ -20,16 +20,17 @@ BENCH := $(OUT)/benchmark_c2c $(OUT)/benchmark_r2c $(OUT)/benchmark_c2c_f $(OUT)
 # the reference's CURRENT GoogleTest suites (tests/ctest): halo_tests.cc and api_tests.cc with their support files and
 # their own MPI-aware main(), unmodified. GoogleTest itself is not in this image: oracle/gtest_shim/gtest/gtest.h
 # implements the subset they use (pinned by tests/test_gtest_shim.py). api_tests.cc reaches into two PRIVATE headers of
-# the reference for its white-box candidate-filter cases; oracle/stubs/internal/*.h + internal_adapter.cc express those
-# three functions through this library's public extension API. transpose_tests.cc is not built: it reads and writes the
+# the reference: internal/exceptions.h is header-only and is used as it is; internal/autotune.h declares functions of
+# the reference's library, so oracle/stubs_ctest/internal/autotune.h stands in for it and internal_adapter.cc expresses
+# those three candidate queries through this library's public extension API. transpose_tests.cc is not built: it reads and writes the
 # reference's private handle / grid-descriptor structs (transpose_tests.cc:431-470); its case matrix is restated in
 # tests/cases.py instead. NVSHMEM-only cases are compiled out exactly as the reference's CMake does without NVSHMEM.
 CTEST := $(REF)/tests/ctest
 CTEST_SUPPORT := $(CTEST)/backend_test_context.cc $(CTEST)/backend_utils.cc $(CTEST)/gpu_test_utils.cc \
                  $(CTEST)/mpi_test_utils.cc $(CTEST)/test_utils.cc $(CTEST)/mpi_test_main.cc
 CTEST_FLAGS := -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -x cu -Xcompiler -Wno-attributes \
-               -I$(ROOT)/oracle/gtest_shim -I$(ROOT)/oracle/stubs -I$(OUT)/gen -I$(ROOT)/include -I$(ROOT)/include/mpi_shim \
-               -I$(CTEST) -L$(ROOT)/cudecomp_b200/lib -lcudecomp -lnccl \
+               -I$(ROOT)/oracle/gtest_shim -I$(ROOT)/oracle/stubs_ctest -I$(OUT)/gen -I$(ROOT)/include -I$(ROOT)/include/mpi_shim \
+               -I$(ROOT)/oracle/stubs -I$(REF)/include -I$(CTEST) -L$(ROOT)/cudecomp_b200/lib -lcudecomp -lnccl \
                -Xlinker -rpath -Xlinker '$$ORIGIN/../../cudecomp_b200/lib'
 CTESTS := $(OUT)/ctest_halo_tests $(OUT)/ctest_api_tests
 
@@ -42,8 +43,8 @@ $(OUT)/gen/backend_config.h:
 $(OUT)/ctest_halo_tests: $(CTEST)/halo_tests.cc $(CTEST_SUPPORT) $(OUT)/gen/backend_config.h $(ROOT)/oracle/gtest_shim/gtest/gtest.h $(ROOT)/cudecomp_b200/lib/libcudecomp.so
 	$(NVCC) $(CTEST_FLAGS) $(CTEST)/halo_tests.cc $(CTEST_SUPPORT) -o $@
 
-$(OUT)/ctest_api_tests: $(CTEST)/api_tests.cc $(CTEST_SUPPORT) $(ROOT)/oracle/stubs/internal_adapter.cc $(OUT)/gen/backend_config.h $(ROOT)/oracle/gtest_shim/gtest/gtest.h $(ROOT)/cudecomp_b200/lib/libcudecomp.so
-	$(NVCC) $(CTEST_FLAGS) $(CTEST)/api_tests.cc $(CTEST_SUPPORT) $(ROOT)/oracle/stubs/internal_adapter.cc -o $@
+$(OUT)/ctest_api_tests: $(CTEST)/api_tests.cc $(CTEST_SUPPORT) $(ROOT)/oracle/stubs_ctest/internal_adapter.cc $(OUT)/gen/backend_config.h $(ROOT)/oracle/gtest_shim/gtest/gtest.h $(ROOT)/cudecomp_b200/lib/libcudecomp.so
+	$(NVCC) $(CTEST_FLAGS) $(CTEST)/api_tests.cc $(CTEST_SUPPORT) $(ROOT)/oracle/stubs_ctest/internal_adapter.cc -o $@
 
 $(OUT)/benchmark_c2c: $(REF)/benchmark/benchmark.cu $(ROOT)/cudecomp_b200/lib/libcudecomp.so
 	@mkdir -p $(OUT)

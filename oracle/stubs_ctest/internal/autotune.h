@@ -1,7 +1,7 @@
 // Stand-in for the reference's PRIVATE header include/internal/autotune.h, so that its API test suite
 // (reference tests/ctest/api_tests.cc, which includes "internal/autotune.h" to test the candidate filters white-box)
 // compiles unmodified against this library. Only the three candidate queries the tests call are declared; they are
-// implemented in oracle/stubs/internal_adapter.cc on top of the public extension cudecompB200GetAutotuneCandidates.
+// implemented in oracle/stubs_ctest/internal_adapter.cc on top of the public extension cudecompB200GetAutotuneCandidates.
 // TEST INFRASTRUCTURE, not part of the product.
 #ifndef CUDECOMP_B200_STUB_INTERNAL_AUTOTUNE_H
 #define CUDECOMP_B200_STUB_INTERNAL_AUTOTUNE_H

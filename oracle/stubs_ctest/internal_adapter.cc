@@ -1,14 +1,18 @@
 // The reference's white-box candidate queries (declared in its private internal/autotune.h) expressed through this
-// library's public extension entry point, for the reference's unmodified tests/ctest/api_tests.cc. TEST INFRASTRUCTURE.
+// library's public extension entry point, for the reference's unmodified tests/ctest/api_tests.cc. The exception type
+// the tests expect is the reference's own (its header-only include/internal/exceptions.h, found on the include path at
+// build time). TEST INFRASTRUCTURE.
 #include "cudecomp_b200_ext.h"
 #include "internal/autotune.h"
+#include <stdexcept>
+
 #include "internal/exceptions.h"
 
 namespace cudecomp {
 
 namespace {
 void check(cudecompResult_t res) {
-  if (res == CUDECOMP_RESULT_INVALID_USAGE) throw InvalidUsage("autotune candidate filters rejected");
+  if (res == CUDECOMP_RESULT_INVALID_USAGE) throw InvalidUsage(__FILE__, __LINE__, "autotune candidate filters rejected");
   if (res != CUDECOMP_RESULT_SUCCESS) throw std::runtime_error("cudecompB200GetAutotuneCandidates failed");
 }
 } // namespace
