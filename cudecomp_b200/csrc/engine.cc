@@ -39,6 +39,7 @@ void checkDeviceError(cudecompGridDesc_t gd) {
   const uint32_t e = arena.errorWordHost();
   if (e == 0) return;
   arena.clearError();
+  if (e == 3) THROW_INTERNAL_ERROR("a TMA bulk copy of an earlier operation did not complete within 20 s");
   THROW_INTERNAL_ERROR(std::string("a device-side wait for a peer rank timed out during an earlier operation (") +
                        (e == 1 ? "entry" : "exit") +
                        " handshake); a rank of the communicator did not enter the same operation");

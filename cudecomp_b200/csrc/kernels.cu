@@ -317,7 +317,21 @@ __global__ void __launch_bounds__(32) rowCopyBulkKernel(const __grid_constant__ 
     while (n_stored < n_loaded) {
       const int s = static_cast<int>(n_stored % kBulkStages);
       const uint32_t parity = (n_stored / kBulkStages) & 1u;
-      while (!bulk::mbarTryWait(&full[s], parity)) {}
+      // a bulk load that never completes (bad address, driver fault) must not spin forever: give up after 20 s,
+      // flag the launch and leave
+      if (!bulk::mbarTryWait(&full[s], parity)) {
+        const uint64_t t0 = globalTimerNs();
+        bool ok = false;
+        while (!(ok = bulk::mbarTryWait(&full[s], parity)))
+          if (globalTimerNs() - t0 > 20000000000ull) break;
+        if (!ok) {
+          if (p.sync.error_word) {
+            *reinterpret_cast<volatile uint32_t*>(p.sync.error_word) = 3u;
+            __threadfence_system();
+          }
+          break;
+        }
+      }
       bulk::store(dst_of[s], bulk_smem + static_cast<size_t>(s) * kBulkChunkBytes, bytes_of[s]);
       ++n_stored;
       // the slot stored one iteration ago may be refilled once its store has finished reading shared memory

@@ -12,7 +12,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet c
 
 @pytest.fixture(scope="module")
 def api_results():
-    results, _ = run_ranks(4, "api_gpu", [dict(name=n) for n in TEST_NAMES], timeout=600)
+    results, _ = run_ranks(4, "api_gpu", [dict(name=n) for n in TEST_NAMES], timeout=300)
     return results
 
 

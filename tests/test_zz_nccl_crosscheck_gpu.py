@@ -27,7 +27,7 @@ def test_library_equals_restated_nccl_arm(nranks):
     import torch
     if torch.cuda.device_count() < nranks:
         pytest.skip("needs %d GPUs" % nranks)
-    results, _ = run_ranks(nranks, "gpu", CASES[nranks], timeout=900)
+    results, _ = run_ranks(nranks, "gpu", CASES[nranks], timeout=420)
     for r in range(nranks):
         for c, case in zip(results[r], CASES[nranks]):
             assert c["ok"], (case["name"], r, c.get("msg"))

@@ -18,7 +18,7 @@ def test_performance_report_table_and_csv():
              dict(base, name="inplace", ops=["XY", "YX"] * 3),
              dict(kind="halo", name="halo", gdims=[40, 36, 44], pdims=[2, 1], dtype="float", axis=0, halo=[1, 1, 1],
                   periods=[True] * 3, fills=["random", "pattern"])]
-    results, logs = run_ranks(2, "gpu", cases, timeout=600, extra_env={
+    results, logs = run_ranks(2, "gpu", cases, timeout=300, extra_env={
         "CUDECOMP_ENABLE_PERFORMANCE_REPORT": "1", "CUDECOMP_PERFORMANCE_REPORT_WARMUP_SAMPLES": "1",
         "CUDECOMP_PERFORMANCE_REPORT_WRITE_DIR": out_dir})
     for r in range(2):

@@ -29,7 +29,7 @@ CASES = [
 
 @pytest.fixture(scope="module")
 def pipe_results():
-    return run_ranks(4, "gpu", CASES, timeout=900)[0]
+    return run_ranks(4, "gpu", CASES, timeout=420)[0]
 
 
 @pytest.mark.parametrize("i", range(len(CASES)), ids=[c["name"] for c in CASES])
@@ -54,7 +54,7 @@ BULK_CASES = [
 
 @pytest.fixture(scope="module")
 def bulk_results():
-    return run_ranks(4, "gpu", BULK_CASES, timeout=900)[0]
+    return run_ranks(4, "gpu", BULK_CASES, timeout=420)[0]
 
 
 @pytest.mark.parametrize("i", range(len(BULK_CASES)), ids=[c["name"] for c in BULK_CASES])

@@ -27,7 +27,7 @@ def test_reference_fft_benchmark(exe, args):
     path = os.path.join(REF_BIN, exe)
     if not os.path.exists(path):
         pytest.skip("oracle/_ref binaries not built (make -f oracle/ref_tests.mk needs /root/reference)")
-    out, codes = run_mpi(4, [path] + args, timeout=600)
+    out, codes = run_mpi(4, [path] + args, timeout=300)
     assert all(c == 0 for c in codes), out[-3000:]
     assert "Result Summary:" in out and "FAILURE" not in out, out[-3000:]
     m = re.search(r"Max error: ([0-9.eE+-]+)", out)

@@ -37,7 +37,7 @@ def test_reference_gtest_suite(label, exe, args, env, monkeypatch):
         mps = tempfile.mkdtemp(prefix="cdb200_mps_")
         open(os.path.join(mps, "nvidia-cuda-mps-control.pid"), "w").write("0\n")
         monkeypatch.setenv("CUDA_MPS_PIPE_DIRECTORY", mps)
-    out, codes = run_mpi(4, [path] + args, timeout=900)
+    out, codes = run_mpi(4, [path] + args, timeout=420)
     failed = re.findall(r"^\[  FAILED  \] (\S+)$", out, re.M)
     assert all(c == 0 for c in codes) and not failed, "%s\n%s\n%s" % (codes, failed[:10], out[-3000:])
     m = re.search(r"\[  PASSED  \] (\d+) tests", out)

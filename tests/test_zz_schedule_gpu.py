@@ -30,7 +30,7 @@ CASES = [
 
 @pytest.fixture(scope="module")
 def schedule_results():
-    return run_ranks(4, "gpu", CASES, timeout=900)[0]
+    return run_ranks(4, "gpu", CASES, timeout=420)[0]
 
 
 @pytest.mark.parametrize("i", range(len(CASES)), ids=[c["name"] for c in CASES])
