@@ -31,20 +31,34 @@ for l in sys.stdin:
 echo "== default schedules, N=$N"
 bench default --no-e2e
 bench inplace --no-e2e --inplace
-echo "== chunked in-place schedule (cudecompB200SetPipelineChunks)"
-for k in 2 4 8 16; do bench inplace_chunks$k --no-e2e --inplace --chunks $k; done
-echo "== TMA bulk row copy (cudecompB200SetKernelVariant)"
-bench bulk --no-e2e --bulk
-bench bulk_inplace_chunks8 --no-e2e --bulk --inplace --chunks 8
-echo "== tile size / peer order / balanced grid (cudecompB200SetSchedule)"
+if [ "$N" != 1 ]; then
+  # these only change something when a communicator has more than one rank
+  echo "== chunked in-place schedule (cudecompB200SetPipelineChunks)"
+  for k in 2 4 8 16; do bench inplace_chunks$k --no-e2e --inplace --chunks $k; done
+  bench inplace_chunks8_1cta --no-e2e --inplace --chunks 8 --ctas 148
+  echo "== TMA bulk row copy (cudecompB200SetKernelVariant)"
+  bench bulk --no-e2e --bulk
+  bench bulk_inplace_chunks8 --no-e2e --bulk --inplace --chunks 8
+  echo "== pairwise slot order"
+  bench pairwise --no-e2e --peer-order 1
+else
+  bench bulk --no-e2e --bulk
+fi
+echo "== tile size / balanced grid (cudecompB200SetSchedule)"
 for t in 16384 65536; do bench tile$t --no-e2e --tile-bytes $t; done
-bench pairwise --no-e2e --peer-order 1
 bench balanced --no-e2e --balance-grid 1
 echo "== 512^3 complex64 (BASELINE config 2): handshake- and tail-sensitive"
 bench c64_512 --no-e2e --grid 512 --dtype float_complex
 for t in 8192 16384; do bench c64_512_tile$t --no-e2e --grid 512 --dtype float_complex --tile-bytes $t; done
 bench c64_512_balanced --no-e2e --grid 512 --dtype float_complex --balance-grid 1
 bench c64_512_balanced_tile16k --no-e2e --grid 512 --dtype float_complex --balance-grid 1 --tile-bytes 16384
+bench c64_512_inplace --no-e2e --grid 512 --dtype float_complex --inplace
+if [ "$N" != 1 ]; then
+  bench c64_512_inplace_chunks4 --no-e2e --grid 512 --dtype float_complex --inplace --chunks 4
+  bench c64_512_pairwise --no-e2e --grid 512 --dtype float_complex --peer-order 1
+fi
+echo "== the default line with the end-to-end leg (host-link ceiling, NUMA binding)"
+bench default_e2e
 
 if [ "$N" = 1 ]; then
   echo "== ncu: launch list and one full capture of the transpose (permuting) kernel, axis-contiguous layout"
