@@ -91,3 +91,22 @@ if [ "$N" != 1 ]; then
   timeout 900 python -m pytest tests/test_zz_nccl_crosscheck_gpu.py -q -m gpu -rxXs -p no:cacheprovider > $OUT/r2_n${N}_nccl_crosscheck.log 2>&1
   tail -5 $OUT/r2_n${N}_nccl_crosscheck.log
 fi
+
+if [ "$N" != 1 ] && [ -x oracle/_ref/benchmark_c2c ]; then
+  echo "== the reference's own FFT benchmark binary (benchmark/benchmark.cu, unmodified) on this library, 1024^3 c2c"
+  refbench() { # label, args...
+    label=$1; shift
+    for r in $(seq 0 $((N-1))); do
+      RANK=$r WORLD_SIZE=$N LOCAL_RANK=$r MASTER_ADDR=127.0.0.1 MASTER_PORT=29940 timeout 600 oracle/_ref/benchmark_c2c "$@" \
+        > $OUT/r2_n${N}_refbench_${label}.rank$r.log 2>&1 &
+    done
+    wait
+    grep -E "Result Summary|FFTSize|GFLOPS|TIME|Max error|SELECTED|time" $OUT/r2_n${N}_refbench_${label}.rank0.log | head -20
+  }
+  PR=$(python -c "print({2:1,4:2,8:2}.get($N,1))"); PC=$((N/PR))
+  refbench inplace --gx 1024 --gy 1024 --gz 1024 -r $PR -c $PC -b 4
+  refbench oop --gx 1024 --gy 1024 --gz 1024 -r $PR -c $PC -b 4 -o
+  refbench oop_ac --gx 1024 --gy 1024 --gz 1024 -r $PR -c $PC -b 4 -o --acx 1 --acy 1 --acz 1
+  CUDECOMP_B200_PIPELINE_CHUNKS=8 refbench inplace_chunks8 --gx 1024 --gy 1024 --gz 1024 -r $PR -c $PC -b 4
+  refbench autotune --gx 1024 --gy 1024 --gz 1024 -r 0 -c 0 -b 0 -o
+fi
