@@ -70,8 +70,8 @@ def build_library(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as pool:
         list(pool.map(lambda c: _run(c, verbose), jobs))
     link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
-    _run(link + ["-o", LIB_PATH] + objects + ["-lrt", "-lpthread"], verbose)
-    _run(link + ["-Xlinker", "--version-script=" + VERSION_SCRIPT, "-o", REALMPI_LIB_PATH] + objects + ["-lrt", "-lpthread"],
+    _run(link + ["-o", LIB_PATH] + objects + ["-lrt", "-lpthread", "-ldl"], verbose)
+    _run(link + ["-Xlinker", "--version-script=" + VERSION_SCRIPT, "-o", REALMPI_LIB_PATH] + objects + ["-lrt", "-lpthread", "-ldl"],
          verbose)
     return LIB_PATH
 

@@ -17,6 +17,7 @@
 #include "cudecomp_b200_ext.h"
 #include "engine.h"
 #include "launch_params.h"
+#include "nvtx_ranges.h"
 #include "errors.h"
 #include "mpi_shim.h"
 
@@ -629,6 +630,7 @@ cudecompResult_t cudecompFree(cudecompHandle_t handle, cudecompGridDesc_t grid_d
     if (!input) THROW_INVALID_USAGE("input argument cannot be null");                                                  \
     if (!output) THROW_INVALID_USAGE("output argument cannot be null");                                                \
     if (!work) THROW_INVALID_USAGE("work argument cannot be null");                                                    \
+    NvtxRange nvtx_range(#NAME);                                                                                       \
     runTranspose(handle, grid_desc, AX, DIR, input, output, work, dtype, input_halo_extents, output_halo_extents,      \
                  input_padding, output_padding, stream);                                                               \
     API_CATCH()                                                                                                        \
@@ -653,6 +655,7 @@ TRANSPOSE_ENTRY(cudecompTransposeYToX, 1, -1)
     if (!input) THROW_INVALID_USAGE("input argument cannot be null");                                                  \
     if (!work) THROW_INVALID_USAGE("work argument cannot be null");                                                    \
     if (dim < 0 || dim > 2) THROW_INVALID_USAGE("dim argument out of range");                                          \
+    NvtxRange nvtx_range(std::string(#NAME "_") + std::to_string(dim));                                                \
     runHalo(handle, grid_desc, AX, input, work, dtype, halo_extents, halo_periods, dim, padding, stream);              \
     API_CATCH()                                                                                                        \
   }

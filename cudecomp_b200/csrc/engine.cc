@@ -6,6 +6,7 @@
 
 #include "errors.h"
 #include "launch_params.h"
+#include "nvtx_ranges.h"
 
 namespace cdb {
 
@@ -234,6 +235,7 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
     return;
   }
   perf.exchange = true;
+  NvtxRange nvtx_exchange("cudecompAlltoall"); // descriptor exchange + the peer-store launch(es): the reference's a2a phase
 
   // Tell the other members which buffers this call uses and learn theirs.
   CallMsg mine;
@@ -338,6 +340,7 @@ void runHalo(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, void* input, voi
   }
 
   perf.exchange = true;
+  NvtxRange nvtx_exchange("cudecompSendRecvPair");
   CallMsg mine;
   std::memset(&mine, 0, sizeof(mine));
   mine.opcode = haloOpcode(ax, dim);

@@ -18,7 +18,7 @@ for f in cudecomp_b200/csrc/*.cc; do
 done
 wait
 g++ -shared -fsanitize=address,undefined -o $B/libcudecomp.so $B/*.cc.o cudecomp_b200/build/kernels.cu.o \
-    -L/usr/local/cuda/lib64 -lcudart -lrt -lpthread || exit 1
+    -L/usr/local/cuda/lib64 -lcudart -lrt -lpthread -ldl || exit 1
 cp cudecomp_b200/lib/libcudecomp.so $B/libcudecomp.release.so
 restore() { cp $B/libcudecomp.release.so cudecomp_b200/lib/libcudecomp.so; touch cudecomp_b200/lib/libcudecomp.so; }
 trap restore EXIT
