@@ -137,45 +137,55 @@ PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<in
   const auto in_str = pa_h.strideG();
   pp.steps.resize(K);
 
-  // ---- push: every box cut by my chunks of the source planes
-  const int64_t nG_me = shape_a[G];
+  // ---- push: step k moves the k-th slice of EVERY box along G (slices are relative to the box, so each step is a
+  // complete all-to-all of 1/K of the data: when G is the split axis `a` the boxes are consecutive plane ranges of my
+  // pencil, and cutting the pencil instead of the boxes would send whole steps to a single peer)
   for (const BoxDesc& box : pp.base.push) {
-    const int64_t start = (G == a) ? off_a[box.peer] : 0; // where the box begins along G in my pencil
     const int64_t len = box.ext[G];
     for (int k = 0; k < K; ++k) {
-      auto [c0, c1] = chunkRange(nG_me, K, k);
-      const int64_t lo = std::max(c0, start), hi = std::min(c1, start + len);
+      auto [lo, hi] = chunkRange(len, K, k);
       if (hi <= lo) continue;
       BoxDesc sub = box;
       sub.ext[G] = hi - lo;
-      sub.src_off += (lo - start) * box.sstr[G];
-      sub.dst_off += (lo - start) * box.dstr[G];
+      sub.src_off += lo * box.sstr[G];
+      sub.dst_off += lo * box.dstr[G];
       pp.steps[k].push.push_back(sub);
     }
   }
 
-  // ---- unpack: what source j's chunk k leaves in my workspace, and the first step at which its destination is free
+  // Source planes (along G, interior coordinates of my pencil) that no push has read after step `step`: one range per
+  // box. G is the slowest axis of the source, so a plane range is one address interval of the input buffer.
+  auto unreadIntervals = [&](int step) {
+    std::vector<std::pair<int64_t, int64_t>> iv; // [first element, one past the last element) of the input buffer
+    for (const BoxDesc& box : pp.base.push) {
+      const int64_t start = (G == a) ? off_a[box.peer] : 0;
+      const int64_t len = box.ext[G];
+      const int64_t first = (step + 1 < K) ? chunkRange(len, K, step + 1).first : len;
+      if (first >= len) continue;
+      iv.push_back({(start + first + pa_h.halo[G]) * in_str[G], (start + len + pa_h.halo[G]) * in_str[G]});
+      if (G != a) break; // every box spans the same planes
+    }
+    return iv;
+  };
+
+  // ---- unpack: what source j's slice k leaves in my workspace, and the first step at which its destination is free
   const auto dense = pb.strideG();
   const auto out_str = pb_h.strideG();
   for (int j = 0; j < P; ++j) {
-    // extent of rank j's source pencil along G, and the part of it that travels to me
-    int64_t nG_j, startj, lenj;
+    // extent along G of the box rank j sends to me, and where it starts in my (dense) destination pencil
+    int64_t lenj, dst0;
     if (G == a) {
-      nG_j = g.gdims[a];
-      startj = off_a[me];
-      lenj = splits_a[me];
+      lenj = splits_a[me]; // my share of a: the same slice of it arrives from every source
+      dst0 = 0;
     } else if (G == b) {
-      nG_j = splits_b[j];
-      startj = 0;
-      lenj = splits_b[j];
+      lenj = splits_b[j]; // rank j's own share of b
+      dst0 = off_b[j];
     } else {
-      nG_j = shape_a[G];
-      startj = 0;
       lenj = shape_a[G];
+      dst0 = 0;
     }
     for (int k = 0; k < K; ++k) {
-      auto [c0, c1] = chunkRange(nG_j, K, k);
-      const int64_t u0 = std::max(c0, startj), u1 = std::min(c1, startj + lenj);
+      auto [u0, u1] = chunkRange(lenj, K, k);
       if (u1 <= u0) continue;
       // the piece in the coordinates of my (dense) destination pencil
       std::array<int64_t, 3> s0{}, ext{};
@@ -185,13 +195,7 @@ PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<in
       }
       s0[b] = off_b[j];
       ext[b] = splits_b[j];
-      if (G == a) {
-        s0[G] = u0 - off_a[me];
-      } else if (G == b) {
-        s0[G] = off_b[j] + u0;
-      } else {
-        s0[G] = u0;
-      }
+      s0[G] = dst0 + u0;
       ext[G] = u1 - u0;
       BoxDesc piece;
       piece.peer = me;
@@ -206,11 +210,14 @@ PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<in
 
       int step = k;
       if (inplace) {
-        // last element this piece writes, against the first source plane no push has read yet
+        // the elements this piece writes, [first, last], against the source planes that are still unread
+        const int64_t first = piece.dst_off;
         const int64_t last = piece.dst_off + (ext[0] - 1) * out_str[0] + (ext[1] - 1) * out_str[1] + (ext[2] - 1) * out_str[2];
         for (step = k; step < K - 1; ++step) {
-          const int64_t first_unread = (chunkRange(nG_me, K, step + 1).first + pa_h.halo[G]) * in_str[G];
-          if (last < first_unread) break;
+          bool clear = true;
+          for (auto& iv : unreadIntervals(step))
+            if (first < iv.second && last >= iv.first) clear = false;
+          if (clear) break;
         }
       }
       pp.steps[step].unpack.push_back(piece);
