@@ -20,7 +20,7 @@ def declared_functions(header):
     return sorted(n for n in names - inline if not n.isupper() and not n.endswith("_t"))
 
 
-@pytest.mark.parametrize("header", ["cudecomp.h", "cudecomp_b200_ext.h", "mpi_shim/mpi.h"])
+@pytest.mark.parametrize("header", ["cudecomp.h", "cudecomp_b200_ext.h", "cudecomp_b200_mpi.h", "mpi_shim/mpi.h"])
 def test_library_exports_every_declared_symbol(header):
     names = declared_functions(header)
     assert len(names) >= 6
