@@ -82,6 +82,14 @@ static inline cudecompResult_t cudecompB200InitFromMPI(cudecompHandle_t* handle,
     for (i = 256; i < 256 + 15 && rendezvous[i] >= '0' && rendezvous[i] <= '9'; ++i) port = port * 10 + (rendezvous[i] - '0');
     if (port <= 0) return CUDECOMP_RESULT_INTERNAL_ERROR;
     rendezvous[255] = 0;
+    {
+      /* ranks on rank 0's own host dial the loopback address: host names do not always resolve (containers) */
+      char mine[MPI_MAX_PROCESSOR_NAME + 1];
+      int len = 0;
+      memset(mine, 0, sizeof(mine));
+      if (MPI_Get_processor_name(mine, &len) == MPI_SUCCESS && len > 0 && strcmp(mine, rendezvous) == 0)
+        strcpy(rendezvous, "127.0.0.1");
+    }
     return cudecompB200InitBootstrap(handle, rank, size, rendezvous, port);
   }
 }
