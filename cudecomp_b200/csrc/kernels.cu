@@ -398,15 +398,16 @@ int maxResidentCtas(KernelKind kind, int size, int threads, uint32_t peer_order)
 }
 
 static cudaError_t launchBulk(const CopyParams& p, const LaunchConfig& cfg, cudaStream_t stream) {
-  static bool configured = false;
   const int smem = kBulkStages * static_cast<int>(kBulkChunkBytes);
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(rowCopyBulkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);
+  // the opt-in for more than 48 KiB of dynamic shared memory is per device (a process may drive several)
+  static std::atomic<uint64_t> configured_devices{0};
+  if (dev >= 64 || !(configured_devices.load(std::memory_order_relaxed) & (1ull << dev))) {
+    cudaError_t e = cudaFuncSetAttribute(rowCopyBulkKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    if (dev < 64) configured_devices.fetch_or(1ull << dev, std::memory_order_relaxed);
+  }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const uint64_t total = static_cast<uint64_t>(p.nboxes) * p.max_tiles;
   // one TMA-driving CTA per SM by default (3 fit by shared memory)
