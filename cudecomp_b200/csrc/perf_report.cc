@@ -45,7 +45,15 @@ const char* dtypeLetter(cudecompDataType_t d) {
 struct Row {
   const PerfSeries* series;
   double count = 0, total = 0, exch = 0, local = 0; // sums over samples, then over ranks
+  // per-sample values of this rank in ring order (CUDECOMP_PERFORMANCE_REPORT_DETAIL > 0), 4 floats per sample:
+  // total, exchange, local [ms], exchange bandwidth [GB/s]
+  std::vector<float> samples;
+  // detail level 2: every rank's samples, `slots` samples per rank, unused slots hold a negative total
+  std::vector<float> all_samples;
+  int slots = 0;
 };
+
+void printSamples(const PerfSettings& s_, cudecompHandle* h, cudecompGridDesc* gd, const std::vector<Row>& rows, bool transposes);
 
 std::string csvName(const cudecompGridDesc* gd, const char* kind) {
   std::ostringstream f;
@@ -180,6 +188,8 @@ void PerfReport::print(cudecompHandle* h, cudecompGridDesc* gd) {
         r.total += total;
         r.exch += exch;
         r.local += local;
+        const double bw = exch > 0 ? static_cast<double>(kv.second.bytes) / 1e6 / exch : 0.0;
+        r.samples.insert(r.samples.end(), {total, static_cast<float>(exch), static_cast<float>(local), static_cast<float>(bw)});
       }
       rows.push_back(r);
     }
@@ -205,6 +215,16 @@ void PerfReport::print(cudecompHandle* h, cudecompGridDesc* gd) {
       }
     } else if (!same && h->rank == 0) {
       std::printf("CUDECOMP:WARN: ranks recorded different operation sets; the report shows rank 0 only\n");
+    }
+    if (same && s_.detail >= 2) {
+      // every rank contributes `samples` slots per configuration (reference: gatherSampleData, src/performance.cc)
+      for (auto& r : rows) {
+        r.slots = s_.samples;
+        std::vector<float> mine(static_cast<size_t>(r.slots) * 4, -1.0f);
+        std::copy(r.samples.begin(), r.samples.begin() + std::min(r.samples.size(), mine.size()), mine.begin());
+        r.all_samples.resize(mine.size() * static_cast<size_t>(h->nranks));
+        allgather(*h->comm, mine.data(), mine.size() * sizeof(float), r.all_samples.data());
+      }
     }
     return rows;
   };
@@ -308,7 +328,82 @@ void PerfReport::print(cudecompHandle* h, cudecompGridDesc* gd) {
       }
     }
   }
+  if (s_.detail > 0) {
+    std::printf("CUDECOMP:\nCUDECOMP: Per-Sample Details:\nCUDECOMP:\n");
+    printSamples(s_, h, gd, trows, true);
+    printSamples(s_, h, gd, hrows, false);
+  }
+  std::printf("CUDECOMP: ================================\nCUDECOMP:\n");
   std::fflush(stdout);
 }
+
+// Per-sample tables and CSV files (CUDECOMP_PERFORMANCE_REPORT_DETAIL 1: this rank's samples, 2: every rank's), in the
+// reference's format (src/performance.cc:560-770). Rank 0 only.
+namespace {
+void printSamples(const PerfSettings& s_, cudecompHandle* h, cudecompGridDesc* gd, const std::vector<Row>& rows, bool transposes) {
+  bool any = false;
+  for (auto& r : rows)
+    if (r.count > 0) any = true;
+  if (!any) return;
+  std::ofstream csv;
+  std::string path;
+  if (!s_.write_dir.empty()) {
+    path = s_.write_dir + "/" + csvName(gd, transposes ? "transpose-samples" : "halo-samples");
+    csv.open(path);
+    if (!csv) {
+      std::printf("CUDECOMP: Warning: Could not open file %s for writing\n", path.c_str());
+    } else {
+      csvHeader(csv, gd);
+      csv << (transposes ? "operation,dtype,input_halo_extents,output_halo_extents,input_padding,output_padding,inplace,"
+                           "managed,rank,sample,total_ms,A2A_ms,local_ms,A2A_BW_GBps\n"
+                         : "operation,dtype,dim,halo_extent,periods,padding,managed,rank,sample,total_ms,SR_ms,local_ms,"
+                           "SR_BW_GBps\n");
+      csv << std::fixed << std::setprecision(3);
+    }
+  }
+  for (auto& r : rows) {
+    if (r.count <= 0) continue;
+    const PerfSeries& s = *r.series;
+    if (transposes)
+      std::printf("CUDECOMP: %s (dtype=%s, halo extents=%s/%s, padding=%s/%s, inplace=%s, managed=%s) samples:\n",
+                  s.operation.c_str(), s.dtype.c_str(), s.halos_a.c_str(), s.halos_b.c_str(), s.pads_a.c_str(),
+                  s.pads_b.c_str(), s.flag_a.c_str(), s.flag_b.c_str());
+    else
+      std::printf("CUDECOMP: %s (dtype=%s, dim=%d, halos=%s, periods=%s, padding=%s, managed=%s) samples:\n",
+                  s.operation.c_str(), s.dtype.c_str(), s.dim, s.halos_a.c_str(), s.flag_a.c_str(), s.pads_a.c_str(),
+                  s.flag_b.c_str());
+    const char* ex = transposes ? "A2A" : "SR";
+    std::printf("CUDECOMP: %-6s %-12s %-9s %-9s %-9s %-9s\n", "rank", "sample", "total", ex, "local",
+                (std::string(ex) + " BW").c_str());
+    std::printf("CUDECOMP: %-6s %-12s %-9s %-9s %-9s %-9s\n", "", "", "[ms]", "[ms]", "[ms]", "[GB/s]");
+    const bool all = s_.detail >= 2 && !r.all_samples.empty();
+    const int nranks = all ? h->nranks : 1;
+    for (int rank = 0; rank < nranks; ++rank) {
+      const float* v = all ? r.all_samples.data() + static_cast<size_t>(rank) * r.slots * 4 : r.samples.data();
+      const int n = all ? r.slots : static_cast<int>(r.samples.size() / 4);
+      for (int k = 0; k < n; ++k) {
+        if (v[4 * k] < 0) continue; // unused slot
+        std::printf("CUDECOMP: %-6d %-12d %-9.3f %-9.3f %-9.3f %-9.3f\n", rank, k, v[4 * k], v[4 * k + 1], v[4 * k + 2],
+                    v[4 * k + 3]);
+        if (csv.is_open()) {
+          csv << s.operation << "," << s.dtype << ",";
+          if (transposes)
+            csv << "\"" << s.halos_a << "\",\"" << s.halos_b << "\",\"" << s.pads_a << "\",\"" << s.pads_b << "\"," << s.flag_a
+                << "," << s.flag_b;
+          else
+            csv << s.dim << ",\"" << s.halos_a << "\",\"" << s.flag_a << "\",\"" << s.pads_a << "\"," << s.flag_b;
+          csv << "," << rank << "," << k << "," << v[4 * k] << "," << v[4 * k + 1] << "," << v[4 * k + 2] << "," << v[4 * k + 3]
+              << "\n";
+        }
+      }
+    }
+    std::printf("CUDECOMP:\n");
+  }
+  if (csv.is_open()) {
+    csv.close();
+    std::printf("CUDECOMP:\nCUDECOMP: Wrote per-sample %s data to %s\n", transposes ? "transpose" : "halo", path.c_str());
+  }
+}
+} // namespace
 
 } // namespace cdb

@@ -20,7 +20,7 @@ def test_performance_report_table_and_csv():
                   periods=[True] * 3, fills=["random", "pattern"])]
     results, logs = run_ranks(2, "gpu", cases, timeout=300, extra_env={
         "CUDECOMP_ENABLE_PERFORMANCE_REPORT": "1", "CUDECOMP_PERFORMANCE_REPORT_WARMUP_SAMPLES": "1",
-        "CUDECOMP_PERFORMANCE_REPORT_WRITE_DIR": out_dir})
+        "CUDECOMP_PERFORMANCE_REPORT_DETAIL": "2", "CUDECOMP_PERFORMANCE_REPORT_WRITE_DIR": out_dir})
     for r in range(2):
         for c in results[r]:
             assert c["ok"], c
@@ -45,3 +45,13 @@ def test_performance_report_table_and_csv():
     assert "# Process grid: [2, 1]" in text
     assert "operation,dtype,dim,halo_extent,periods,padding,managed,samples,total_ms,SR_ms,local_ms,SR_BW_GBps" in \
         open(hfiles[0]).read()
+    # detail level 2: per-sample rows of both ranks, and the per-sample CSV files (reference src/performance.cc:560-770)
+    assert "CUDECOMP: Per-Sample Details:" in log
+    assert "CUDECOMP: TransposeXY (dtype=D, halo extents=[0,0,0]/[0,0,0], padding=[0,0,0]/[0,0,0], inplace=N, managed=N) samples:" in log
+    sample_rows = [l.split() for l in log.splitlines() if l.startswith("CUDECOMP: ") and len(l.split()) == 7 and
+                   l.split()[1] in ("0", "1") and l.split()[2].isdigit()]
+    assert {r[1] for r in sample_rows} == {"0", "1"}  # both ranks' samples gathered on rank 0
+    sfiles = glob.glob(os.path.join(out_dir, "cudecomp-perf-report-transpose-samples-*.csv"))
+    assert sfiles and ("operation,dtype,input_halo_extents,output_halo_extents,input_padding,output_padding,inplace,managed,"
+                       "rank,sample,total_ms,A2A_ms,local_ms,A2A_BW_GBps") in open(sfiles[0]).read()
+    assert glob.glob(os.path.join(out_dir, "cudecomp-perf-report-halo-samples-*.csv"))
