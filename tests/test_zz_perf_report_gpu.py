@@ -30,7 +30,7 @@ def test_performance_report_table_and_csv():
     rows = [l for l in log.splitlines() if l.startswith("CUDECOMP: Transpose")]
     assert any(l.split()[1] == "TransposeXY" and l.split()[2] == "D" for l in rows), rows
     # an out-of-place exchange is one kernel: everything is A2A time, nothing local; in-place has a local unpack
-    xy = [l.split() for l in rows if l.split()[1] == "TransposeXY"]
+    xy = [l.split() for l in rows if l.split()[1] == "TransposeXY" and l.split()[2] == "D"]  # table rows, not sample headers
     assert len(xy) == 2
     for f in xy:
         total, a2a, local = float(f[-4]), float(f[-3]), float(f[-2])
