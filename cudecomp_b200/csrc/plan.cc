@@ -208,16 +208,38 @@ PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<in
       piece.dst_off = dot3(d0, out_str);
       if (piece.count() == 0) continue;
 
-      int step = k;
-      if (inplace) {
-        // the elements this piece writes, [first, last], against the source planes that are still unread
-        const int64_t first = piece.dst_off;
-        const int64_t last = piece.dst_off + (ext[0] - 1) * out_str[0] + (ext[1] - 1) * out_str[1] + (ext[2] - 1) * out_str[2];
-        for (step = k; step < K - 1; ++step) {
+      // first step at which everything `pc` writes has been read by the pushes (in place only)
+      auto firstFreeStep = [&](const BoxDesc& pc) {
+        const int64_t first = pc.dst_off;
+        const int64_t last = pc.dst_off + (pc.ext[0] - 1) * out_str[0] + (pc.ext[1] - 1) * out_str[1] + (pc.ext[2] - 1) * out_str[2];
+        int st = k;
+        for (; st < K - 1; ++st) {
           bool clear = true;
-          for (auto& iv : unreadIntervals(step))
+          for (auto& iv : unreadIntervals(st))
             if (first < iv.second && last >= iv.first) clear = false;
           if (clear) break;
+        }
+        return st;
+      };
+      int step = k;
+      if (inplace) {
+        step = firstFreeStep(piece);
+        // A piece that has to wait is cut along the slowest axis of the destination layout and every part waits only
+        // for the source planes IT overwrites: a piece spans P source slices' worth of memory when G is the split
+        // axis, so uncut it would wait for the last of them (P/K of the pencil left for after the last push; 1/K cut).
+        const int D = pb.order[2];
+        const int64_t parts = std::min<int64_t>(piece.ext[D], std::min(P, 8));
+        if (step > k && parts > 1) {
+          for (int64_t q = 0; q < parts; ++q) {
+            auto [q0, q1] = chunkRange(piece.ext[D], static_cast<int>(parts), static_cast<int>(q));
+            if (q1 <= q0) continue;
+            BoxDesc part = piece;
+            part.ext[D] = q1 - q0;
+            part.src_off += q0 * dense[D];
+            part.dst_off += q0 * out_str[D];
+            pp.steps[firstFreeStep(part)].unpack.push_back(part);
+          }
+          continue;
         }
       }
       pp.steps[step].unpack.push_back(piece);
