@@ -513,7 +513,7 @@ def plan_halo_boxes(config, rank, ax, dim, halo_extents, halo_periods=None, padd
 
 
 def plan_pipelined_transpose_boxes(config, rank, ax, direction, input_halo_extents=None, output_halo_extents=None,
-                                   input_padding=None, output_padding=None, inplace=False, nchunks=4, max_boxes=1024):
+                                   input_padding=None, output_padding=None, inplace=False, nchunks=4, max_boxes=8192):
     """Chunked staged schedule (boxes carry their step). Empty list when chunking does not apply."""
     arr = (cudecompB200Box_t * max_boxes)()
     n = lib.cudecompB200PlanPipelinedTransposeBoxes(ctypes.byref(config), rank, ax, direction,
