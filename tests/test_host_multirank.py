@@ -212,3 +212,17 @@ def test_descriptor_mailbox_stress(nranks):
                            timeout=300)
     for r in range(nranks):
         assert all(c["ok"] for c in results[r]), results[r]
+
+
+def test_sixteen_ranks_plans_and_mailbox():
+    """Communicators of 16 ranks (one launch carries at most 16 boxes, kernels.h kMaxBoxes): 4x4 and both slab grids,
+    planned by 16 real processes, executed with numpy and compared with the oracle; then the mailbox with 16 members."""
+    cases = [dict(kind="transpose", name="p4x4", gdims=[33, 34, 35], pdims=[4, 4], dtype="double"),
+             dict(kind="transpose", name="p16x1", gdims=[40, 34, 35], pdims=[16, 1], dtype="double"),
+             dict(kind="transpose", name="p1x16_axis_contiguous", gdims=[40, 34, 35], pdims=[1, 16], dtype="double",
+                  axis_contiguous=[True] * 3)]
+    results, _ = run_ranks(16, "plan", cases, timeout=500)
+    for i, case in enumerate(cases):
+        check_transposes(case, [r[i] for r in results])
+    results, _ = run_ranks(16, "mailbox", [dict(name="stress16", iterations=2000, seed=9)], timeout=500)
+    assert all(r[0]["ok"] for r in results)
