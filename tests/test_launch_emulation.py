@@ -266,3 +266,25 @@ def test_balanced_grid():
         assert 296 <= b <= 370
         util = lambda c: slots / (c * -(-slots // c))
         assert util(b) >= util(370) - 1e-12
+
+
+def test_seventeen_rank_communicator_needs_two_launches():
+    """17 ranks in one communicator = 17 boxes per transpose, one more than a launch carries (kMaxBoxes = 16): the boxes
+    are split over two launches (the handshake enters with the first and leaves with the last, engine.cc launchBoxes)."""
+    for pdims in ([17, 1], [1, 17]):
+        d = dict(gdims=[40, 36, 38], pdims=pdims, axis_contiguous=[False] * 3, mem_order=None, gdims_dist=None,
+                 col_major=False, halos={str(a): [0, 0, 0] for a in range(3)}, pads={str(a): [0, 0, 0] for a in range(3)})
+        s = dict(es=8, tile_bytes=0, peer_order=1, kernel_variant=0, grid=5, threads=256, misalign=0)
+        check_transposes(d, s)
+        cfg, o = make_config(d), make_oracle(d)
+        op = "XY" if pdims[0] == 17 else "YZ"
+        ax, direction = OPS[op]
+        a, b = orc.transpose_axes(op)
+        push = cd.plan_transpose_boxes(cfg, 3, ax, direction)
+        assert len(push) == 17
+        src = emu.aligned_array(o.pencil_info(3, a).size, np.int64, 0, 1)
+        outs = {bx["peer_rank"]: emu.aligned_array(o.pencil_info(bx["peer_rank"], b).size, np.int64, 0, 0) for bx in push}
+        gi = group_index(push)
+        st_ = emu.run_boxes(push, [src] * 17, [outs[bx["peer_rank"]] for bx in push], 8, [src] + list(outs.values()),
+                            me=gi[3], comm_size=17, peer_index=[gi[bx["peer_rank"]] for bx in push])
+        assert st_["launches"] == 2
