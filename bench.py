@@ -135,7 +135,10 @@ def run_reference(args, rank, world):
     nz = max(nz, pd[1] * 4)
     gd = [n, n, nz]
     o = orc.Oracle(gd, pd, (args.axis_contiguous,) * 3)
-    cores = o.max_threads()
+    # every core this process may run on: torchrun exports OMP_NUM_THREADS=1 to its workers, which would leave the
+    # reference arm single-threaded at N > 1 although the other ranks exit immediately
+    cores = len(os.sched_getaffinity(0))
+    o.set_threads(cores)
     dt = orc.NP_DTYPES[args.dtype]
     es = np.dtype(dt).itemsize
     bufs_a = [np.ones(max(o.pencil_info(r, ax).size for ax in range(3)), dt) for r in range(o.nranks)]
@@ -487,6 +490,7 @@ def cpu_baseline(args, pd):
     from oracle import oracle as orc
     n, nz = args.n, 32
     o = orc.Oracle([n, n, nz], pd, (args.axis_contiguous,) * 3)
+    o.set_threads(len(os.sched_getaffinity(0)))
     dt = orc.NP_DTYPES[args.dtype]
     es = np.dtype(dt).itemsize
     A = [np.ones(o.pencil_info(0, 0).size, dt)]
