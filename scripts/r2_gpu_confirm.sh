@@ -110,3 +110,4 @@ if [ "$N" != 1 ] && [ -x oracle/_ref/benchmark_c2c ]; then
   CUDECOMP_B200_PIPELINE_CHUNKS=8 refbench inplace_chunks8 --gx 1024 --gy 1024 --gz 1024 -r $PR -c $PC -b 4
   refbench autotune --gx 1024 --gy 1024 --gz 1024 -r 0 -c 0 -b 0 -o
 fi
+echo "== summary table"; python scripts/r2_summarize.py $OUT > $OUT/r2_n${N}_summary.md 2>&1; cat $OUT/r2_n${N}_summary.md | head -60
