@@ -183,9 +183,13 @@ class RestatedTranspose:
                 self.groups[members] = grp
 
     def _dist_exchange(self, send, recv, send_counts, recv_counts, members):
+        import torch
         import torch.distributed as dist
         n_in, n_out = sum(send_counts), sum(recv_counts)
-        dist.all_to_all_single(recv[:n_out], send[:n_in], recv_counts, send_counts, group=self.groups[tuple(members)])
+        es = send.element_size()
+        # exchanged as raw bytes: the payload is never computed on, and not every backend accepts complex tensors
+        dist.all_to_all_single(recv[:n_out].view(torch.uint8), send[:n_in].view(torch.uint8), [c * es for c in recv_counts],
+                               [c * es for c in send_counts], group=self.groups[tuple(members)])
 
 
 def _prod(shape):
