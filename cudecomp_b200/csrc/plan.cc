@@ -228,7 +228,7 @@ PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<in
         // for the source planes IT overwrites: a piece spans P source slices' worth of memory when G is the split
         // axis, so uncut it would wait for the last of them (P/K of the pencil left for after the last push; 1/K cut).
         const int D = pb.order[2];
-        const int64_t parts = std::min<int64_t>(piece.ext[D], std::min(P, 8));
+        const int64_t parts = std::min<int64_t>(piece.ext[D], std::min(std::max(P, K), 16));
         if (step > k && parts > 1) {
           for (int64_t q = 0; q < parts; ++q) {
             auto [q0, q1] = chunkRange(piece.ext[D], static_cast<int>(parts), static_cast<int>(q));
