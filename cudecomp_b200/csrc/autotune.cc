@@ -489,7 +489,7 @@ void autotuneTransposes(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecom
         tryAlternatives();
       }
       if (dims.chunks && (any_inplace || backendIsStaged(best_backend))) {
-        for (int k : {4, 8}) {
+        for (int k : {4, 8, 16}) {
           Schedule a = best_schedule;
           a.chunks = k;
           alternatives.push_back(a);
