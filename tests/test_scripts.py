@@ -1,0 +1,35 @@
+"""The host-only helper scripts keep working: scripts/explain_plan.py (plans, tiling and the time model for a
+configuration) and scripts/r2_summarize.py (markdown table from bench JSON lines)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_explain_plan_reproduces_the_measured_round_trips():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "explain_plan.py"), "--grid", "1024", "--pdims", "2x4",
+                          "--chunks", "8"], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert out.returncode == 0, out.stderr
+    last = out.stdout.strip().splitlines()[-1]
+    # "round trip, model: out of place (direct) 8.17 ms; in place staged 10.82 ms; in place chunked (K = 8) 8.77 ms"
+    nums = [float(tok) for tok in last.replace(";", " ").split() if tok.replace(".", "", 1).isdigit() and "." in tok]
+    direct, staged, chunked = nums
+    assert abs(direct - 8.10) < 0.3 and abs(staged - 10.76) < 0.3  # measured: profiles/r1_n8_bench*.json
+    assert direct < chunked < staged
+    # every step of every chunked operation is a complete all-to-all (no step talks to a single peer of a 4-rank group)
+    for line in out.stdout.splitlines():
+        if "peers per step" in line:
+            assert "peers per step [2]" in line or "peers per step [4]" in line, line
+
+
+def test_r2_summarize_reads_bench_lines(tmp_path):
+    for name, src in (("r2_n8_default.json", "r1_n8_bench.json"), ("r2_n8_inplace.json", "r1_n8_bench_inplace.json")):
+        with open(os.path.join(ROOT, "profiles", src)) as f:
+            line = json.loads(f.readline())
+        (tmp_path / name).write_text(json.dumps(line) + "\n")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "r2_summarize.py"), str(tmp_path)],
+                         capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    assert "### 8 GPUs" in out.stdout and "| default |" in out.stdout and "| inplace |" in out.stdout
