@@ -65,6 +65,38 @@ template <int U, int H> __global__ void __launch_bounds__(512) simtCopy(const ui
   }
 }
 
+// 256-bit accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256): the same tile shape with 32-byte vectors, i.e. one
+// warp instruction covers 1 KiB. Question for the NVLink path: do wider stores raise the SM-store ceiling?
+struct alignas(32) V32 {
+  uint64_t a, b, c, d;
+};
+__device__ __forceinline__ V32 ld256(const V32* p) {
+  V32 v;
+  asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st256(V32* p, V32 v) {
+  asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v.a), "l"(v.b), "l"(v.c), "l"(v.d) : "memory");
+}
+template <int U> __global__ void __launch_bounds__(256) simtCopy256(const V32* src, V32* dst, size_t nvec) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const size_t tile = 1024; // 32 KiB
+  const size_t ntiles = (nvec + tile - 1) / tile;
+  for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const size_t base = t * tile;
+    const uint32_t n = (uint32_t)((nvec - base < tile) ? nvec - base : tile);
+    for (uint32_t p = warp * 32 * U; p < n; p += nw * 32 * U) {
+      V32 v[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        if (p + lane + 32 * k < n) v[k] = ld256(src + base + p + lane + 32 * k);
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        if (p + lane + 32 * k < n) st256(dst + base + p + lane + 32 * k, v[k]);
+    }
+  }
+}
+
 // P=2 transpose shape: half of the tiles stay local, half go to the peer.
 // mode 0: tiles alternate local/peer inside every CTA; mode 1: the first `peer_ctas` CTAs only push, the rest only copy.
 template <int U> __global__ void __launch_bounds__(256) mixedCopy(const uint4* src, uint4* dst_local, uint4* dst_peer,
@@ -255,6 +287,17 @@ int main(int argc, char** argv) {
     fflush(stdout);
   };
 
+  // PULL instead of push: the same kernels reading the PEER's buffer and writing local memory (only meaningful for the
+  // two peer columns; "local" repeats the local copy). If remote loads beat remote stores, a receiver-driven transpose
+  // would have a higher ceiling than the sender-driven one the engine uses.
+  auto reportPull = [&](const char* name, auto launchTo) {
+    if (ndev != 2) return;
+    double p1 = timeIt({&dv[0]}, [&](Dev& d) { launchTo(d, dv[1 - d.id].a, d.b); });
+    double p2 = timeIt({&dv[0], &dv[1]}, [&](Dev& d) { launchTo(d, dv[1 - d.id].a, d.b); });
+    printf("%-44s %10s %10.1f %10.1f\n", name, "(pull)", bytes / p1 / 1e6, bytes / p2 / 1e6);
+    fflush(stdout);
+  };
+
   report("cudaMemcpyAsync (copy engine)", [&](Dev& d, char* s, char* t) {
     CK(cudaMemcpyAsync(t, s, bytes, cudaMemcpyDeviceToDevice, d.st));
   });
@@ -263,6 +306,22 @@ int main(int argc, char** argv) {
     char nm[96];
     snprintf(nm, sizeof nm, "simt U=4 cs grid=%d", grid);
     report(nm, [&](Dev& d, char* s, char* t) { simtCopy<4, CS><<<grid, 256, 0, d.st>>>((const uint4*)s, (uint4*)t, nvec); });
+  }
+  for (int grid : {sms * 1, sms * 2, sms * 5 / 2, sms * 4}) {
+    char nm[96];
+    snprintf(nm, sizeof nm, "simt 256-bit U=2 grid=%d", grid);
+    report(nm, [&](Dev& d, char* s, char* t) { simtCopy256<2><<<grid, 256, 0, d.st>>>((const V32*)s, (V32*)t, bytes / 32); });
+    snprintf(nm, sizeof nm, "simt 256-bit U=4 grid=%d", grid);
+    report(nm, [&](Dev& d, char* s, char* t) { simtCopy256<4><<<grid, 256, 0, d.st>>>((const V32*)s, (V32*)t, bytes / 32); });
+  }
+  for (int grid : {sms * 1, sms * 2, sms * 5 / 2, sms * 4, sms * 8}) {
+    char nm[96];
+    snprintf(nm, sizeof nm, "PULL simt U=4 cs grid=%d", grid);
+    reportPull(nm, [&](Dev& d, char* s, char* t) { simtCopy<4, CS><<<grid, 256, 0, d.st>>>((const uint4*)s, (uint4*)t, nvec); });
+    snprintf(nm, sizeof nm, "PULL simt U=8 cs grid=%d", grid);
+    reportPull(nm, [&](Dev& d, char* s, char* t) { simtCopy<8, CS><<<grid, 256, 0, d.st>>>((const uint4*)s, (uint4*)t, nvec); });
+    snprintf(nm, sizeof nm, "PULL simt 256-bit U=4 grid=%d", grid);
+    reportPull(nm, [&](Dev& d, char* s, char* t) { simtCopy256<4><<<grid, 256, 0, d.st>>>((const V32*)s, (V32*)t, bytes / 32); });
   }
   for (int grid : {sms * 1, sms * 3 / 2, sms * 2, sms * 5 / 2, sms * 3}) {
     char nm[96];
@@ -335,6 +394,16 @@ int main(int argc, char** argv) {
   tma(tmaCopy<4>, 4, 32768, 1);
   tma(tmaCopy<4>, 4, 49152, 1);
   tma(tmaCopy<8>, 8, 2048, 8);
+  for (int i = 0; i < ndev; ++i) {
+    CK(cudaSetDevice(i));
+    CK(cudaFuncSetAttribute(tmaCopy<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 16384));
+  }
+  for (int cps : {1, 2})RUN_PULL_TMA:
+  {
+    char nm[96];
+    snprintf(nm, sizeof nm, "PULL tma bulk stages=8 chunk=16K ctas/SM=%d", cps);
+    reportPull(nm, [&](Dev& d, char* s, char* t) { tmaCopy<8><<<sms * cps, 32, 8 * 16384, d.st>>>(s, t, bytes, 16384); });
+  }
 
   // verify the last TMA copy
   CK(cudaSetDevice(0));

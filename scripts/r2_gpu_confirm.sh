@@ -111,3 +111,4 @@ if [ "$N" != 1 ] && [ -x oracle/_ref/benchmark_c2c ]; then
   refbench autotune --gx 1024 --gy 1024 --gz 1024 -r 0 -c 0 -b 0 -o
 fi
 echo "== summary table"; python scripts/r2_summarize.py $OUT > $OUT/r2_n${N}_summary.md 2>&1; cat $OUT/r2_n${N}_summary.md | head -60
+if [ "$N" = 2 ]; then echo "== copy microbenchmark: push vs pull, 128- vs 256-bit accesses"; nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo bench/microbench_copy.cu -o /tmp/mb && timeout 600 /tmp/mb 2048 > $OUT/r2_n2_microbench_copy.txt 2>&1; grep -E "copy engine|256-bit|PULL|simt U=4 cs grid=370|verify" $OUT/r2_n2_microbench_copy.txt | head -40; fi
