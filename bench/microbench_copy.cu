@@ -398,8 +398,7 @@ int main(int argc, char** argv) {
     CK(cudaSetDevice(i));
     CK(cudaFuncSetAttribute(tmaCopy<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 16384));
   }
-  for (int cps : {1, 2})RUN_PULL_TMA:
-  {
+  for (int cps : {1, 2}) {
     char nm[96];
     snprintf(nm, sizeof nm, "PULL tma bulk stages=8 chunk=16K ctas/SM=%d", cps);
     reportPull(nm, [&](Dev& d, char* s, char* t) { tmaCopy<8><<<sms * cps, 32, 8 * 16384, d.st>>>(s, t, bytes, 16384); });
