@@ -264,7 +264,8 @@ static void initHandle(cudecompHandle_t h, const CommPtr& parent) {
   h->env_col_major = envFlag("CUDECOMP_USE_COL_MAJOR_RANK_ORDER");
   h->perf.readEnvironment();
   if (const char* v = std::getenv("CUDECOMP_B200_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(0, std::atoi(v));
-  if (const char* v = std::getenv("CUDECOMP_B200_KERNEL")) h->kernel_variant = (std::strcmp(v, "bulk") == 0) ? 1 : 0;
+  if (const char* v = std::getenv("CUDECOMP_B200_KERNEL"))
+    h->kernel_variant = (std::strcmp(v, "bulk") == 0) ? 1 : (std::strcmp(v, "wide") == 0 ? 2 : 0);
   if (const char* v = std::getenv("CUDECOMP_B200_TILE_BYTES")) h->tile_bytes = std::max(0, std::atoi(v));
   if (const char* v = std::getenv("CUDECOMP_B200_PEER_ORDER"))
     h->peer_order = (std::strcmp(v, "pairwise") == 0 || std::strcmp(v, "1") == 0) ? 1 : 0;
@@ -696,7 +697,7 @@ cudecompResult_t cudecompB200SetKernelVariant(cudecompHandle_t handle, cudecompG
   API_TRY
   checkHandle(handle);
   checkGridDesc(handle, grid_desc);
-  if (variant < 0 || variant > 1) THROW_INVALID_USAGE("variant must be 0 (LDG/STG) or 1 (TMA bulk)");
+  if (variant < 0 || variant > 2) THROW_INVALID_USAGE("variant must be 0 (LDG/STG.128), 1 (TMA bulk) or 2 (LDG/STG.256)");
   grid_desc->kernel_variant = variant;
   API_CATCH()
 }

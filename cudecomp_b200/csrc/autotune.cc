@@ -233,7 +233,8 @@ std::string describeSchedule(const Schedule& s) {
                   ", order: " + (s.peer_order ? "pairwise" : "one-shot");
   if (s.balance) d += ", balanced grid";
   if (s.chunks > 1) d += ", chunks: " + std::to_string(s.chunks);
-  if (s.variant) d += ", TMA bulk";
+  if (s.variant == 1) d += ", TMA bulk";
+  if (s.variant == 2) d += ", 256-bit LDG/STG";
   return d;
 }
 
@@ -497,9 +498,11 @@ void autotuneTransposes(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecom
         tryAlternatives();
       }
       if (dims.bulk) {
-        Schedule a = best_schedule;
-        a.variant = 1;
-        alternatives.push_back(a);
+        for (int variant : {1, 2}) { // TMA bulk, 256-bit LDG/STG
+          Schedule a = best_schedule;
+          a.variant = variant;
+          alternatives.push_back(a);
+        }
         tryAlternatives();
       }
     }

@@ -97,6 +97,20 @@ __device__ __forceinline__ void syncExit(const SyncParams& s) {
 template <typename V> __device__ __forceinline__ V loadStream(const V* p) { return __ldcs(p); }
 template <typename V> __device__ __forceinline__ void storeStream(V* p, const V& v) { __stcs(p, v); }
 
+// 32-byte vectors: sm_100 has 256-bit global loads and stores (SASS LDG.E.EF.ENL2.256 / STG.E.EF.ENL2.256), one warp
+// instruction then covers 1 KiB. Opt-in (kernel variant 2) until measured against the 128-bit default.
+struct alignas(32) Vec32 {
+  uint64_t a, b, c, d;
+};
+template <> __device__ __forceinline__ Vec32 loadStream<Vec32>(const Vec32* p) {
+  Vec32 v;
+  asm volatile("ld.global.cs.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p));
+  return v;
+}
+template <> __device__ __forceinline__ void storeStream<Vec32>(Vec32* p, const Vec32& v) {
+  asm volatile("st.global.cs.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v.a), "l"(v.b), "l"(v.c), "l"(v.d) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // ROWCOPY: every box is a grid of rows that are contiguous on both sides. V is the widest vector all
 // addresses and strides of the launch are aligned to (16, 8 or 4 bytes).
@@ -352,6 +366,7 @@ using KernelFn = void (*)(const CopyParams);
 template <int kOrder> KernelFn pickKernelOrdered(KernelKind kind, int size) {
   if (kind == KernelKind::ROWCOPY) {
     switch (size) {
+    case 32: return rowCopyKernel<Vec32, kOrder>;
     case 16: return rowCopyKernel<uint4, kOrder>;
     case 8: return rowCopyKernel<uint2, kOrder>;
     case 4: return rowCopyKernel<uint32_t, kOrder>;
@@ -375,7 +390,7 @@ KernelFn pickKernel(KernelKind kind, int size, uint32_t peer_order = 0) {
 } // namespace
 
 int maxResidentCtas(KernelKind kind, int size, int threads, uint32_t peer_order) {
-  static int cache[2][2][3] = {};
+  static int cache[2][2][4] = {};
   static int cache_dev = -1;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -386,7 +401,7 @@ int maxResidentCtas(KernelKind kind, int size, int threads, uint32_t peer_order)
   if (kind == KernelKind::ROWCOPY_BULK) return 0; // not used: launchBulk sizes its own grid
   const int oi = peer_order ? 1 : 0;
   const int ki = (kind == KernelKind::ROWCOPY) ? 0 : 1;
-  const int si = (size == 16) ? 2 : (size == 8 ? 1 : 0);
+  const int si = (size == 32) ? 3 : (size == 16) ? 2 : (size == 8 ? 1 : 0);
   if (threads == 256 && cache[oi][ki][si] > 0) return cache[oi][ki][si];
   KernelFn fn = pickKernel(kind, size, peer_order);
   int per_sm = 0, sms = 0;

@@ -63,7 +63,7 @@ struct CopyParams {
   uint32_t nboxes;
   uint32_t max_tiles; // max over boxes; slot t of the launch -> (box, tile) by slotToBoxTile (tiling.h)
   uint32_t elem_size; // 4, 8 or 16
-  uint32_t vec_size;  // ROWCOPY: 4, 8 or 16
+  uint32_t vec_size;  // ROWCOPY: 4, 8, 16 or 32
   uint32_t peer_order; // slot order: 0 interleaved over the boxes (one-shot), 1 rounds, one peer after the other (pairwise)
   uint32_t pad_[3];
 };

@@ -58,7 +58,7 @@ std::vector<PreparedLaunch> prepareLaunches(const std::vector<LaunchBox>& boxes,
 
   int V = 16;
   if (kind == KernelKind::ROWCOPY) {
-    uint64_t a = 16;
+    uint64_t a = (tuning.kernel_variant == 2) ? 32 : 16; // variant 2: 256-bit accesses where everything is 32-byte aligned
     for (size_t i = 0; i < canon.size(); ++i) {
       const CanonBox& c = canon[i];
       const uint64_t sa = reinterpret_cast<uint64_t>(live[i]->src_base) + static_cast<uint64_t>(live[i]->d.src_off) * es;
@@ -68,7 +68,7 @@ std::vector<PreparedLaunch> prepareLaunches(const std::vector<LaunchBox>& boxes,
         if (c.n[k] > 1) a = std::min({a, lowBit(static_cast<uint64_t>(c.ss[k]) * es), lowBit(static_cast<uint64_t>(c.ds[k]) * es)});
       }
     }
-    V = static_cast<int>(std::min<uint64_t>(a, 16));
+    V = static_cast<int>(std::min<uint64_t>(a, 32));
     if (V < 4) THROW_INVALID_USAGE("buffers must be aligned to the element size");
   }
 

@@ -21,7 +21,8 @@ struct LaunchBox {
 struct LaunchTuning {
   int tile_bytes = 0;     // bytes of a ROWCOPY tile (0: kDefaultTileBytes); power of two in [4 KiB, 256 KiB]
   int peer_order = 0;     // CopyParams::peer_order
-  int kernel_variant = 0; // 1: TMA bulk row copy where every row is 16-byte aligned and at least 2 KiB long
+  int kernel_variant = 0; // 1: TMA bulk row copy where every row is 16-byte aligned and at least 2 KiB long;
+                          // 2: 256-bit LDG/STG where every address and stride is 32-byte aligned (else 128-bit)
 };
 
 constexpr int kDefaultTileBytes = 32768;

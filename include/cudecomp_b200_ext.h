@@ -44,8 +44,9 @@ cudecompResult_t cudecompB200SetTuning(cudecompHandle_t handle, cudecompGridDesc
                                        int32_t force_staged);
 
 /* Row-copy kernel variant: 0 = LDG/STG.128 (default), 1 = TMA bulk copies (cp.async.bulk through shared memory) for
- * launches whose rows are all 16-byte aligned and at least 2 KiB long; other launches keep variant 0. Also settable
- * with CUDECOMP_B200_KERNEL=bulk. EXPERIMENTAL in round 1 (measured equal in bench/microbench_copy.cu, the product
+ * launches whose rows are all 16-byte aligned and at least 2 KiB long; other launches keep variant 0. 2 = 256-bit loads and
+ * stores (sm_100 LDG/STG.256) where every address and stride is 32-byte aligned. Also settable with
+ * CUDECOMP_B200_KERNEL=bulk|wide. EXPERIMENTAL in round 1 (measured equal in bench/microbench_copy.cu, the product
  * kernel is not yet confirmed on hardware). */
 cudecompResult_t cudecompB200SetKernelVariant(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t variant);
 

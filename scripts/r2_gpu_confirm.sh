@@ -44,6 +44,8 @@ if [ "$N" != 1 ]; then
 else
   bench bulk --no-e2e --bulk
 fi
+echo "== 256-bit LDG/STG row copy (kernel variant 2)"
+bench wide --no-e2e --wide
 echo "== tile size / balanced grid (cudecompB200SetSchedule)"
 for t in 16384 65536; do bench tile$t --no-e2e --tile-bytes $t; done
 bench balanced --no-e2e --balance-grid 1
@@ -52,6 +54,7 @@ bench c64_512 --no-e2e --grid 512 --dtype float_complex
 for t in 8192 16384; do bench c64_512_tile$t --no-e2e --grid 512 --dtype float_complex --tile-bytes $t; done
 bench c64_512_balanced --no-e2e --grid 512 --dtype float_complex --balance-grid 1
 bench c64_512_balanced_tile16k --no-e2e --grid 512 --dtype float_complex --balance-grid 1 --tile-bytes 16384
+bench c64_512_wide --no-e2e --grid 512 --dtype float_complex --wide
 bench c64_512_inplace --no-e2e --grid 512 --dtype float_complex --inplace
 if [ "$N" != 1 ]; then
   bench c64_512_inplace_chunks4 --no-e2e --grid 512 --dtype float_complex --inplace --chunks 4

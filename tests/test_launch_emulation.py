@@ -34,7 +34,7 @@ def rand_fill(arr, rng):
 @st.composite
 def schedules(draw):
     return dict(es=draw(st.sampled_from([4, 8, 16])), tile_bytes=draw(st.sampled_from([0, 4096, 8192, 16384, 65536])),
-                peer_order=draw(st.sampled_from([0, 1])), kernel_variant=draw(st.sampled_from([0, 1])),
+                peer_order=draw(st.sampled_from([0, 1])), kernel_variant=draw(st.sampled_from([0, 1, 2])),
                 grid=draw(st.sampled_from([0, 1, 3, 7, 64])), threads=draw(st.sampled_from([256, 128, 64])),
                 misalign=draw(st.sampled_from([0, 0, 1, 2, 3])))
 
@@ -220,6 +220,8 @@ def test_kernel_selection_and_vector_width():
     assert run(4, 0, misalign=4)["vec"] == 4
     assert run(16, 1)["kinds"] == 4        # rows of 128 x 16 B = 2 KiB: TMA bulk
     assert run(8, 1)["kinds"] == 1         # 1 KiB rows: stays SIMT
+    assert run(16, 2)["vec"] == 32         # variant 2: 256-bit accesses, everything here is 32-byte aligned
+    assert run(16, 2, misalign=16)["vec"] == 16  # ... unless a buffer is only 16-byte aligned
     assert run(16, 1)["accesses"] == 2 * 4 * 6   # one bulk copy per row segment: 2 peers x (4 x 6) rows of my pencil
     # axis-contiguous layouts permute: the tiled transpose kernel
     d2 = dict(d, axis_contiguous=[True] * 3)

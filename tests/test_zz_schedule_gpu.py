@@ -23,6 +23,10 @@ CASES = [
     dict(BASE, name="Pairwise_tile8k_balanced_halo_padding", gdims=[48, 32, 40], pdims=[2, 2], dtype="double",
          out_of_place=True, peer_order=1, tile_bytes=8192, balance_grid=1,
          halos={"0": [1, 1, 1], "1": [1, 1, 1], "2": [1, 1, 1]}, pads={"0": [1, 0, 0], "1": [0, 1, 0], "2": [0, 0, 2]}),
+    dict(BASE, name="Wide256_oop_2x2_c128", gdims=[64, 40, 48], pdims=[2, 2], dtype="double_complex", out_of_place=True,
+         kernel_variant=2),
+    dict(BASE, name="Wide256_inplace_2x2_uneven_float_falls_back", gdims=[31, 30, 29], pdims=[2, 2], dtype="float",
+         kernel_variant=2),
     dict(BASE, name="Pairwise_bulk_oop_2x2", gdims=[256, 24, 20], pdims=[2, 2], dtype="double_complex", out_of_place=True,
          peer_order=1, kernel_variant=1),
 ]
