@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--bulk", action="store_true", help="TMA bulk row-copy variant (experimental)")
     ap.add_argument("--wide", action="store_true", help="256-bit LDG/STG row-copy variant (experimental)")
+    ap.add_argument("--pull", action="store_true", help="receiver-driven direct transposes (experimental)")
     ap.add_argument("--chunks", type=int, default=0, help="chunked schedule of staged transposes (experimental)")
     ap.add_argument("--tile-bytes", type=int, default=0, help="row-copy tile size (0 = 32 KiB)")
     ap.add_argument("--peer-order", type=int, default=0, help="0 one-shot interleaved, 1 pairwise rounds")
@@ -269,6 +270,8 @@ def run_native(args, rank, world, local_rank):
         cd.check(cd.set_kernel_variant(handle, gd, 1))
     if args.wide:
         cd.check(cd.set_kernel_variant(handle, gd, 2))
+    if args.pull:
+        cd.check(cd.set_transfer_mode(handle, gd, 1))
     if args.chunks:
         cd.check(cd.set_pipeline_chunks(handle, gd, args.chunks))
     if args.tile_bytes or args.peer_order or args.balance_grid:

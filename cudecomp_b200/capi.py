@@ -195,6 +195,7 @@ _sig("cudecompB200CheckErrors", ctypes.c_int, [cudecompHandle_t, cudecompGridDes
 _sig("cudecompB200SetPipelineChunks", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32])
 _sig("cudecompB200SetKernelVariant", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32])
 _sig("cudecompB200SetSchedule", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32, _i32, _i32])
+_sig("cudecompB200SetTransferMode", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32])
 _sig("cudecompB200DescribeTransposeBoxes", _i32,
      [cudecompHandle_t, cudecompGridDesc_t, _i32, _i32, _i32p, _i32p, _i32p, _i32p, _i32, _P(cudecompB200Box_t), _i32])
 _sig("cudecompB200DescribeHaloBoxes", _i32,
@@ -452,6 +453,10 @@ def set_schedule(handle, grid_desc, tile_bytes=0, peer_order=0, balance_grid=Fal
     return lib.cudecompB200SetSchedule(handle, grid_desc, int(tile_bytes), int(peer_order), 1 if balance_grid else 0)
 
 
+def set_transfer_mode(handle, grid_desc, mode):
+    return lib.cudecompB200SetTransferMode(handle, grid_desc, int(mode))
+
+
 def set_pipeline_chunks(handle, grid_desc, nchunks):
     return lib.cudecompB200SetPipelineChunks(handle, grid_desc, int(nchunks))
 
@@ -497,7 +502,7 @@ def plan_transpose_boxes(config, rank, ax, direction, input_halo_extents=None, o
     arr = (cudecompB200Box_t * max_boxes)()
     n = lib.cudecompB200PlanTransposeBoxes(ctypes.byref(config), rank, ax, direction, _arr3(input_halo_extents),
                                            _arr3(output_halo_extents), _arr3(input_padding), _arr3(output_padding),
-                                           1 if staged else 0, arr, max_boxes)
+                                           int(staged), arr, max_boxes)
     if n < 0:
         raise CudecompError(-n, "cudecompB200PlanTransposeBoxes")
     return _boxes(n, arr)

@@ -270,6 +270,7 @@ static void initHandle(cudecompHandle_t h, const CommPtr& parent) {
   if (const char* v = std::getenv("CUDECOMP_B200_PEER_ORDER"))
     h->peer_order = (std::strcmp(v, "pairwise") == 0 || std::strcmp(v, "1") == 0) ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_BALANCE_GRID")) h->balance_grid = std::atoi(v) != 0 ? 1 : 0;
+  if (const char* v = std::getenv("CUDECOMP_B200_TRANSFER")) h->pull_mode = (std::strcmp(v, "pull") == 0) ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_DIRECT")) h->allow_direct = std::strcmp(v, "0") != 0;
   double spin_s = 60.0;
   if (const char* v = std::getenv("CUDECOMP_B200_DEVICE_TIMEOUT")) spin_s = std::atof(v);
@@ -374,6 +375,7 @@ cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudeco
   gd->tile_bytes = handle->tile_bytes;
   gd->peer_order = handle->peer_order;
   gd->balance_grid = handle->balance_grid;
+  gd->pull_mode = handle->pull_mode;
   if (gd->config.rank_order == CUDECOMP_RANK_ORDER_DEFAULT)
     gd->config.rank_order = handle->env_col_major ? CUDECOMP_RANK_ORDER_COL_MAJOR : CUDECOMP_RANK_ORDER_ROW_MAJOR;
 
@@ -716,6 +718,15 @@ cudecompResult_t cudecompB200SetSchedule(cudecompHandle_t handle, cudecompGridDe
   API_CATCH()
 }
 
+cudecompResult_t cudecompB200SetTransferMode(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t mode) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (mode < 0 || mode > 1) THROW_INVALID_USAGE("mode must be 0 (sender-driven, push) or 1 (receiver-driven, pull)");
+  grid_desc->pull_mode = mode; // must be set to the same value on every rank
+  API_CATCH()
+}
+
 cudecompResult_t cudecompB200SetPipelineChunks(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t nchunks) {
   API_TRY
   checkHandle(handle);
@@ -866,6 +877,11 @@ int32_t cudecompB200PlanTransposeBoxes(const cudecompGridDescConfig_t* config, i
   try {
     GridGeom g = geomFromConfig(config);
     if (rank < 0 || rank >= g.pdims[0] * g.pdims[1]) THROW_INVALID_USAGE("rank out of range");
+    if (staged == 2) { // receiver-driven direct plan: peer_rank names the owner of the SOURCE buffer
+      TransposePlan pull = buildPullTransposePlan(g, pidxOfRank(g, rank), ax, dir, input_halo_extents, output_halo_extents,
+                                                  input_padding, output_padding);
+      return emitBoxes(pull.push, pull.unpack, boxes, max_boxes);
+    }
     TransposePlan plan = buildTransposePlan(g, pidxOfRank(g, rank), ax, dir, input_halo_extents, output_halo_extents,
                                             input_padding, output_padding, staged ? DstKind::STAGE : DstKind::FINAL, false);
     return emitBoxes(plan.push, plan.unpack, boxes, max_boxes);

@@ -205,7 +205,8 @@ struct Schedule {
   int peer_order = 0; // 0 one-shot interleaved, 1 pairwise rounds
   int balance = 0;    // balanced grid
   int chunks = 0;     // chunked staged schedule (in-place / staged calls)
-  int variant = 0;    // 1: TMA bulk row copy
+  int variant = 0;    // 1: TMA bulk row copy, 2: 256-bit LDG/STG
+  int pull = 0;       // 1: receiver-driven direct transposes
 };
 
 void applySchedule(cudecompGridDesc_t gd, const Schedule& s) {
@@ -215,6 +216,7 @@ void applySchedule(cudecompGridDesc_t gd, const Schedule& s) {
   gd->balance_grid = s.balance;
   gd->pipeline_chunks = s.chunks;
   gd->kernel_variant = s.variant;
+  gd->pull_mode = s.pull;
 }
 
 Schedule currentSchedule(const cudecompGridDesc_t gd) {
@@ -225,6 +227,7 @@ Schedule currentSchedule(const cudecompGridDesc_t gd) {
   s.balance = gd->balance_grid;
   s.chunks = gd->pipeline_chunks;
   s.variant = gd->kernel_variant;
+  s.pull = gd->pull_mode;
   return s;
 }
 
@@ -235,15 +238,16 @@ std::string describeSchedule(const Schedule& s) {
   if (s.chunks > 1) d += ", chunks: " + std::to_string(s.chunks);
   if (s.variant == 1) d += ", TMA bulk";
   if (s.variant == 2) d += ", 256-bit LDG/STG";
+  if (s.pull) d += ", receiver-driven";
   return d;
 }
 
 // CUDECOMP_B200_AUTOTUNE_SCHEDULES: which schedule dimensions the second tuning phase explores on the winning
-// (grid, family): comma list of tile, order, balance, chunks, bulk, or "all". The CTA count is always swept (phase 1).
+// (grid, family): comma list of tile, order, balance, chunks, bulk, pull, or "all". The CTA count is always swept (phase 1).
 // Default: none -- the dimensions below were added after the round-1 hardware budget was spent and join the default
 // sweep once confirmed on hardware.
 struct ScheduleDims {
-  bool tile = false, order = false, balance = false, chunks = false, bulk = false;
+  bool tile = false, order = false, balance = false, chunks = false, bulk = false, pull = false;
 };
 
 ScheduleDims scheduleDimsFromEnvironment() {
@@ -256,7 +260,8 @@ ScheduleDims scheduleDimsFromEnvironment() {
     size_t end = s.find(',', start);
     if (end == std::string::npos) end = s.size();
     const std::string name = s.substr(start, end - start);
-    if (name == "all") d.tile = d.order = d.balance = d.chunks = d.bulk = true;
+    if (name == "all") d.tile = d.order = d.balance = d.chunks = d.bulk = d.pull = true;
+    else if (name == "pull") d.pull = true;
     else if (name == "tile") d.tile = true;
     else if (name == "order") d.order = true;
     else if (name == "balance") d.balance = true;
@@ -450,7 +455,7 @@ void autotuneTransposes(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecom
     // when it is faster than everything seen so far
     const ScheduleDims dims = scheduleDimsFromEnvironment();
     if (valid && tune_backend && t_best < std::numeric_limits<double>::max() &&
-        (dims.tile || dims.order || dims.balance || dims.chunks || dims.bulk)) {
+        (dims.tile || dims.order || dims.balance || dims.chunks || dims.bulk || dims.pull)) {
       setGeometry(gd, best_grid);
       if (gd->mbox.valid()) gd->mbox.reset(*h->comm);
       gd->config.transpose_comm_backend = static_cast<cudecompTransposeCommBackend_t>(best_backend);
@@ -486,6 +491,12 @@ void autotuneTransposes(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecom
       if (dims.balance) {
         Schedule a = best_schedule;
         a.balance = 1;
+        alternatives.push_back(a);
+        tryAlternatives();
+      }
+      if (dims.pull && !backendIsStaged(best_backend)) {
+        Schedule a = best_schedule;
+        a.pull = 1;
         alternatives.push_back(a);
         tryAlternatives();
       }

@@ -244,6 +244,7 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
   mine.flags = inplace ? 1u : 0u;
   describeBuffer(output, &mine.data);
   describeBuffer(work, &mine.work);
+  if (gd->pull_mode && !inplace) describeBuffer(input, &mine.src); // else left zeroed: not exportable
   fillReleases(h, &mine);
   std::vector<CallMsg> msgs;
   gd->mbox.exchange(probe.axes.comm == COMM_COL ? 0 : 1, probe.group_world, probe.me, mine, msgs);
@@ -265,7 +266,24 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
     if (i != probe.me) peers.push_back(probe.group_world[i]);
   const SyncParams sync = makeSync(gd, peers);
 
-  if (direct) {
+  // Receiver-driven variant of the direct path: every member's INPUT must be mappable, nobody in place (a peer's input
+  // is read while that peer writes its own output). Same kernel, same handshake: the entry flag says "my input is
+  // ready", the exit flag "I have read everything I needed from you"; the output is written locally.
+  bool pull = direct && gd->pull_mode;
+  for (auto& m : msgs)
+    if (!m.src.exportable) pull = false;
+
+  if (pull) {
+    gd->last_path = CUDECOMP_B200_PATH_DIRECT;
+    TransposePlan pl = buildPullTransposePlan(gd->geom, gd->pidx, ax, dir, in_halo, out_halo, in_pad, out_pad);
+    std::vector<ResolvedBox> boxes;
+    for (auto& b : pl.push) {
+      const char* src = (b.peer == pl.me) ? static_cast<const char*>(input)
+                                          : static_cast<const char*>(h->peers.resolve(b.peer_world, msgs[b.peer].src));
+      boxes.push_back({b, src, static_cast<char*>(output)});
+    }
+    launchBoxes(gd, boxes, es, sync, stream, pl.me, P);
+  } else if (direct) {
     gd->last_path = CUDECOMP_B200_PATH_DIRECT;
     std::vector<ResolvedBox> boxes;
     for (auto& b : probe.push) {

@@ -49,6 +49,7 @@ struct cudecompHandle {
   int tile_bytes = 0;            // CUDECOMP_B200_TILE_BYTES
   int peer_order = 0;            // CUDECOMP_B200_PEER_ORDER=pairwise -> 1
   int balance_grid = 0;          // CUDECOMP_B200_BALANCE_GRID=1
+  int pull_mode = 0;             // CUDECOMP_B200_TRANSFER=pull
   uint64_t release_count = 0;    // buffers freed through cudecompFree so far
   uint64_t released[cdb::kReleaseSlots] = {0}; // ids of the most recent ones, newest first
 };
@@ -76,6 +77,7 @@ struct cudecompGridDesc {
   int tile_bytes = 0;     // row-copy tile size (0: 32 KiB), see launch_params.h
   int peer_order = 0;     // 0: slots interleaved over the peers (one-shot), 1: one peer after the other (pairwise rounds)
   int balance_grid = 0;   // 1: pick the CTA count whose last grid-stride round is fullest (kernels.h chooseGrid)
+  int pull_mode = 0;      // 1: direct transposes are receiver-driven (each rank LOADS its blocks from the peers' inputs)
   cudaStream_t side_stream = nullptr;
   std::vector<cudaEvent_t> side_events;
 };

@@ -42,6 +42,7 @@ struct CallMsg {
   uint32_t flags;
   BufDesc data;    // transpose: output buffer; halo: the pencil buffer
   BufDesc work;    // workspace
+  BufDesc src;     // transpose: input buffer (only described when the receiver-driven mode is on)
   // cudecompFree is not collective in practice (the reference's own tests free workspaces on a subset of the
   // ranks), so releases are announced here: how many buffers this rank has freed so far and the ids of the most
   // recent ones. Readers drop their imports of those buffers (all imports of the rank if they missed some).

@@ -107,6 +107,28 @@ TransposePlan buildTransposePlan(const GridGeom& g, const std::array<int, 2>& pi
   return plan;
 }
 
+TransposePlan buildPullTransposePlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dir,
+                                     const int32_t in_halo[3], const int32_t out_halo[3], const int32_t in_pad[3],
+                                     const int32_t out_pad[3]) {
+  TransposePlan plan = buildTransposePlan(g, pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, DstKind::FINAL, false);
+  if (plan.noop) return plan;
+  const int ci = plan.axes.comm;
+  plan.push.clear();
+  plan.wire_elems = 0;
+  for (int j = 0; j < plan.comm_size; ++j) {
+    auto pj = pidx;
+    pj[ci] = j;
+    const TransposePlan theirs =
+        buildTransposePlan(g, pj, ax, dir, in_halo, out_halo, in_pad, out_pad, DstKind::FINAL, false);
+    BoxDesc b = theirs.push[plan.me]; // what rank j sends to me: its source strides, my destination strides
+    b.peer = j;
+    b.peer_world = plan.group_world[j];
+    if (j != plan.me) plan.wire_elems += b.count();
+    plan.push.push_back(b);
+  }
+  return plan;
+}
+
 namespace {
 // chunk k of [0, n) cut into K parts
 inline std::pair<int64_t, int64_t> chunkRange(int64_t n, int K, int k) { return {k * n / K, (k + 1) * n / K}; }

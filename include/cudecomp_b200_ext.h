@@ -59,6 +59,12 @@ cudecompResult_t cudecompB200SetKernelVariant(cudecompHandle_t handle, cudecompG
 cudecompResult_t cudecompB200SetSchedule(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t tile_bytes,
                                          int32_t peer_order, int32_t balance_grid);
 
+/* Who drives a direct (out-of-place, peer-mappable) transpose: 0 = the sender stores its blocks into the peers' outputs
+ * (default), 1 = the receiver loads its blocks from the peers' inputs and writes its own output locally. Same kernel,
+ * same handshake, identical results; needs every member's INPUT to be peer-mappable, otherwise the call silently uses
+ * mode 0. Same value on every rank. Also CUDECOMP_B200_TRANSFER=pull. EXPERIMENTAL until measured on hardware. */
+cudecompResult_t cudecompB200SetTransferMode(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t mode);
+
 /* Chunked schedule of staged transposes (in-place calls, NVSHMEM-family backends, non-exportable outputs): the pencil
  * is pushed in `nchunks` chunks and unpacking overlaps the next chunk's push (csrc/plan.h PipelinedPlan). 0 or 1 = off
  * (default; also settable for all descriptors with CUDECOMP_B200_PIPELINE_CHUNKS). Same value on every rank.
@@ -83,7 +89,9 @@ int32_t cudecompB200DescribeHaloBoxes(cudecompHandle_t handle, cudecompGridDesc_
 /* Handle-free variants: the plan any `rank` of a `pdims[0] x pdims[1]` grid would execute for `config` (only gdims,
  * gdims_dist, pdims, rank_order, transpose_axis_contiguous and transpose_mem_order are read). Pure host arithmetic,
  * used to property-test the planner over arbitrary decompositions in one process. Returns the number of boxes, or
- * minus the cudecompResult_t code on error (e.g. -2 for decompositions with empty pencils). */
+ * minus the cudecompResult_t code on error (e.g. -2 for decompositions with empty pencils). For
+ * cudecompB200PlanTransposeBoxes, staged == 2 returns the receiver-driven plan (cudecompB200SetTransferMode):
+ * peer_rank is then the rank whose INPUT the box is read from, and the destination is the calling rank's output. */
 int32_t cudecompB200PlanTransposeBoxes(const cudecompGridDescConfig_t* config, int32_t rank, int32_t ax, int32_t dir,
                                        const int32_t input_halo_extents[], const int32_t output_halo_extents[],
                                        const int32_t input_padding[], const int32_t output_padding[], int32_t staged,

@@ -41,6 +41,9 @@ if [ "$N" != 1 ]; then
   bench bulk_inplace_chunks8 --no-e2e --bulk --inplace --chunks 8
   echo "== pairwise slot order"
   bench pairwise --no-e2e --peer-order 1
+  echo "== receiver-driven direct transposes (cudecompB200SetTransferMode)"
+  bench pull --no-e2e --pull
+  bench pull_wide --no-e2e --pull --wide
 else
   bench bulk --no-e2e --bulk
 fi
@@ -59,6 +62,7 @@ bench c64_512_inplace --no-e2e --grid 512 --dtype float_complex --inplace
 if [ "$N" != 1 ]; then
   bench c64_512_inplace_chunks4 --no-e2e --grid 512 --dtype float_complex --inplace --chunks 4
   bench c64_512_pairwise --no-e2e --grid 512 --dtype float_complex --peer-order 1
+  bench c64_512_pull --no-e2e --grid 512 --dtype float_complex --pull
 fi
 echo "== the default line with the end-to-end leg (host-link ceiling, NUMA binding)"
 bench default_e2e

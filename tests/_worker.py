@@ -118,6 +118,8 @@ def transpose_case(gpu, handle, rank, case):
             cd.check(cd.set_pipeline_chunks(handle, gd, case["pipeline_chunks"]))
         if case.get("kernel_variant"):
             cd.check(cd.set_kernel_variant(handle, gd, case["kernel_variant"]))
+        if case.get("pull"):
+            cd.check(cd.set_transfer_mode(handle, gd, 1))
         if case.get("tile_bytes") or case.get("peer_order") or case.get("balance_grid"):
             cd.check(cd.set_schedule(handle, gd, case.get("tile_bytes", 0), case.get("peer_order", 0),
                                      bool(case.get("balance_grid"))))

@@ -290,3 +290,33 @@ def test_seventeen_rank_communicator_needs_two_launches():
         st_ = emu.run_boxes(push, [src] * 17, [outs[bx["peer_rank"]] for bx in push], 8, [src] + list(outs.values()),
                             me=gi[3], comm_size=17, peer_index=[gi[bx["peer_rank"]] for bx in push])
         assert st_["launches"] == 2
+
+
+@settings(max_examples=EXAMPLES, deadline=None, suppress_health_check=list(HealthCheck))
+@given(st.one_of(decompositions(), long_row_decompositions()), schedules())
+def test_emulated_receiver_driven_transposes_equal_oracle(d, s):
+    """Receiver-driven direct plans (cudecompB200SetTransferMode): the same kernels with the SOURCE in a peer's buffer."""
+    cfg, o = make_config(d), make_oracle(d)
+    n = o.nranks
+    dt = DT[s["es"]]
+    off = s["misalign"] * s["es"]
+    rng = np.random.default_rng(21)
+    for op, (ax, direction) in OPS.items():
+        a, b = orc.transpose_axes(op)
+        if o.has_empty_pencils(a) or o.has_empty_pencils(b):
+            continue
+        ha, hb, pa, pb = d["halos"][str(a)], d["halos"][str(b)], d["pads"][str(a)], d["pads"][str(b)]
+        ins = [emu.aligned_array(o.pencil_info(r, a, ha, pa).size, dt, off) for r in range(n)]
+        for x in ins:
+            rand_fill(x, rng)
+        want = [np.full(o.pencil_info(r, b, hb, pb).size, -3, dt) for r in range(n)]
+        o.transpose(op, ins, want, ha, hb, pa, pb)
+        outs = [emu.aligned_array(w.size, dt, off, -3) for w in want]
+        for r in range(n):
+            pull = cd.plan_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, 2)
+            gi = group_index(pull)
+            st_ = emulate(pull, lambda bx: ins[bx["peer_rank"]], lambda bx: outs[r], ins + outs, s, me=gi[r], comm=len(gi),
+                          peer_index=[gi[bx["peer_rank"]] for bx in pull])
+            assert st_["bytes_written"] == o.pencil_info(r, b).size * s["es"]  # my whole output interior, exactly once
+        for r in range(n):
+            assert np.array_equal(outs[r], want[r]), (d, s, op, r)

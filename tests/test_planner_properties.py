@@ -90,6 +90,34 @@ def test_transpose_plans_equal_oracle(d):
 
 
 @settings(max_examples=int(__import__("os").environ.get("CDB_HYPOTHESIS_EXAMPLES", "150")), deadline=None, suppress_health_check=list(HealthCheck))
+@given(decompositions())
+def test_receiver_driven_plans_equal_oracle(d):
+    """cudecompB200SetTransferMode(1): every rank LOADS its blocks from the peers' inputs. Box j of rank r reads rank j's
+    input with rank j's strides and writes rank r's output with rank r's strides."""
+    cfg, o = make_config(d), make_oracle(d)
+    n = o.nranks
+    for op, (ax, direction) in OPS.items():
+        a, b = orc.transpose_axes(op)
+        if o.has_empty_pencils(a) or o.has_empty_pencils(b):
+            continue
+        ha, hb, pa, pb = d["halos"][str(a)], d["halos"][str(b)], d["pads"][str(a)], d["pads"][str(b)]
+        rng = np.random.default_rng(9)
+        ins = [rng.integers(1, 1 << 40, o.pencil_info(r, a, ha, pa).size).astype(np.int64) for r in range(n)]
+        want = [np.full(o.pencil_info(r, b, hb, pb).size, -3, np.int64) for r in range(n)]
+        o.transpose(op, ins, want, ha, hb, pa, pb)
+        outs = [np.full(w.size, -3, np.int64) for w in want]
+        for r in range(n):
+            pull = cd.plan_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, 2)
+            push = cd.plan_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, 0)
+            assert sorted(bx["peer_rank"] for bx in pull) == sorted(bx["peer_rank"] for bx in push)  # same communicator
+            for box in pull:
+                assert not box["is_unpack"]
+                apply_box(box, ins[box["peer_rank"]], outs[r])
+        for r in range(n):
+            assert np.array_equal(outs[r], want[r]), (d, op, r)
+
+
+@settings(max_examples=int(__import__("os").environ.get("CDB_HYPOTHESIS_EXAMPLES", "150")), deadline=None, suppress_health_check=list(HealthCheck))
 @given(decompositions(), st.lists(st.integers(0, 3), min_size=3, max_size=3), st.lists(st.booleans(), min_size=3, max_size=3),
        st.lists(st.integers(0, 2), min_size=3, max_size=3))
 def test_halo_plans_equal_oracle(d, halo, periods, padding):

@@ -23,6 +23,11 @@ CASES = [
     dict(BASE, name="Pairwise_tile8k_balanced_halo_padding", gdims=[48, 32, 40], pdims=[2, 2], dtype="double",
          out_of_place=True, peer_order=1, tile_bytes=8192, balance_grid=1,
          halos={"0": [1, 1, 1], "1": [1, 1, 1], "2": [1, 1, 1]}, pads={"0": [1, 0, 0], "1": [0, 1, 0], "2": [0, 0, 2]}),
+    dict(BASE, name="Pull_oop_2x2_c128", gdims=[64, 40, 48], pdims=[2, 2], dtype="double_complex", out_of_place=True, pull=1),
+    dict(BASE, name="Pull_oop_4x1_uneven_axis_contiguous_halos", gdims=[31, 30, 29], pdims=[4, 1], dtype="float",
+         out_of_place=True, pull=1, axis_contiguous=[True] * 3,
+         halos={"0": [1, 1, 1], "1": [1, 0, 1], "2": [0, 1, 1]}, pads={"0": [1, 0, 0], "1": [0, 1, 0], "2": [0, 0, 2]}),
+    dict(BASE, name="Pull_inplace_falls_back_to_staged_push", gdims=[32, 40, 48], pdims=[2, 2], dtype="double", pull=1),
     dict(BASE, name="Wide256_oop_2x2_c128", gdims=[64, 40, 48], pdims=[2, 2], dtype="double_complex", out_of_place=True,
          kernel_variant=2),
     dict(BASE, name="Wide256_inplace_2x2_uneven_float_falls_back", gdims=[31, 30, 29], pdims=[2, 2], dtype="float",
