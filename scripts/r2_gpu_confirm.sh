@@ -115,7 +115,7 @@ if [ "$N" = 8 ]; then
   bench default
   bench inplace --no-e2e --inplace
   echo "$CANDIDATES_8" | while IFS='|' read -r label args; do
-    [ -n "$label" ] && bench $label --no-e2e $args
+    [ -n "$label" ] && bench $label --no-e2e $args < /dev/null
   done
   echo "== GPU-side baseline: the reference's NCCL arm restated"
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29970 \
