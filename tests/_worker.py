@@ -334,6 +334,7 @@ def plan_case(handle, rank, case):
                 out["transposes"]["%s/%d" % (op, staged)] = cd.describe_transpose_boxes(
                     handle, gd, ax, d, halos.get(str(a)), halos.get(str(b)), pads.get(str(a)), pads.get(str(b)), staged)
         if case.get("halo"):
+            out["halo_workspace"] = [cd.cudecompGetHaloWorkspaceSize(handle, gd, ax, case["halo"])[1] for ax in range(3)]
             for ax in range(3):
                 for dim in range(3):
                     for staged in (False, True):

@@ -80,7 +80,7 @@ def run_boxes(boxes, srcs, dsts, es, legal, me=-1, comm_size=0, peer_index=None,
     if rc != 0:
         raise EmuError(err.value.decode())
     return dict(launches=stats[0], bytes_written=stats[1], accesses=stats[2], kinds=stats[3], vec=stats[4], slots=stats[5],
-                balanced_grid=stats[6])
+                balanced_grid=stats[6], longest_row=stats[7])
 
 
 def aligned_array(n, dtype, offset_bytes=0, fill=None):

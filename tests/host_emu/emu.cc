@@ -6,6 +6,7 @@
 // lane by lane with loops that restate those of csrc/kernels.cu. Every vector access is checked for alignment and
 // against the legal address ranges, and bytes are copied on numpy buffers, so a Python test can compare the outcome
 // with the oracle without a GPU. What it cannot show: memory ordering, the cross-GPU handshake, TMA/mbarrier protocol.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -198,7 +199,8 @@ void walkBulk(const CopyParams& p, int grid, Walk& w) {
 // boxes[i] moves from src_bases[i] to dst_bases[i] (element offsets inside the box). peer_index[i]: communicator index
 // of the destination rank. ranges: every address a launch may touch. grid <= 0: 370 CTAs (2.5 x 148 SMs).
 // stats: [0] launches, [1] bytes written, [2] vector / bulk accesses, [3] bitmask of kernel kinds (1 row copy,
-// 2 transpose, 4 bulk), [4] vector width of the row copy, [5] slots over all launches, [6] balanced grid for those slots.
+// 2 transpose, 4 bulk), [4] vector width of the row copy, [5] slots over all launches, [6] balanced grid for those slots,
+// [7] longest row of a row-copy box in bytes (shows whether contiguous axes were merged).
 extern "C" int cdb_emu_run_boxes(const cudecompB200Box_t* boxes, const int32_t* peer_index, int nboxes,
                                  const void* const* src_bases, void* const* dst_bases, const char* const* range_lo,
                                  const int64_t* range_len, int nranges, int es, int tile_bytes, int peer_order,
@@ -227,9 +229,12 @@ extern "C" int cdb_emu_run_boxes(const cudecompB200Box_t* boxes, const int32_t* 
     std::vector<PreparedLaunch> launches = prepareLaunches(lb, es, tuning, me, comm_size);
     Ranges ranges{range_lo, range_len, nranges};
     Walk w{ranges};
-    int64_t kinds = 0, slots = 0;
+    int64_t kinds = 0, slots = 0, longest_row = 0;
     for (auto& l : launches) {
       const CopyParams& p = l.params;
+      if (l.kind != KernelKind::TRANSPOSE)
+        for (uint32_t b = 0; b < p.nboxes; ++b)
+          longest_row = std::max<int64_t>(longest_row, static_cast<int64_t>(p.box[b].row_vecs) * p.vec_size);
       const uint64_t total = static_cast<uint64_t>(p.nboxes) * p.max_tiles;
       slots += static_cast<int64_t>(total);
       const int dflt = (l.kind == KernelKind::ROWCOPY) ? 370 : (l.kind == KernelKind::TRANSPOSE ? 592 : 148);
@@ -253,6 +258,7 @@ extern "C" int cdb_emu_run_boxes(const cudecompB200Box_t* boxes, const int32_t* 
       stats[3] = kinds;
       stats[5] = slots;
       stats[6] = chooseGrid(grid, 370, 1 << 20, static_cast<uint64_t>(slots), 1);
+      stats[7] = longest_row;
     }
     return 0;
   } catch (const std::exception& e) {

@@ -209,3 +209,24 @@ def test_schedule_knobs_validate_their_arguments(handle):
     assert cd.set_pipeline_chunks(handle, gd, 65) == INV
     assert cd.set_pipeline_chunks(handle, gd, 8) == 0
     cd.cudecompGridDescDestroy(handle, gd)
+
+
+def test_workspace_sizes_match_the_oracle_for_odd_shapes(handle):
+    """cudecompGetHaloWorkspaceSize / cudecompGetTransposeWorkspaceSize against the oracle on one rank for shapes whose
+    three extents differ and halos that differ per dimension (a swapped axis in the face product would hide behind the
+    maximum over the dimensions or behind the rounding to 64 elements on friendlier shapes)."""
+    from oracle import oracle as orc
+    import itertools
+    for gdims, ac in itertools.product([(9, 130, 17), (200, 3, 70), (65, 66, 5)], [False, True]):
+        c = _config(gdims=gdims)
+        for i in range(3):
+            c.transpose_axis_contiguous[i] = ac
+        res, gd = cd.cudecompGridDescCreate(handle, c)
+        assert res == 0
+        o = orc.Oracle(list(gdims), [1, 1], (ac,) * 3)
+        assert cd.cudecompGetTransposeWorkspaceSize(handle, gd) == (0, o.transpose_workspace_size())
+        for halo in [(1, 0, 0), (0, 1, 0), (0, 0, 1), (3, 1, 2), (1, 4, 1), (2, 2, 5)]:
+            for ax in range(3):
+                assert cd.cudecompGetHaloWorkspaceSize(handle, gd, ax, halo) == (0, o.halo_workspace_size(0, ax, list(halo))), (
+                    gdims, ac, halo, ax)
+        cd.cudecompGridDescDestroy(handle, gd)

@@ -81,6 +81,8 @@ def check_halos(case, results):
     n = o.nranks
     dt = np.float64
     halo, per, pad = case["halo"], case.get("periods") or [False] * 3, case.get("padding")
+    for r in range(n):  # workspace sizes through the C ABI against the oracle (reference src/cudecomp.cc:1434-1459)
+        assert results[r]["halo_workspace"] == [o.halo_workspace_size(r, ax, halo) for ax in range(3)], (case["name"], r)
     for ax in range(3):
         for staged in (False, True):
             data = [orc.pattern_pencil(o.pencil_info(r, ax, halo, pad), case["gdims"], dt) for r in range(n)]

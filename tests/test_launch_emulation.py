@@ -229,6 +229,30 @@ def test_kernel_selection_and_vector_width():
     assert run(8, 0, dd=d2, cfg_=cfg2, o_=o2)["kinds"] == 2
 
 
+def test_contiguous_axes_are_merged_into_long_rows():
+    """Y->Z in the default layout moves, per z-plane, a block of x-rows that is contiguous on both sides: the planner
+    must hand the kernel ONE row per plane (2 MB at the headline size), not one row per x-line -- the per-row index
+    arithmetic and the tile tails depend on it. The results would be the same either way, so only this test sees it."""
+    d = dict(gdims=[32, 24, 10], pdims=[1, 2], axis_contiguous=[False] * 3, mem_order=None, gdims_dist=None, col_major=False,
+             halos={str(a): [0, 0, 0] for a in range(3)}, pads={str(a): [0, 0, 0] for a in range(3)})
+    cfg, o = make_config(d), make_oracle(d)
+    push = cd.plan_transpose_boxes(cfg, 0, 1, 1)  # Y->Z: y is split in two blocks of 12
+    src = emu.aligned_array(o.pencil_info(0, 1).size, np.int64, 0, 1)
+    outs = [emu.aligned_array(o.pencil_info(r, 2).size, np.int64, 0, 0) for r in range(2)]
+    st_ = emu.run_boxes(push, [src] * 2, [outs[bx["peer_rank"]] for bx in push], 8, [src] + outs, me=0, comm_size=2,
+                        peer_index=[0, 1])
+    assert st_["kinds"] == 1 and st_["longest_row"] == 32 * 12 * 8  # x-lines of one y-block merged: 32 x 12 elements
+    # X->Y cannot merge (the x-range is cut in the source): rows stay x-lines of half the x extent
+    d2 = dict(d, pdims=[2, 1])
+    cfg2, o2 = make_config(d2), make_oracle(d2)
+    push = cd.plan_transpose_boxes(cfg2, 0, 0, 1)
+    src = emu.aligned_array(o2.pencil_info(0, 0).size, np.int64, 0, 1)
+    outs = [emu.aligned_array(o2.pencil_info(r, 1).size, np.int64, 0, 0) for r in range(2)]
+    st_ = emu.run_boxes(push, [src] * 2, [outs[bx["peer_rank"]] for bx in push], 8, [src] + outs, me=0, comm_size=2,
+                        peer_index=[0, 1])
+    assert st_["longest_row"] == 16 * 8
+
+
 def test_slot_orders_are_permutations():
     import ctypes
     lib = emu.lib()

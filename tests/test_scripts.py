@@ -18,10 +18,15 @@ def test_explain_plan_reproduces_the_measured_round_trips():
     direct, staged, chunked = nums
     assert abs(direct - 8.10) < 0.3 and abs(staged - 10.76) < 0.3  # measured: profiles/r1_n8_bench*.json
     assert direct < chunked < staged
-    # every step of every chunked operation is a complete all-to-all (no step talks to a single peer of a 4-rank group)
+    # every step of every chunked operation is a complete all-to-all (no step talks to a single peer of a 4-rank group),
+    # and most of the local unpack overlaps later pushes (a hazard test that is merely too cautious would pass every
+    # correctness test and silently lose this)
+    import re
     for line in out.stdout.splitlines():
         if "peers per step" in line:
             assert "peers per step [2]" in line or "peers per step [4]" in line, line
+            overlapped = float(re.search(r"unpacked beside later pushes (\d+) %", line).group(1))
+            assert overlapped >= 75, line
 
 
 def test_r2_summarize_reads_bench_lines(tmp_path):
