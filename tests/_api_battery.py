@@ -404,7 +404,51 @@ def halo_rejects_empty_pencils(e, handle, rank, with_gpu):  # api_tests.cc:1535-
              "halo update on a decomposition with empty pencils")
 
 
+def autotune_grid_rules_without_timing(e, handle, rank, with_gpu):
+    """Which process grids the autotuner considers at all (reference src/autotune.cc:94-106,361-373), observable without
+    a device: with nothing to time, the first candidate that survives the rules is selected. 4 ranks, row-major:
+    candidates in order 4x1, 2x2, 1x4; a grid is dropped when it leaves a pencil empty (pdims[0] > min(gx, gy) or
+    pdims[1] > min(gy, gz)), when it splits unevenly and uneven decompositions are not allowed, or when the
+    CUDECOMP_AUTOTUNE_P_*_RANGE variables exclude it; nothing left -> NOT_SUPPORTED."""
+    import torch
+    if with_gpu or torch.cuda.is_available():
+        return  # with a device the candidates are timed and the fastest one wins
+
+    def selected(gdims, allow_uneven=True, env=None):
+        c = distributed_config()
+        c.gdims[:] = gdims
+        c.pdims[:] = [0, 0]
+        o = fast_autotune_options()
+        o.allow_uneven_decompositions = allow_uneven
+        old = {k: os.environ.get(k) for k in (env or {})}
+        os.environ.update(env or {})
+        try:
+            res, gd = create(handle, c, o)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        if res != OK:
+            return res
+        cd.cudecompGridDescDestroy(handle, gd)
+        return list(c.pdims)  # written back to the caller's config (reference src/cudecomp.cc:1247-1265)
+
+    e.eq([4, 1], selected((8, 6, 10)), "first candidate, everything allowed")
+    e.eq([2, 2], selected((8, 6, 10), allow_uneven=False), "4x1 splits y = 6 unevenly")
+    e.eq([4, 1], selected((8, 8, 10), allow_uneven=False), "4x1 splits 8 x 8 evenly")
+    e.eq([2, 2], selected((2, 8, 8)), "4x1 would leave X pencils empty (4 > min(2, 8))")
+    e.eq([1, 4], selected((1, 8, 8)), "only 1x4 keeps every pencil populated")
+    e.eq(NOT_SUPPORTED, selected((1, 1, 8)), "no grid keeps every pencil populated")
+    e.eq(NOT_SUPPORTED, selected((6, 6, 7), allow_uneven=False), "no even split of z = 7 or y = 6 by 4 / of 7 by 2")
+    e.eq([2, 2], selected((8, 6, 10), env={"CUDECOMP_AUTOTUNE_P_ROW_RANGE": "1,2"}), "row range excludes 4x1")
+    e.eq([1, 4], selected((8, 6, 10), env={"CUDECOMP_AUTOTUNE_P_COL_RANGE": "3,4"}), "column range leaves 1x4")
+    e.eq(INV, selected((8, 6, 10), env={"CUDECOMP_AUTOTUNE_P_ROW_RANGE": "3,3"}), "range excludes every candidate")
+
+
 TESTS = [
+    autotune_grid_rules_without_timing,
     init_rejects_invalid_arguments,
     finalize_rejects_invalid_arguments,
     multiple_live_handles,
