@@ -420,6 +420,28 @@ def shim_battery(rank, nranks):
         cd.cudecompGridDescDestroy(h, gd)
     cd.cudecompFinalize(h)
     out["wtime_positive"] = cd.lib.MPI_Wtime() > 0
+    # wider coverage of the typed reductions and the in-place conventions
+    MPI_UNSIGNED, MPI_INT64_T = (2 << 8) | 4, (1 << 8) | 8
+    big = (ctypes.c_int64 * 5)(*[(1 << 40) + 1000 * rank + k for k in range(5)])
+    bigr = (ctypes.c_int64 * 5)()
+    assert L.MPI_Allreduce(big, bigr, 5, MPI_INT64_T, SUM, W) == 0
+    out["allreduce_int64_sum"] = list(bigr)
+    u = (ctypes.c_uint32 * 1)(1 if rank < 2 else 0x80000000 + rank)
+    assert L.MPI_Allreduce(IN_PLACE, u, 1, MPI_UNSIGNED, MAX, W) == 0
+    out["allreduce_unsigned_max"] = u[0]
+    neg = (ctypes.c_int * 1)(rank - 5)
+    assert L.MPI_Allreduce(IN_PLACE, neg, 1, MPI_INT, MIN, W) == 0
+    out["allreduce_int_min_negative"] = neg[0]
+    ag = (ctypes.c_int64 * (2 * nranks))()
+    ag[2 * rank], ag[2 * rank + 1] = (1 << 33) + rank, -rank
+    assert L.MPI_Allgather(IN_PLACE, 0, 0, ag, 2, MPI_INT64_T, W) == 0
+    out["allgather_inplace"] = list(ag)
+    selfsum = (ctypes.c_double * 3)(1.25, 2.5, float(rank))
+    selfout = (ctypes.c_double * 3)()
+    assert L.MPI_Allreduce(selfsum, selfout, 3, MPI_DOUBLE, SUM, 2) == 0  # MPI_COMM_SELF: one rank, not in place
+    out["allreduce_self"] = list(selfout)
+    L.MPI_Comm_free.argtypes = [ctypes.c_void_p]
+    out["comm_free_null"] = L.MPI_Comm_free(None)
     return out
 
 

@@ -202,6 +202,10 @@ def test_mpi_shim_collectives_on_4_ranks():
         assert out["freed"] == [0, 0]
         assert out["subcomm_handle"] == [0, 0] and out["subcomm_shape"] == [8, 8, 4]
         assert out["wtime_positive"]
+        assert out["allreduce_int64_sum"] == [4 * (1 << 40) + 1000 * (0 + 1 + 2 + 3) + 4 * k for k in range(5)]
+        assert out["allreduce_unsigned_max"] == 0x80000003 and out["allreduce_int_min_negative"] == -5
+        assert out["allgather_inplace"] == [v for q in range(4) for v in ((1 << 33) + q, -q)]
+        assert out["allreduce_self"] == [1.25, 2.5, float(r)] and out["comm_free_null"] == 0
     assert results[0][0]["gather_root0"] == [100, 101, 102, 103]
     assert results[0][0]["reduce_max_root0"] == 9
 
