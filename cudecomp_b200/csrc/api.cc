@@ -877,9 +877,10 @@ int32_t cudecompB200PlanTransposeBoxes(const cudecompGridDescConfig_t* config, i
   try {
     GridGeom g = geomFromConfig(config);
     if (rank < 0 || rank >= g.pdims[0] * g.pdims[1]) THROW_INVALID_USAGE("rank out of range");
-    if (staged == 2) { // receiver-driven direct plan: peer_rank names the owner of the SOURCE buffer
+    if (staged == 2 || staged == 3) { // receiver-driven plans (3: through my workspace); peer_rank owns the SOURCE
       TransposePlan pull = buildPullTransposePlan(g, pidxOfRank(g, rank), ax, dir, input_halo_extents, output_halo_extents,
-                                                  input_padding, output_padding);
+                                                  input_padding, output_padding,
+                                                  staged == 3 ? DstKind::STAGE : DstKind::FINAL, false);
       return emitBoxes(pull.push, pull.unpack, boxes, max_boxes);
     }
     TransposePlan plan = buildTransposePlan(g, pidxOfRank(g, rank), ax, dir, input_halo_extents, output_halo_extents,

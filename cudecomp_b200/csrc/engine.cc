@@ -244,7 +244,7 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
   mine.flags = inplace ? 1u : 0u;
   describeBuffer(output, &mine.data);
   describeBuffer(work, &mine.work);
-  if (gd->pull_mode && !inplace) describeBuffer(input, &mine.src); // else left zeroed: not exportable
+  if (gd->pull_mode) describeBuffer(input, &mine.src); // else left zeroed: not exportable
   fillReleases(h, &mine);
   std::vector<CallMsg> msgs;
   gd->mbox.exchange(probe.axes.comm == COMM_COL ? 0 : 1, probe.group_world, probe.me, mine, msgs);
@@ -253,12 +253,19 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
   bool direct = h->allow_direct && !gd->force_staged &&
                 gd->config.transpose_comm_backend < CUDECOMP_TRANSPOSE_COMM_NVSHMEM; // NVSHMEM* values = staged schedule
   bool work_ok = true;
+  bool src_ok = gd->pull_mode != 0; // receiver-driven: every member's INPUT must be mappable
   for (auto& m : msgs) {
     if (m.flags & 1u) direct = false; // anybody in place: peers may not overwrite a buffer that is still being read
     if (!m.data.exportable) direct = false;
     if (!m.work.exportable) work_ok = false;
+    if (!m.src.exportable) src_ok = false;
   }
-  if (!direct && !work_ok)
+  // Receiver-driven staged schedule: every rank loads its blocks from the peers' inputs into its OWN workspace and
+  // unpacks locally, so nothing is written into a peer's memory (the workspace need not be mappable). In place this is
+  // safe for the same reason the sender-driven staged schedule is: a pencil is only overwritten by its owner's unpack,
+  // after the exit handshake has told it that every peer has finished reading.
+  const bool pull_staged = !direct && src_ok && !(gd->pipeline_chunks > 1);
+  if (!direct && !work_ok && !pull_staged)
     THROW_INVALID_USAGE("the workspace must be device memory that peers can map: allocate it with cudecompMalloc");
 
   std::vector<int> peers;
@@ -269,9 +276,7 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
   // Receiver-driven variant of the direct path: every member's INPUT must be mappable, nobody in place (a peer's input
   // is read while that peer writes its own output). Same kernel, same handshake: the entry flag says "my input is
   // ready", the exit flag "I have read everything I needed from you"; the output is written locally.
-  bool pull = direct && gd->pull_mode;
-  for (auto& m : msgs)
-    if (!m.src.exportable) pull = false;
+  const bool pull = direct && src_ok;
 
   if (pull) {
     gd->last_path = CUDECOMP_B200_PATH_DIRECT;
@@ -292,6 +297,22 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
       boxes.push_back({b, static_cast<const char*>(input), dst});
     }
     launchBoxes(gd, boxes, es, sync, stream, probe.me, P);
+  } else if (pull_staged) {
+    gd->last_path = CUDECOMP_B200_PATH_STAGED;
+    TransposePlan pl = buildPullTransposePlan(gd->geom, gd->pidx, ax, dir, in_halo, out_halo, in_pad, out_pad,
+                                              DstKind::STAGE, inplace);
+    std::vector<ResolvedBox> pullb, unpack;
+    for (auto& b : pl.push) {
+      const char* src = (b.peer == pl.me) ? static_cast<const char*>(input)
+                                          : static_cast<const char*>(h->peers.resolve(b.peer_world, msgs[b.peer].src));
+      pullb.push_back({b, src, static_cast<char*>(work)});
+    }
+    for (auto& b : pl.unpack) unpack.push_back({b, static_cast<const char*>(work), static_cast<char*>(output)});
+    SyncParams nosync;
+    std::memset(&nosync, 0, sizeof(nosync));
+    launchBoxes(gd, pullb, es, sync, stream, pl.me, P);
+    PerfReport::markExchangeDone(perf.sample, stream);
+    launchBoxes(gd, unpack, es, nosync, stream);
   } else {
     gd->last_path = CUDECOMP_B200_PATH_STAGED;
     if (gd->pipeline_chunks > 1 &&

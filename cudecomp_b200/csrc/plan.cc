@@ -109,8 +109,8 @@ TransposePlan buildTransposePlan(const GridGeom& g, const std::array<int, 2>& pi
 
 TransposePlan buildPullTransposePlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dir,
                                      const int32_t in_halo[3], const int32_t out_halo[3], const int32_t in_pad[3],
-                                     const int32_t out_pad[3]) {
-  TransposePlan plan = buildTransposePlan(g, pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, DstKind::FINAL, false);
+                                     const int32_t out_pad[3], DstKind kind, bool inplace) {
+  TransposePlan plan = buildTransposePlan(g, pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, kind, inplace);
   if (plan.noop) return plan;
   const int ci = plan.axes.comm;
   plan.push.clear();
@@ -118,8 +118,7 @@ TransposePlan buildPullTransposePlan(const GridGeom& g, const std::array<int, 2>
   for (int j = 0; j < plan.comm_size; ++j) {
     auto pj = pidx;
     pj[ci] = j;
-    const TransposePlan theirs =
-        buildTransposePlan(g, pj, ax, dir, in_halo, out_halo, in_pad, out_pad, DstKind::FINAL, false);
+    const TransposePlan theirs = buildTransposePlan(g, pj, ax, dir, in_halo, out_halo, in_pad, out_pad, kind, false);
     BoxDesc b = theirs.push[plan.me]; // what rank j sends to me: its source strides, my destination strides
     b.peer = j;
     b.peer_world = plan.group_world[j];

@@ -59,9 +59,11 @@ TransposePlan buildTransposePlan(const GridGeom& g, const std::array<int, 2>& pi
 // rank's strides on the source side (its input pencil, mapped into my address space) and with MY strides on the
 // destination side (my output pencil). Box j is exactly the box rank j would push to me, so the union over all ranks
 // moves the same cells as the sender-driven plan. `peer` / `peer_world` name the rank that owns the SOURCE buffer.
+// With kind == STAGE the destination is the dense pencil in MY workspace (then `unpack` holds the local copy into the
+// output, as in the sender-driven staged plan): nobody writes into a peer's memory at all.
 TransposePlan buildPullTransposePlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dir,
                                      const int32_t in_halo[3], const int32_t out_halo[3], const int32_t in_pad[3],
-                                     const int32_t out_pad[3]);
+                                     const int32_t out_pad[3], DstKind kind = DstKind::FINAL, bool inplace = false);
 
 // Chunked schedule of a staged transpose: the pencil is cut into K chunks along the slowest axis of the SOURCE memory
 // order; step s pushes chunk s to every peer's workspace and, once that has landed, unpacks every piece whose

@@ -62,7 +62,9 @@ cudecompResult_t cudecompB200SetSchedule(cudecompHandle_t handle, cudecompGridDe
 /* Who drives a direct (out-of-place, peer-mappable) transpose: 0 = the sender stores its blocks into the peers' outputs
  * (default), 1 = the receiver loads its blocks from the peers' inputs and writes its own output locally. Same kernel,
  * same handshake, identical results; needs every member's INPUT to be peer-mappable, otherwise the call silently uses
- * mode 0. Same value on every rank. Also CUDECOMP_B200_TRANSFER=pull. EXPERIMENTAL until measured on hardware. */
+ * mode 0. Staged calls (in place, forced staging) then load into the receiver's OWN workspace and unpack locally, so
+ * nothing is written into a peer's memory and the workspace need not be peer-mappable (chunked staging keeps the
+ * sender-driven schedule). Same value on every rank. Also CUDECOMP_B200_TRANSFER=pull. EXPERIMENTAL until measured. */
 cudecompResult_t cudecompB200SetTransferMode(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t mode);
 
 /* Chunked schedule of staged transposes (in-place calls, NVSHMEM-family backends, non-exportable outputs): the pencil

@@ -81,6 +81,7 @@ if [ "$N" = 2 ] || [ "$N" = 4 ]; then
   bench wide --no-e2e --wide
   bench pull --no-e2e --pull
   bench pull_wide --no-e2e --pull --wide
+  bench pull_inplace --no-e2e --pull --inplace
   bench pairwise --no-e2e --peer-order 1
   bench balanced --no-e2e --balance-grid 1
   bench tile16384 --no-e2e --tile-bytes 16384

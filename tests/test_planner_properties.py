@@ -115,6 +115,19 @@ def test_receiver_driven_plans_equal_oracle(d):
                 apply_box(box, ins[box["peer_rank"]], outs[r])
         for r in range(n):
             assert np.array_equal(outs[r], want[r]), (d, op, r)
+        # through the receiver's own workspace (staged == 3): load into `work`, then the local unpack
+        outs = [np.full(w.size, -3, np.int64) for w in want]
+        for r in range(n):
+            work = np.full(max(o.transpose_workspace_size(), 1), -9, np.int64)
+            plan = cd.plan_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, 3)
+            for box in plan:
+                if not box["is_unpack"]:
+                    apply_box(box, ins[box["peer_rank"]], work)
+            for box in plan:
+                if box["is_unpack"]:
+                    apply_box(box, work, outs[r])
+        for r in range(n):
+            assert np.array_equal(outs[r], want[r]), (d, op, r, "pull staged")
 
 
 @settings(max_examples=int(__import__("os").environ.get("CDB_HYPOTHESIS_EXAMPLES", "150")), deadline=None, suppress_health_check=list(HealthCheck))

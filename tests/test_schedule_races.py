@@ -134,7 +134,7 @@ def build_chain(d, mode, inplace, K=4, broken=None):
                 plans[r] = cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, None, None, None, None, inplace, K)
             else:
                 plans[r] = cd.plan_transpose_boxes(cfg, r, ax, direction, None, None, None, None,
-                                                   {"direct": 0, "staged": 1, "pull": 2}[eff])
+                                                   {"direct": 0, "staged": 1, "pull": 2, "pull_staged": 3}[eff])
         groups = {}
         for r in range(n):
             members = tuple(sorted({b["peer_rank"] for b in plans[r] if not b["is_unpack"]} | {r}))
@@ -147,9 +147,9 @@ def build_chain(d, mode, inplace, K=4, broken=None):
                 push = [b for b in plans[r] if not b["is_unpack"] and (steps == 1 or b["step"] == s)]
                 L = g.launch(r, "main", "%s#%d push%d r%d" % (op, opi, s, r), [last_main[r]] if last_main[r] is not None else [])
                 for b in push:
-                    if eff == "pull":
+                    if eff in ("pull", "pull_staged"):
                         L["reads"].append(((b["peer_rank"], src_name), cells(b, "src")))
-                        L["writes"].append(((r, dst_name), cells(b, "dst")))
+                        L["writes"].append(((r, dst_name if eff == "pull" else "work"), cells(b, "dst")))
                     else:
                         target = "work" if eff in ("staged", "chunked") else dst_name
                         L["reads"].append(((r, src_name), cells(b, "src")))
@@ -194,7 +194,8 @@ GRIDS = [([8, 6, 10], [2, 2], False), ([7, 9, 8], [2, 2], True), ([8, 8, 8], [1,
 
 @pytest.mark.parametrize("gdims,pdims,ac", GRIDS, ids=["%dx%d%s" % (p[0], p[1], "_ac" if a else "") for _, p, a in GRIDS])
 @pytest.mark.parametrize("mode,inplace", [("direct", False), ("pull", False), ("staged", True), ("staged", False),
-                                          ("chunked", True), ("chunked", False)])
+                                          ("pull_staged", True), ("pull_staged", False), ("chunked", True),
+                                          ("chunked", False)])
 def test_schedules_are_race_free(gdims, pdims, ac, mode, inplace):
     g = build_chain(decomposition(gdims, pdims, ac), mode, inplace, K=3)
     assert g.races() == []

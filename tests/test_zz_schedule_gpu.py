@@ -27,7 +27,11 @@ CASES = [
     dict(BASE, name="Pull_oop_4x1_uneven_axis_contiguous_halos", gdims=[31, 30, 29], pdims=[4, 1], dtype="float",
          out_of_place=True, pull=1, axis_contiguous=[True] * 3,
          halos={"0": [1, 1, 1], "1": [1, 0, 1], "2": [0, 1, 1]}, pads={"0": [1, 0, 0], "1": [0, 1, 0], "2": [0, 0, 2]}),
-    dict(BASE, name="Pull_inplace_falls_back_to_staged_push", gdims=[32, 40, 48], pdims=[2, 2], dtype="double", pull=1),
+    dict(BASE, name="PullStaged_inplace_2x2", gdims=[32, 40, 48], pdims=[2, 2], dtype="double", pull=1),
+    dict(BASE, name="PullStaged_inplace_1x4_c128_private_workspace", gdims=[24, 32, 40], pdims=[1, 4], dtype="double_complex",
+         pull=1, work_alloc="torch"),  # nobody writes into a peer's workspace, so it need not come from cudecompMalloc
+    dict(BASE, name="PullStaged_forced_oop_axis_contiguous", gdims=[30, 29, 35], pdims=[2, 2], dtype="float",
+         out_of_place=True, force_staged=True, pull=1, axis_contiguous=[True] * 3),
     dict(BASE, name="Wide256_oop_2x2_c128", gdims=[64, 40, 48], pdims=[2, 2], dtype="double_complex", out_of_place=True,
          kernel_variant=2),
     dict(BASE, name="Wide256_inplace_2x2_uneven_float_falls_back", gdims=[31, 30, 29], pdims=[2, 2], dtype="float",
