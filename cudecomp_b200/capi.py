@@ -523,7 +523,7 @@ def plan_pipelined_transpose_boxes(config, rank, ax, direction, input_halo_exten
     arr = (cudecompB200Box_t * max_boxes)()
     n = lib.cudecompB200PlanPipelinedTransposeBoxes(ctypes.byref(config), rank, ax, direction,
                                                     _arr3(input_halo_extents), _arr3(output_halo_extents),
-                                                    _arr3(input_padding), _arr3(output_padding), 1 if inplace else 0,
+                                                    _arr3(input_padding), _arr3(output_padding), int(inplace),
                                                     nchunks, arr, max_boxes)
     if n < 0:
         raise CudecompError(-n, "cudecompB200PlanPipelinedTransposeBoxes")

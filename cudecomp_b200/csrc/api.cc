@@ -901,9 +901,10 @@ int32_t cudecompB200PlanPipelinedTransposeBoxes(const cudecompGridDescConfig_t* 
   try {
     GridGeom g = geomFromConfig(config);
     if (rank < 0 || rank >= g.pdims[0] * g.pdims[1]) THROW_INVALID_USAGE("rank out of range");
+    // inplace: bit 0 = in place, bit 1 = receiver-driven (peer_rank of a push box then owns the SOURCE)
     PipelinedPlan pp = buildPipelinedTransposePlan(g, pidxOfRank(g, rank), ax, dir, input_halo_extents,
-                                                   output_halo_extents, input_padding, output_padding, inplace != 0,
-                                                   nchunks);
+                                                   output_halo_extents, input_padding, output_padding, (inplace & 1) != 0,
+                                                   nchunks, (inplace & 2) != 0);
     int32_t n = 0, total = 0;
     for (size_t s = 0; s < pp.steps.size(); ++s) {
       for (int pass = 0; pass < 2; ++pass) {

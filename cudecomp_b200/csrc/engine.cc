@@ -143,9 +143,9 @@ uint32_t haloOpcode(int ax, int dim) { return 0x200u + static_cast<uint32_t>(ax)
 bool runPipelinedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, void* input, void* output, void* work,
                         int es, const int32_t in_halo[], const int32_t out_halo[], const int32_t in_pad[],
                         const int32_t out_pad[], bool inplace, const std::vector<CallMsg>& msgs,
-                        const std::vector<int>& peers, PerfSample* perf, cudaStream_t stream) {
+                        const std::vector<int>& peers, PerfSample* perf, cudaStream_t stream, bool pull) {
   PipelinedPlan pp = buildPipelinedTransposePlan(gd->geom, gd->pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, inplace,
-                                                 gd->pipeline_chunks);
+                                                 gd->pipeline_chunks, pull);
   if (pp.steps.empty()) return false;
   const size_t K = pp.steps.size();
   if (!gd->side_stream) {
@@ -169,6 +169,12 @@ bool runPipelinedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int d
     if (s > 0) sync.do_entry = 0;
     std::vector<ResolvedBox> push, unpack;
     for (auto& b : pp.steps[s].push) {
+      if (pull) { // load the slice from its owner's input into my workspace
+        const char* src = (b.peer == pp.base.me) ? static_cast<const char*>(input)
+                                                 : static_cast<const char*>(h->peers.resolve(b.peer_world, msgs[b.peer].src));
+        push.push_back({b, src, static_cast<char*>(work)});
+        continue;
+      }
       char* dst = (b.peer == pp.base.me) ? static_cast<char*>(work)
                                          : static_cast<char*>(h->peers.resolve(b.peer_world, msgs[b.peer].work));
       push.push_back({b, static_cast<const char*>(input), dst});
@@ -264,7 +270,7 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
   // unpacks locally, so nothing is written into a peer's memory (the workspace need not be mappable). In place this is
   // safe for the same reason the sender-driven staged schedule is: a pencil is only overwritten by its owner's unpack,
   // after the exit handshake has told it that every peer has finished reading.
-  const bool pull_staged = !direct && src_ok && !(gd->pipeline_chunks > 1);
+  const bool pull_staged = !direct && src_ok;
   if (!direct && !work_ok && !pull_staged)
     THROW_INVALID_USAGE("the workspace must be device memory that peers can map: allocate it with cudecompMalloc");
 
@@ -299,6 +305,10 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
     launchBoxes(gd, boxes, es, sync, stream, probe.me, P);
   } else if (pull_staged) {
     gd->last_path = CUDECOMP_B200_PATH_STAGED;
+    if (gd->pipeline_chunks > 1 &&
+        runPipelinedStaged(h, gd, ax, dir, input, output, work, es, in_halo, out_halo, in_pad, out_pad, inplace, msgs,
+                           peers, perf.sample, stream, true))
+      return;
     TransposePlan pl = buildPullTransposePlan(gd->geom, gd->pidx, ax, dir, in_halo, out_halo, in_pad, out_pad,
                                               DstKind::STAGE, inplace);
     std::vector<ResolvedBox> pullb, unpack;
@@ -317,7 +327,7 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
     gd->last_path = CUDECOMP_B200_PATH_STAGED;
     if (gd->pipeline_chunks > 1 &&
         runPipelinedStaged(h, gd, ax, dir, input, output, work, es, in_halo, out_halo, in_pad, out_pad, inplace, msgs,
-                           peers, perf.sample, stream))
+                           peers, perf.sample, stream, false))
       return;
     TransposePlan st = buildTransposePlan(gd->geom, gd->pidx, ax, dir, in_halo, out_halo, in_pad, out_pad,
                                           DstKind::STAGE, inplace);

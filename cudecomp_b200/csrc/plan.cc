@@ -135,7 +135,27 @@ inline std::pair<int64_t, int64_t> chunkRange(int64_t n, int K, int k) { return 
 
 PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dir,
                                           const int32_t in_halo[3], const int32_t out_halo[3], const int32_t in_pad[3],
-                                          const int32_t out_pad[3], bool inplace, int nchunks) {
+                                          const int32_t out_pad[3], bool inplace, int nchunks, bool pull) {
+  if (pull) {
+    PipelinedPlan mine = buildPipelinedTransposePlan(g, pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, inplace, nchunks);
+    if (mine.steps.empty()) return mine;
+    const int ci = mine.base.axes.comm;
+    for (auto& st : mine.steps) st.push.clear();
+    for (int j = 0; j < mine.base.comm_size; ++j) {
+      auto pj = pidx;
+      pj[ci] = j;
+      const PipelinedPlan theirs =
+          buildPipelinedTransposePlan(g, pj, ax, dir, in_halo, out_halo, in_pad, out_pad, inplace, nchunks);
+      for (size_t s = 0; s < theirs.steps.size() && s < mine.steps.size(); ++s)
+        for (BoxDesc b : theirs.steps[s].push) {
+          if (b.peer != mine.base.me) continue;
+          b.peer = j;
+          b.peer_world = mine.base.group_world[j];
+          mine.steps[s].push.push_back(b);
+        }
+    }
+    return mine;
+  }
   PipelinedPlan pp;
   pp.base = buildTransposePlan(g, pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, DstKind::STAGE, inplace);
   if (pp.base.noop || nchunks <= 1 || pp.base.push.empty()) return pp;

@@ -79,9 +79,13 @@ struct PipelinedPlan {
   int chunk_axis = -1;             // global axis the chunks run along
   std::vector<PipelineStep> steps; // empty: not applicable, run `base` as is
 };
+// pull == true: the receiver-driven mirror image. Step s then holds, per source rank j, the slice rank j would have
+// pushed to me in its step s (its source strides, `peer` = j); the unpack lists are unchanged, because the same data
+// lands in my workspace at the same step and the planes of my pencil that are still unread after step s are the same
+// (they are now read by the peers' later steps instead of by mine).
 PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dir,
                                           const int32_t in_halo[3], const int32_t out_halo[3], const int32_t in_pad[3],
-                                          const int32_t out_pad[3], bool inplace, int nchunks);
+                                          const int32_t out_pad[3], bool inplace, int nchunks, bool pull = false);
 
 struct HaloPlan {
   bool nothing = false; // zero halo width, or no neighbour in this dimension

@@ -63,8 +63,7 @@ cudecompResult_t cudecompB200SetSchedule(cudecompHandle_t handle, cudecompGridDe
  * (default), 1 = the receiver loads its blocks from the peers' inputs and writes its own output locally. Same kernel,
  * same handshake, identical results; needs every member's INPUT to be peer-mappable, otherwise the call silently uses
  * mode 0. Staged calls (in place, forced staging) then load into the receiver's OWN workspace and unpack locally, so
- * nothing is written into a peer's memory and the workspace need not be peer-mappable (chunked staging keeps the
- * sender-driven schedule). Same value on every rank. Also CUDECOMP_B200_TRANSFER=pull. EXPERIMENTAL until measured. */
+ * nothing is written into a peer's memory and the workspace need not be peer-mappable (also with chunked staging). Same value on every rank. Also CUDECOMP_B200_TRANSFER=pull. EXPERIMENTAL until measured. */
 cudecompResult_t cudecompB200SetTransferMode(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t mode);
 
 /* Chunked schedule of staged transposes (in-place calls, NVSHMEM-family backends, non-exportable outputs): the pencil
@@ -103,7 +102,8 @@ int32_t cudecompB200PlanHaloBoxes(const cudecompGridDescConfig_t* config, int32_
                                   int32_t staged, cudecompB200Box_t* boxes, int32_t max_boxes);
 
 /* The chunked (pipelined) variant of the staged schedule for `nchunks` chunks (csrc/plan.h PipelinedPlan): boxes carry
- * the step they run in. Returns 0 boxes when chunking does not apply. */
+ * the step they run in. Returns 0 boxes when chunking does not apply. `inplace`: bit 0 = in place, bit 1 = receiver-
+ * driven (cudecompB200SetTransferMode; peer_rank of a push box is then the rank whose input it is loaded from). */
 int32_t cudecompB200PlanPipelinedTransposeBoxes(const cudecompGridDescConfig_t* config, int32_t rank, int32_t ax,
                                                 int32_t dir, const int32_t input_halo_extents[],
                                                 const int32_t output_halo_extents[], const int32_t input_padding[],

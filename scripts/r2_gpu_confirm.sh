@@ -82,6 +82,7 @@ if [ "$N" = 2 ] || [ "$N" = 4 ]; then
   bench pull --no-e2e --pull
   bench pull_wide --no-e2e --pull --wide
   bench pull_inplace --no-e2e --pull --inplace
+  bench pull_inplace_chunks8 --no-e2e --pull --inplace --chunks 8
   bench pairwise --no-e2e --peer-order 1
   bench balanced --no-e2e --balance-grid 1
   bench tile16384 --no-e2e --tile-bytes 16384

@@ -189,14 +189,15 @@ def _box_cells(box, which):
     return off + sum(idx[k] * strides[k] for k in range(3))
 
 
-def run_pipelined(cfg, o, op, ha, hb, pa, pb, inplace, K, ins):
+def run_pipelined(cfg, o, op, ha, hb, pa, pb, inplace, K, ins, pull=False):
     """Executes the chunked schedule of every rank step by step the way the device would be allowed to:
     step s = all pushes of chunk s, then all unpacks scheduled for step s. Returns the output buffers, or None if
     chunking does not apply."""
     ax, direction = OPS[op]
     a, b = orc.transpose_axes(op)
     n = o.nranks
-    plans = [cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, inplace, K) for r in range(n)]
+    plans = [cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, int(inplace) + (2 if pull else 0), K)
+             for r in range(n)]
     if not any(plans):
         return None
     sizes = [max(o.pencil_info(r, a, ha, pa).size, o.pencil_info(r, b, hb, pb).size) for r in range(n)]
@@ -214,9 +215,11 @@ def run_pipelined(cfg, o, op, ha, hb, pa, pb, inplace, K, ins):
                 if box["step"] == s and not box["is_unpack"]:
                     dst = _box_cells(box, "dst")
                     peer = box["peer_rank"]
-                    assert (arrived[peer][dst] == -1).all(), "a workspace cell is written twice"
-                    arrived[peer][dst] = s
-                    works[peer][dst] = bufs[r][_box_cells(box, "src")]
+                    # sender-driven: r stores into peer's workspace; receiver-driven: r loads from peer's pencil
+                    owner, source = (r, peer) if pull else (peer, r)
+                    assert (arrived[owner][dst] == -1).all(), "a workspace cell is written twice"
+                    arrived[owner][dst] = s
+                    works[owner][dst] = bufs[source][_box_cells(box, "src")]
         for r in range(n):
             for box in plans[r]:
                 if box["step"] == s and box["is_unpack"]:
@@ -228,8 +231,8 @@ def run_pipelined(cfg, o, op, ha, hb, pa, pb, inplace, K, ins):
 
 @settings(max_examples=int(__import__("os").environ.get("CDB_HYPOTHESIS_EXAMPLES", "150")), deadline=None,
           suppress_health_check=list(HealthCheck))
-@given(decompositions(), st.sampled_from([2, 3, 4, 8]), st.booleans())
-def test_pipelined_schedule_equals_oracle(d, K, inplace):
+@given(decompositions(), st.sampled_from([2, 3, 4, 8]), st.booleans(), st.booleans())
+def test_pipelined_schedule_equals_oracle(d, K, inplace, pull):
     cfg, o = make_config(d), make_oracle(d)
     n = o.nranks
     for op in OPS:
@@ -248,8 +251,8 @@ def test_pipelined_schedule_equals_oracle(d, K, inplace):
             ref_in.append(buf)
         ref_out = ref_in if inplace else [np.full(sizes[r], -3, np.int64) for r in range(n)]
         o.transpose(op, ref_in, ref_out, ha, hb, pa, pb)
-        got = run_pipelined(cfg, o, op, ha, hb, pa, pb, inplace, K, ins)
+        got = run_pipelined(cfg, o, op, ha, hb, pa, pb, inplace, K, ins, pull)
         if got is None:
             continue
         for r in range(n):
-            assert np.array_equal(got[r], ref_out[r]), (d, op, K, inplace, r)
+            assert np.array_equal(got[r], ref_out[r]), (d, op, K, inplace, pull, r)

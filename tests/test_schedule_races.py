@@ -130,8 +130,9 @@ def build_chain(d, mode, inplace, K=4, broken=None):
             eff = "staged" if inplace else "direct"
         plans = {}
         for r in range(n):
-            if eff == "chunked":
-                plans[r] = cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, None, None, None, None, inplace, K)
+            if eff in ("chunked", "pull_chunked"):
+                plans[r] = cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, None, None, None, None,
+                                                             int(inplace) + (2 if eff == "pull_chunked" else 0), K)
             else:
                 plans[r] = cd.plan_transpose_boxes(cfg, r, ax, direction, None, None, None, None,
                                                    {"direct": 0, "staged": 1, "pull": 2, "pull_staged": 3}[eff])
@@ -139,7 +140,7 @@ def build_chain(d, mode, inplace, K=4, broken=None):
         for r in range(n):
             members = tuple(sorted({b["peer_rank"] for b in plans[r] if not b["is_unpack"]} | {r}))
             groups.setdefault(members, []).append(r)
-        steps = K if eff == "chunked" else 1
+        steps = K if eff in ("chunked", "pull_chunked") else 1
         side_last = [None] * n
         for s in range(steps):
             step_launch = {}
@@ -147,7 +148,7 @@ def build_chain(d, mode, inplace, K=4, broken=None):
                 push = [b for b in plans[r] if not b["is_unpack"] and (steps == 1 or b["step"] == s)]
                 L = g.launch(r, "main", "%s#%d push%d r%d" % (op, opi, s, r), [last_main[r]] if last_main[r] is not None else [])
                 for b in push:
-                    if eff in ("pull", "pull_staged"):
+                    if eff in ("pull", "pull_staged", "pull_chunked"):
                         L["reads"].append(((b["peer_rank"], src_name), cells(b, "src")))
                         L["writes"].append(((r, dst_name if eff == "pull" else "work"), cells(b, "dst")))
                     else:
@@ -195,7 +196,7 @@ GRIDS = [([8, 6, 10], [2, 2], False), ([7, 9, 8], [2, 2], True), ([8, 8, 8], [1,
 @pytest.mark.parametrize("gdims,pdims,ac", GRIDS, ids=["%dx%d%s" % (p[0], p[1], "_ac" if a else "") for _, p, a in GRIDS])
 @pytest.mark.parametrize("mode,inplace", [("direct", False), ("pull", False), ("staged", True), ("staged", False),
                                           ("pull_staged", True), ("pull_staged", False), ("chunked", True),
-                                          ("chunked", False)])
+                                          ("chunked", False), ("pull_chunked", True), ("pull_chunked", False)])
 def test_schedules_are_race_free(gdims, pdims, ac, mode, inplace):
     g = build_chain(decomposition(gdims, pdims, ac), mode, inplace, K=3)
     assert g.races() == []

@@ -30,6 +30,9 @@ CASES = [
     dict(BASE, name="PullStaged_inplace_2x2", gdims=[32, 40, 48], pdims=[2, 2], dtype="double", pull=1),
     dict(BASE, name="PullStaged_inplace_1x4_c128_private_workspace", gdims=[24, 32, 40], pdims=[1, 4], dtype="double_complex",
          pull=1, work_alloc="torch"),  # nobody writes into a peer's workspace, so it need not come from cudecompMalloc
+    dict(BASE, name="PullChunked4_inplace_2x2", gdims=[32, 40, 48], pdims=[2, 2], dtype="double", pull=1, pipeline_chunks=4),
+    dict(BASE, name="PullChunked3_inplace_1x4_uneven_axis_contiguous", gdims=[30, 29, 35], pdims=[1, 4], dtype="float_complex",
+         pull=1, pipeline_chunks=3, axis_contiguous=[True] * 3),
     dict(BASE, name="PullStaged_forced_oop_axis_contiguous", gdims=[30, 29, 35], pdims=[2, 2], dtype="float",
          out_of_place=True, force_staged=True, pull=1, axis_contiguous=[True] * 3),
     dict(BASE, name="Wide256_oop_2x2_c128", gdims=[64, 40, 48], pdims=[2, 2], dtype="double_complex", out_of_place=True,
