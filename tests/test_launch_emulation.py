@@ -159,8 +159,8 @@ def test_emulated_halos_equal_oracle(d, s, halo, periods, padding):
 
 
 @settings(max_examples=max(EXAMPLES // 3, 20), deadline=None, suppress_health_check=list(HealthCheck))
-@given(decompositions(), schedules(), st.sampled_from([2, 3, 4, 8]), st.booleans())
-def test_emulated_pipelined_schedule_equals_oracle(d, s, K, inplace):
+@given(decompositions(), schedules(), st.sampled_from([2, 3, 4, 8]), st.booleans(), st.booleans())
+def test_emulated_pipelined_schedule_equals_oracle(d, s, K, inplace, pull):
     """The chunked schedule executed step by step (engine.cc runPipelinedStaged): push launches of step k, then the
     unpack launches of step k, every launch through the emulator."""
     cfg, o = make_config(d), make_oracle(d)
@@ -171,7 +171,8 @@ def test_emulated_pipelined_schedule_equals_oracle(d, s, K, inplace):
         if o.has_empty_pencils(a) or o.has_empty_pencils(b):
             continue
         ha, hb, pa, pb = d["halos"][str(a)], d["halos"][str(b)], d["pads"][str(a)], d["pads"][str(b)]
-        plans = [cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, inplace, K) for r in range(n)]
+        plans = [cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, int(inplace) + (2 if pull else 0), K)
+                 for r in range(n)]
         if not any(plans):
             continue
         rng = np.random.default_rng(5)
@@ -189,13 +190,17 @@ def test_emulated_pipelined_schedule_equals_oracle(d, s, K, inplace):
             for r in range(n):
                 push = [bx for bx in plans[r] if bx["step"] == step and not bx["is_unpack"]]
                 gi = group_index(plans[r])
-                emulate(push, lambda bx: bufs[r], lambda bx: works[bx["peer_rank"]], legal, s, me=gi.get(r, -1), comm=len(gi),
-                        peer_index=[gi[bx["peer_rank"]] for bx in push])
+                if pull:  # load from the owner's pencil into my workspace
+                    emulate(push, lambda bx: bufs[bx["peer_rank"]], lambda bx: works[r], legal, s, me=gi.get(r, -1),
+                            comm=len(gi), peer_index=[gi[bx["peer_rank"]] for bx in push])
+                else:
+                    emulate(push, lambda bx: bufs[r], lambda bx: works[bx["peer_rank"]], legal, s, me=gi.get(r, -1),
+                            comm=len(gi), peer_index=[gi[bx["peer_rank"]] for bx in push])
             for r in range(n):
                 unpack = [bx for bx in plans[r] if bx["step"] == step and bx["is_unpack"]]
                 emulate(unpack, lambda bx: works[r], lambda bx: outs[r], legal, s)
         for r in range(n):
-            assert np.array_equal(outs[r], ref_out[r]), (d, s, op, K, inplace, r)
+            assert np.array_equal(outs[r], ref_out[r]), (d, s, op, K, inplace, pull, r)
 
 
 def test_kernel_selection_and_vector_width():
