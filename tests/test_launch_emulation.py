@@ -292,6 +292,7 @@ def test_balanced_grid():
     b = g(0, 370, 444, 4096, 1)                           # 4096 slots: 12 full rounds of 342 CTAs instead of 11.07 of 370
     assert 296 <= b <= 370 and -(-4096 // b) * b - 4096 < 10
     assert g(0, 370, 444, 370 * 50, 1) == 370             # already even: unchanged
+    assert g(0, 370, 444, 3600, 1) == 360                 # 300 and 360 both divide 3600: the larger count wins the tie
     for slots in (371, 1000, 4097, 65536, 99991):
         b = g(0, 370, 444, slots, 1)
         assert 296 <= b <= 370
