@@ -64,6 +64,13 @@ if [ "$N" = 1 ]; then
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --axis-contiguous > $OUT/r2_n1_ncu_ac_full.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:rowCopyBulkKernel -c 1 -o $OUT/r2_n1_bulk_full \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --bulk > $OUT/r2_n1_ncu_bulk_full.log 2>&1
+  # text exports travel back in any case; the reports themselves only when they are small (gpurun_out is capped at 64 MiB)
+  for rep in $OUT/r2_n1_transpose_full $OUT/r2_n1_bulk_full; do
+    [ -f $rep.ncu-rep ] || continue
+    ncu -i $rep.ncu-rep --page raw --csv > $rep.raw.csv 2>/dev/null
+    ncu -i $rep.ncu-rep --page details > $rep.details.txt 2>/dev/null
+    [ $(stat -c %s $rep.ncu-rep) -gt 20000000 ] && rm -f $rep.ncu-rep
+  done
 fi
 
 if [ "$N" = 2 ] || [ "$N" = 4 ]; then
