@@ -38,3 +38,32 @@ def test_r2_summarize_reads_bench_lines(tmp_path):
                          capture_output=True, text=True, timeout=60)
     assert out.returncode == 0, out.stderr
     assert "### 8 GPUs" in out.stdout and "| default |" in out.stdout and "| inplace |" in out.stdout
+
+
+def test_runbook_only_uses_flags_bench_py_knows():
+    """scripts/r2_gpu_confirm.sh spends GPU minutes: every `bench <label> <args>` line and every CANDIDATES_8 entry must
+    parse with bench.py's own argument parser (a typo would only show up on the GPU box)."""
+    import importlib.util
+    import re
+    import shlex
+    spec = importlib.util.spec_from_file_location("bench_main", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    text = open(os.path.join(ROOT, "scripts", "r2_gpu_confirm.sh")).read()
+    lines = []
+    for line in text.splitlines():
+        m = re.match(r"\s*(?:for \w+ in [^;]+; do )?bench (\S+)(.*?)(?:; done)?$", line)
+        if m and "$label" not in line and "()" not in line:
+            lines.append(m.group(2))
+    for entry in re.search(r'CANDIDATES_8:-"(.*?)"\}', text, re.S).group(1).splitlines():
+        lines.append(entry.split("|", 1)[1])
+    assert len(lines) > 30
+    old_argv = sys.argv
+    try:
+        for args in lines:
+            args = re.sub(r"\$\w+", "8", args)  # loop variables ($k, $t)
+            sys.argv = ["bench.py"] + shlex.split(args)
+            parsed = bench.parse_args()
+            assert parsed.n in (512, 1024)
+    finally:
+        sys.argv = old_argv
