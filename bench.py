@@ -53,7 +53,10 @@ def parse_args():
     ap.add_argument("--bulk", action="store_true", help="TMA bulk row-copy variant (experimental)")
     ap.add_argument("--wide", action="store_true", help="256-bit LDG/STG row-copy variant (experimental)")
     ap.add_argument("--pull", action="store_true", help="receiver-driven direct transposes (experimental)")
-    ap.add_argument("--chunks", type=int, default=0, help="chunked schedule of staged transposes (experimental)")
+    ap.add_argument("--chunks", type=int, default=0, help="chunks of staged (in-place) transposes, 0 = from the pencil size")
+    ap.add_argument("--staged-mode", type=int, default=0, help="0 one phased launch per staged transpose, 1 separate launches")
+    ap.add_argument("--lag", type=int, default=0, help="phases between a chunk's push and its unpack (0 = library default)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed integer-pattern check after the timed region")
     ap.add_argument("--tile-bytes", type=int, default=0, help="row-copy tile size (0 = 32 KiB)")
     ap.add_argument("--peer-order", type=int, default=0, help="0 one-shot interleaved, 1 pairwise rounds")
     ap.add_argument("--balance-grid", type=int, default=0, help="1: CTA count with the fullest last grid-stride round")
@@ -129,12 +132,11 @@ def run_reference(args, rank, world):
     import torch  # noqa: F401  (only for parity of the environment; not used by the timed code)
 
     n = args.n
-    nz = max(1, min(n, 32))  # 1024 x 1024 x 32 complex128 = 0.54 GB: ~1/32 of the workload per step
     pd = GRID_BY_N.get(args.gpus, (1, args.gpus))
     if args.pdims:
         pd = tuple(int(v) for v in args.pdims.split("x"))
-    # the sample keeps the full x-y extent (what the X<->Y exchange moves) and thins z
-    nz = max(nz, pd[1] * 4)
+    # whole grid when the host can hold it and `steps + warmup` round trips end within ~3 minutes, else a z-slab
+    nz = cpu_sample_nz(args, pd, budget_s=180.0, steps=args.steps + args.warmup)
     gd = [n, n, nz]
     o = orc.Oracle(gd, pd, (args.axis_contiguous,) * 3)
     # every core this process may run on: torchrun exports OMP_NUM_THREADS=1 to its workers, which would leave the
@@ -161,8 +163,9 @@ def run_reference(args, rank, world):
         step()
     dt_s = (time.perf_counter() - t0) / args.steps
     value = 4.0 * S_total / dt_s / 1e9
-    sample = "z-slab %dx%dx%d of the %d^3 %s grid, %s, pdims %dx%d as %d in-process ranks" % (
-        n, n, nz, n, args.dtype, "in-place" if args.inplace else "out-of-place", pd[0], pd[1], o.nranks)
+    sample = "%s %dx%dx%d of the %d^3 %s grid, %s, pdims %dx%d as %d in-process ranks" % (
+        "the whole grid" if nz == n else "z-slab", n, n, nz, n, args.dtype,
+        "in-place" if args.inplace else "out-of-place", pd[0], pd[1], o.nranks)
     line = {
         "impl": "reference", "metric": "effective transpose GB/s (4*S/t round trip, whole job)", "value": value,
         "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_s * 1e3,
@@ -174,6 +177,37 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def mem_available_bytes():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
+
+
+def cpu_sample_nz(args, pd, budget_s, gbs_guess=15.0, steps=1):
+    """z extent of the CPU sample: the WHOLE grid when host memory (input + output + the oracle's send / receive staging =
+    4 grids) and the time budget allow it, else the largest power-of-two z-slab that does. The x-y extent is always
+    full (what the X<->Y exchange moves); z only has to hold 4 planes per rank of the row communicator."""
+    import numpy as np
+    from oracle import oracle as orc
+    es = np.dtype(orc.NP_DTYPES[args.dtype]).itemsize
+    n = args.n
+    nz = n
+    avail = mem_available_bytes()
+    while nz > max(pd[1] * 4, 8):
+        grid_bytes = float(n) * n * nz * es
+        fits = avail == 0 or 4.5 * grid_bytes < 0.6 * avail
+        quick = 4.0 * grid_bytes / (gbs_guess * 1e9) * steps <= budget_s
+        if fits and quick:
+            break
+        nz //= 2
+    return max(nz, pd[1] * 4)
 
 
 def workload_config(args, pd, sample=None):
@@ -222,7 +256,7 @@ def run_native(args, rank, world, local_rank):
     # The CPU leg runs first, before this process narrows its affinity to the GPU's NUMA node: it gets every core the
     # process was given (threads created later would inherit the narrowed mask).
     cpu_first = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         pd0 = tuple(int(v) for v in args.pdims.split("x")) if args.pdims else GRID_BY_N.get(world, (1, world))
         cpu_first = cpu_baseline(args, pd0)
 
@@ -274,6 +308,8 @@ def run_native(args, rank, world, local_rank):
         cd.check(cd.set_transfer_mode(handle, gd, 1))
     if args.chunks:
         cd.check(cd.set_pipeline_chunks(handle, gd, args.chunks))
+    if args.staged_mode or args.lag:
+        cd.check(cd.set_staged_mode(handle, gd, args.staged_mode, args.lag))
     if args.tile_bytes or args.peer_order or args.balance_grid:
         cd.check(cd.set_schedule(handle, gd, args.tile_bytes, args.peer_order, bool(args.balance_grid)))
 
@@ -328,6 +364,56 @@ def run_native(args, rank, world, local_rank):
     ms_step = max_over_ranks(total_ms / args.steps)
     op_ms = [max_over_ranks(v) for v in op_ms]
     value = world * 4.0 * S / (ms_step * 1e-3) / 1e9
+
+    # ---- parity at size (untimed): the reference tests' known answer (tests/ctest/transpose_tests.cc:333-378) -- every
+    # element carries its GLOBAL linear index as an integer bit pattern (16-byte elements: the index and its bitwise
+    # complement), built and compared on the device. After each of the four operations this rank's whole output pencil
+    # must equal the analytic pattern of that orientation, on every rank.
+    parity = None
+    if not args.no_parity:
+        infos = [cd.cudecompGetPencilInfo(handle, gd, ax)[1] for ax in range(3)]
+        gstride = [1, args.n, args.n * args.n]
+        idt = torch.int32 if es == 4 else torch.int64
+
+        def expected(ax):
+            p = infos[ax]
+            terms = []
+            for k in range(3):
+                v = (torch.arange(p.shape[k], device=dev, dtype=torch.int64) + p.lo[k]) * gstride[p.order[k]]
+                terms.append(v.to(idt))
+            g = (terms[2][:, None, None] + terms[1][None, :, None] + terms[0][None, None, :]).reshape(-1)
+            if es == 16:
+                return torch.stack([g, ~g], dim=1).reshape(-1)
+            return g
+
+        def as_ints(t, nelem):
+            return t.view(idt)[: nelem * (2 if es == 16 else 1)]
+
+        pa, pb = (a, b) if not args.inplace else (a, a)
+        as_ints(pa, sizes[0]).copy_(expected(0))
+        if not args.inplace:
+            pb.zero_()
+        bad_ops, cur, other = [], pa, pb
+        AXIS_AFTER = {"XY": 1, "YZ": 2, "ZY": 1, "YX": 0}
+        for op in OPS:
+            cd.check(cd.TRANSPOSES[op](handle, gd, cur, cur if args.inplace else other, work, dt_enum, None, None, None,
+                                       None, stream), op)
+            res_t = cur if args.inplace else other
+            ax = AXIS_AFTER[op]
+            want = expected(ax)
+            if not torch.equal(as_ints(res_t, sizes[ax]), want):
+                bad_ops.append(op)
+            del want
+            if not args.inplace:
+                cur, other = other, cur
+        torch.cuda.synchronize()
+        cd.check(cd.check_errors(handle, gd), "device-side handshake (parity run)")
+        ok_all = max_over_ranks(float(len(bad_ops))) == 0.0
+        parity = {"checked_ops": 4, "ok": bool(ok_all), "ranks": world,
+                  "pattern": "global linear index per element as integer bits, compared on the device on every rank "
+                             "after each operation (whole output pencil)", "failed_ops_rank0": bad_ops}
+        # restore a benign payload for the end-to-end leg
+        a.uniform_(0.0, 1.0, generator=gen)
 
     # ---- end to end: pinned host pencil -> device -> round trip -> pinned host, every step.
     # Steps are software-pipelined over two device buffer sets and three streams (H2D | transposes | D2H), the way a
@@ -426,7 +512,7 @@ def run_native(args, rank, world, local_rank):
     kern_ms = sum(op_ms) / 4.0
     achieved = 2.0 * S / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": TRAFFIC_BYTES.get((world, args.n, args.dtype, args.inplace)),
+                "traffic": measured_traffic(world, args),
                 "kernel": "cdb::transposeKernel<uint4>" if args.axis_contiguous else "cdb::rowCopyKernel<uint4>",
                 "peak_source": peak_src,
                 "per_op_ms": dict(zip(OPS, op_ms)), "algorithmic_bytes_per_launch": 2.0 * S,
@@ -465,6 +551,8 @@ def run_native(args, rank, world, local_rank):
                 "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
                 "host_enqueue_us_per_op": host_us_per_op,
                 "path": {0: "none", 1: "local", 2: "direct", 3: "staged"}[cd.last_path(handle, gd)]}
+        if parity:
+            line["parity"] = parity
         if nvlink:
             line["nvlink"] = nvlink
         if e2e:
@@ -482,25 +570,36 @@ def run_native(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu capture
-# (profiles/), keyed by (n_gpus, grid edge, dtype, inplace). Filled in when a capture of that configuration exists.
-TRAFFIC_BYTES = {
-    # profiles/r1_n1_rowcopy_full.txt: 17.180 GB read + 17.135 GB written per launch (algorithmic 2S = 34.360 GB)
-    (1, 1024, "double_complex", False): 34.315e9,
-}
+def measured_traffic(world, args):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu captures:
+    profiles/traffic.json lists one entry per captured configuration (kernel, commit, source file). None when this
+    configuration has no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            entries = json.load(f)["entries"]
+    except (OSError, ValueError, KeyError):
+        return None
+    for e in entries:
+        if (e.get("n_gpus") == world and e.get("grid") == args.n and e.get("dtype") == args.dtype and
+                bool(e.get("inplace")) == bool(args.inplace) and
+                bool(e.get("axis_contiguous")) == bool(args.axis_contiguous)):
+            return e.get("dram_bytes_per_launch")
+    return None
 
 
 def cpu_baseline(args, pd):
     """The oracle on this box's host cores, bounded sample of the same workload (see run_reference)."""
     import numpy as np
     from oracle import oracle as orc
-    n, nz = args.n, 32
+    n = args.n
+    reps = 2
+    nz = cpu_sample_nz(args, pd, budget_s=25.0, steps=reps + 1)  # about 10-30 s of CPU work
     o = orc.Oracle([n, n, nz], pd, (args.axis_contiguous,) * 3)
     o.set_threads(len(os.sched_getaffinity(0)))
     dt = orc.NP_DTYPES[args.dtype]
     es = np.dtype(dt).itemsize
-    A = [np.ones(o.pencil_info(0, 0).size, dt)]
-    B = [np.zeros_like(A[0])]
+    A = [np.ones(max(o.pencil_info(r, ax).size for ax in range(3)), dt) for r in range(o.nranks)]
+    B = [np.zeros_like(x) for x in A]
 
     def step():
         cur, other = A, B
@@ -509,13 +608,13 @@ def cpu_baseline(args, pd):
             if not args.inplace:
                 cur, other = other, cur
     step()
-    reps = 3
     t0 = time.perf_counter()
     for _ in range(reps):
         step()
     t = (time.perf_counter() - t0) / reps
     return {"value": 4.0 * n * n * nz * es / t / 1e9, "unit": "GB/s", "cores": o.max_threads(), "kind": "port",
-            "sample": "z-slab %dx%dx%d of the %d^3 %s grid, %d timed round trips" % (n, n, nz, n, args.dtype, reps)}
+            "sample": "%s %dx%dx%d of the %d^3 %s grid, pdims %dx%d as in-process ranks, %d timed round trips" % (
+                "the whole grid" if nz == n else "z-slab", n, n, nz, n, args.dtype, pd[0], pd[1], reps)}
 
 
 def main():

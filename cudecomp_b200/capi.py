@@ -138,7 +138,7 @@ API_SYMBOLS = [
     "cudecompUpdateHalosZ",
 ]
 EXT_SYMBOLS = ["cudecompB200GetLaunchCount", "cudecompB200GetLastPath", "cudecompB200SetTuning",
-               "cudecompB200CheckErrors", "cudecompB200SetPipelineChunks", "cudecompB200SetKernelVariant", "cudecompB200DescribeTransposeBoxes", "cudecompB200DescribeHaloBoxes",
+               "cudecompB200CheckErrors", "cudecompB200SetPipelineChunks", "cudecompB200SetStagedMode", "cudecompB200SetKernelVariant", "cudecompB200DescribeTransposeBoxes", "cudecompB200DescribeHaloBoxes",
                "cudecompB200PlanTransposeBoxes", "cudecompB200PlanHaloBoxes", "cudecompB200PlanPipelinedTransposeBoxes",
                "cudecompB200SelfTestMailbox", "cudecompB200GetAutotuneCandidates"]
 MPI_SHIM_SYMBOLS = ["MPI_Init", "MPI_Init_thread", "MPI_Initialized", "MPI_Finalize", "MPI_Finalized", "MPI_Abort",
@@ -193,6 +193,7 @@ _sig("cudecompB200GetLastPath", ctypes.c_int, [cudecompHandle_t, cudecompGridDes
 _sig("cudecompB200SetTuning", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32, _i32])
 _sig("cudecompB200CheckErrors", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t])
 _sig("cudecompB200SetPipelineChunks", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32])
+_sig("cudecompB200SetStagedMode", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32, _i32])
 _sig("cudecompB200SetKernelVariant", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32])
 _sig("cudecompB200SetSchedule", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32, _i32, _i32])
 _sig("cudecompB200SetTransferMode", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32])
@@ -459,6 +460,11 @@ def set_transfer_mode(handle, grid_desc, mode):
 
 def set_pipeline_chunks(handle, grid_desc, nchunks):
     return lib.cudecompB200SetPipelineChunks(handle, grid_desc, int(nchunks))
+
+
+def set_staged_mode(handle, grid_desc, mode, lag=0):
+    """0: staged transposes run as ONE phased launch (default), 1: separate push / unpack launches; lag 0 keeps the value."""
+    return lib.cudecompB200SetStagedMode(handle, grid_desc, int(mode), int(lag))
 
 
 def check_errors(handle, grid_desc):

@@ -214,6 +214,7 @@ void destroyGridDescResources(cudecompGridDesc_t gd, bool collective) {
     gd->pad_slot = -1;
   }
   gd->mbox.destroy();
+  releaseFusedCache(gd);
   for (cudaEvent_t e : gd->side_events) cudaEventDestroy(e);
   gd->side_events.clear();
   if (gd->side_stream) cudaStreamDestroy(gd->side_stream);
@@ -271,6 +272,8 @@ static void initHandle(cudecompHandle_t h, const CommPtr& parent) {
     h->peer_order = (std::strcmp(v, "pairwise") == 0 || std::strcmp(v, "1") == 0) ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_BALANCE_GRID")) h->balance_grid = std::atoi(v) != 0 ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_TRANSFER")) h->pull_mode = (std::strcmp(v, "pull") == 0) ? 1 : 0;
+  if (const char* v = std::getenv("CUDECOMP_B200_STAGED")) h->staged_mode = (std::strcmp(v, "launches") == 0) ? 1 : 0;
+  if (const char* v = std::getenv("CUDECOMP_B200_FUSED_LAG")) h->fused_lag = std::min(8, std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("CUDECOMP_B200_DIRECT")) h->allow_direct = std::strcmp(v, "0") != 0;
   double spin_s = 60.0;
   if (const char* v = std::getenv("CUDECOMP_B200_DEVICE_TIMEOUT")) spin_s = std::atof(v);
@@ -376,6 +379,8 @@ cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudeco
   gd->peer_order = handle->peer_order;
   gd->balance_grid = handle->balance_grid;
   gd->pull_mode = handle->pull_mode;
+  gd->staged_mode = handle->staged_mode;
+  gd->fused_lag = handle->fused_lag;
   if (gd->config.rank_order == CUDECOMP_RANK_ORDER_DEFAULT)
     gd->config.rank_order = handle->env_col_major ? CUDECOMP_RANK_ORDER_COL_MAJOR : CUDECOMP_RANK_ORDER_ROW_MAJOR;
 
@@ -733,6 +738,17 @@ cudecompResult_t cudecompB200SetPipelineChunks(cudecompHandle_t handle, cudecomp
   checkGridDesc(handle, grid_desc);
   if (nchunks < 0 || nchunks > 64) THROW_INVALID_USAGE("nchunks must be in [0, 64]");
   grid_desc->pipeline_chunks = nchunks; // must be set to the same value on every rank
+  API_CATCH()
+}
+
+cudecompResult_t cudecompB200SetStagedMode(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t mode, int32_t lag) {
+  API_TRY
+  checkHandle(handle);
+  checkGridDesc(handle, grid_desc);
+  if (mode < 0 || mode > 1) THROW_INVALID_USAGE("mode must be 0 (one phased launch) or 1 (separate launches)");
+  if (lag < 0 || lag > 8) THROW_INVALID_USAGE("lag must be in [0, 8] (0 keeps the current value)");
+  grid_desc->staged_mode = mode; // must be set to the same value on every rank
+  if (lag > 0) grid_desc->fused_lag = lag;
   API_CATCH()
 }
 

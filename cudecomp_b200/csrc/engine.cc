@@ -20,7 +20,24 @@ int64_t dtypeSize(cudecompDataType_t dtype) {
   THROW_INVALID_USAGE("unknown data type");
 }
 
+int autoFusedChunks(int64_t pencil_bytes) {
+  const int64_t k = pencil_bytes / (int64_t(8) << 20);
+  return static_cast<int>(std::min<int64_t>(std::max<int64_t>(k, 1), 16));
+}
+
+void releaseFusedCache(cudecompGridDesc_t gd) {
+  if (gd->fused_cache.empty()) return;
+  cudaDeviceSynchronize(); // a running phased launch may still read its tables
+  for (auto& e : gd->fused_cache) {
+    if (e.dev) cudaFree(e.dev);
+    if (e.host) cudaFreeHost(e.host);
+  }
+  gd->fused_cache.clear();
+  (void)cudaGetLastError();
+}
+
 void setGeometry(cudecompGridDesc_t gd, const std::array<int32_t, 2>& pdims) {
+  releaseFusedCache(gd); // plans depend on the process grid
   gd->config.pdims[0] = pdims[0];
   gd->config.pdims[1] = pdims[1];
   GridGeom& g = gd->geom;
@@ -39,10 +56,16 @@ void checkDeviceError(cudecompGridDesc_t gd) {
   if (!arena.valid()) return;
   const uint32_t e = arena.errorWordHost();
   if (e == 0) return;
+  // launches that gave up left without their bookkeeping: drain the device and zero this rank's counters
+  cudaDeviceSynchronize();
+  if (gd->pad_slot >= 0)
+    cudaMemset(arena.mine(gd->pad_slot) + kPadCounter, 0, 8 * sizeof(uint64_t)),
+        cudaMemset(arena.mine(gd->pad_slot) + kPadPhaseCounter, 0, kMaxPhases * sizeof(uint64_t));
+  (void)cudaGetLastError();
   arena.clearError();
   if (e == 3) THROW_INTERNAL_ERROR("a TMA bulk copy of an earlier operation did not complete within 20 s");
   THROW_INTERNAL_ERROR(std::string("a device-side wait for a peer rank timed out during an earlier operation (") +
-                       (e == 1 ? "entry" : "exit") +
+                       (e == 1 ? "entry" : (e == 2 ? "exit" : "chunk")) +
                        " handshake); a rank of the communicator did not enter the same operation");
 }
 
@@ -195,6 +218,108 @@ bool runPipelinedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int d
   return true;
 }
 
+
+// Fused staged schedule: ONE phased launch (kernels.h PhasedParams) pushes chunk s into the peers' workspaces while it
+// unpacks chunk s - lag from mine, with per-chunk flags instead of per-chunk launches. Replaces the pack / a2a / unpack
+// pipeline of reference include/internal/comm_routines.h:427-631 (cudecompAlltoallPipelined) for in-place and other
+// staged calls. Returns false when the schedule does not apply (boxes that are not row copies: differing memory
+// orders); the caller then runs separate launches. Every member takes the same decision: it depends on the geometry,
+// the layouts and K only... and on buffer alignment, which can only lower the vector width, never the shape.
+bool runFusedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, void* input, void* output, void* work, int es,
+                    const int32_t in_halo[], const int32_t out_halo[], const int32_t in_pad[], const int32_t out_pad[],
+                    bool inplace, const std::vector<CallMsg>& msgs, const TransposePlan& probe, const SyncParams& sync,
+                    PerfSample* perf, cudaStream_t stream) {
+  const int P = probe.comm_size;
+  // Rank-independent decisions only (every member must run the same number of phases): equal memory orders make every
+  // box a row copy whatever its extents; the chunk count comes from the average pencil size.
+  for (int k = 0; k < 3; ++k)
+    if (gd->geom.order[probe.axes.a][k] != gd->geom.order[probe.axes.b][k]) return false;
+  int K = gd->pipeline_chunks;
+  if (K <= 0)
+    K = autoFusedChunks(static_cast<int64_t>(gd->geom.gdims[0]) * gd->geom.gdims[1] * gd->geom.gdims[2] /
+                        std::max(1, gd->handle->nranks) * es);
+  const int lag = std::max(1, gd->fused_lag);
+  K = std::min(K, kMaxPhases - lag);
+
+  // resolve the peers' workspaces first: they are part of the cache key (a peer may have re-allocated)
+  std::vector<char*> peer_work(P, nullptr);
+  for (int i = 0; i < P; ++i)
+    peer_work[i] = (i == probe.me) ? static_cast<char*>(work)
+                                   : static_cast<char*>(h->peers.resolve(probe.group_world[i], msgs[i].work));
+
+  std::string key;
+  auto put = [&](const void* p, size_t n) { key.append(static_cast<const char*>(p), n); };
+  const int32_t zero3[3] = {0, 0, 0};
+  const int32_t head[8] = {ax, dir, es, K, lag, gd->tile_bytes, inplace ? 1 : 0, P};
+  put(head, sizeof(head));
+  put(&input, sizeof(input));
+  put(&output, sizeof(output));
+  put(in_halo ? in_halo : zero3, 12);
+  put(out_halo ? out_halo : zero3, 12);
+  put(in_pad ? in_pad : zero3, 12);
+  put(out_pad ? out_pad : zero3, 12);
+  put(peer_work.data(), peer_work.size() * sizeof(char*));
+
+  static uint64_t tick = 0;
+  FusedPlanEntry* entry = nullptr;
+  for (auto& e : gd->fused_cache)
+    if (e.key == key) entry = &e;
+  if (!entry) {
+    PipelinedPlan pp;
+    if (K > 1) pp = buildPipelinedTransposePlan(gd->geom, gd->pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, inplace, K, false);
+    std::vector<std::vector<ResolvedBox>> push, unpack;
+    if (K > 1 && !pp.steps.empty()) {
+      push.resize(pp.steps.size());
+      unpack.resize(pp.steps.size());
+      for (size_t s = 0; s < pp.steps.size(); ++s) {
+        for (auto& b : pp.steps[s].push) push[s].push_back({b, static_cast<const char*>(input), peer_work[b.peer]});
+        for (auto& b : pp.steps[s].unpack) unpack[s].push_back({b, static_cast<const char*>(work), static_cast<char*>(output)});
+      }
+    } else {
+      TransposePlan st = buildTransposePlan(gd->geom, gd->pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, DstKind::STAGE, inplace);
+      push.resize(1);
+      unpack.resize(1);
+      for (auto& b : st.push) push[0].push_back({b, static_cast<const char*>(input), peer_work[b.peer]});
+      for (auto& b : st.unpack) unpack[0].push_back({b, static_cast<const char*>(work), static_cast<char*>(output)});
+    }
+    LaunchTuning tuning;
+    tuning.tile_bytes = gd->tile_bytes;
+    PhasedLaunch pl;
+    if (!preparePhased(push, unpack, es, tuning, lag, &pl))
+      THROW_INTERNAL_ERROR("staged schedule with equal memory orders is not a row copy");
+
+    if (gd->fused_cache.size() >= 64) releaseFusedCache(gd);
+    FusedPlanEntry e;
+    e.key = key;
+    const size_t box_bytes = pl.boxes.size() * sizeof(KBox);
+    e.bytes = box_bytes + pl.phases.size() * sizeof(PhaseDesc);
+    CHECK_CUDA(cudaMalloc(&e.dev, std::max<size_t>(e.bytes, 256)));
+    CHECK_CUDA(cudaHostAlloc(&e.host, std::max<size_t>(e.bytes, 256), cudaHostAllocDefault));
+    std::memcpy(e.host, pl.boxes.data(), box_bytes);
+    std::memcpy(static_cast<char*>(e.host) + box_bytes, pl.phases.data(), pl.phases.size() * sizeof(PhaseDesc));
+    CHECK_CUDA(cudaMemcpyAsync(e.dev, e.host, e.bytes, cudaMemcpyHostToDevice, stream));
+    std::memset(&e.params, 0, sizeof(e.params));
+    e.params.boxes = static_cast<const KBox*>(e.dev);
+    e.params.phases = reinterpret_cast<const PhaseDesc*>(static_cast<char*>(e.dev) + box_bytes);
+    e.params.nphases = static_cast<uint32_t>(pl.phases.size());
+    e.params.npush_phases = pl.npush_phases;
+    e.params.elem_size = static_cast<uint32_t>(es);
+    e.params.vec_size = static_cast<uint32_t>(pl.vec_size);
+    e.total_slots = pl.total_slots;
+    gd->fused_cache.push_back(e);
+    entry = &gd->fused_cache.back();
+  }
+  entry->last_use = ++tick;
+  PhasedParams params = entry->params;
+  params.sync = sync;
+  LaunchConfig cfg;
+  cfg.grid = gd->grid_ctas;
+  cudaError_t err = launchPhased(params, entry->total_slots, cfg, stream);
+  if (err != cudaSuccess) THROW_CUDA_ERROR(std::string("kernel launch failed: ") + cudaGetErrorString(err));
+  PerfReport::markExchangeDone(perf, stream);
+  return true;
+}
+
 } // namespace
 
 void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, void* input, void* output, void* work,
@@ -325,6 +450,9 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
     launchBoxes(gd, unpack, es, nosync, stream);
   } else {
     gd->last_path = CUDECOMP_B200_PATH_STAGED;
+    if (gd->staged_mode == 0 && runFusedStaged(h, gd, ax, dir, input, output, work, es, in_halo, out_halo, in_pad, out_pad,
+                                               inplace, msgs, probe, sync, perf.sample, stream))
+      return;
     if (gd->pipeline_chunks > 1 &&
         runPipelinedStaged(h, gd, ax, dir, input, output, work, es, in_halo, out_halo, in_pad, out_pad, inplace, msgs,
                            peers, perf.sample, stream, false))

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <memory>
 #include <set>
+#include <string>
 #include <vector>
 
 #include "bootstrap.h"
@@ -24,6 +25,20 @@ enum {
   CUDECOMP_B200_PATH_DIRECT = 2, // peer stores straight into the destination buffers, one kernel
   CUDECOMP_B200_PATH_STAGED = 3  // peer stores into the peers' workspace + local unpack kernel
 };
+
+namespace cdb {
+// One cached phased launch: tables resident in device memory, uploaded once from a pinned host copy that stays alive
+// with the entry (so the upload is a plain asynchronous copy and the steady state does no host work but the lookup).
+struct FusedPlanEntry {
+  std::string key;
+  void* dev = nullptr;     // [KBox boxes...][PhaseDesc phases...]
+  void* host = nullptr;    // pinned copy
+  size_t bytes = 0;
+  PhasedParams params{};   // sync block filled per call
+  uint64_t total_slots = 0;
+  uint64_t last_use = 0;
+};
+} // namespace cdb
 
 struct cudecompHandle {
   bool initialized = false;
@@ -50,6 +65,8 @@ struct cudecompHandle {
   int peer_order = 0;            // CUDECOMP_B200_PEER_ORDER=pairwise -> 1
   int balance_grid = 0;          // CUDECOMP_B200_BALANCE_GRID=1
   int pull_mode = 0;             // CUDECOMP_B200_TRANSFER=pull
+  int staged_mode = 0;           // CUDECOMP_B200_STAGED=launches -> 1 (separate push / unpack launches)
+  int fused_lag = 2;             // CUDECOMP_B200_FUSED_LAG
   uint64_t release_count = 0;    // buffers freed through cudecompFree so far
   uint64_t released[cdb::kReleaseSlots] = {0}; // ids of the most recent ones, newest first
 };
@@ -80,9 +97,20 @@ struct cudecompGridDesc {
   int pull_mode = 0;      // 1: direct transposes are receiver-driven (each rank LOADS its blocks from the peers' inputs)
   cudaStream_t side_stream = nullptr;
   std::vector<cudaEvent_t> side_events;
+  // Staged transposes (in place, forced staging, unmappable outputs): 0 = ONE phased launch that pushes chunk s while it
+  // unpacks chunk s - lag (kernels.h PhasedParams; the default), 1 = separate launches (push, unpack; chunked: K pushes
+  // on the caller's stream, unpacks on a side stream).
+  int staged_mode = 0;
+  int fused_lag = 2;
+  std::vector<cdb::FusedPlanEntry> fused_cache; // device tables of phased launches, keyed by everything they depend on
 };
 
 namespace cdb {
+
+// chunks of the fused staged schedule when pipeline_chunks == 0 (auto): about 8 MiB of pencil per chunk, 1..16
+int autoFusedChunks(int64_t pencil_bytes);
+
+void releaseFusedCache(cudecompGridDesc_t gd);
 
 void setGeometry(cudecompGridDesc_t gd, const std::array<int32_t, 2>& pdims);
 

@@ -35,39 +35,53 @@ __device__ __forceinline__ void stReleaseSys(uint64_t* p, uint64_t v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Monotonic publish: a later step's flag may overtake an earlier one on its way to the peer (they are written by
+// different CTAs), so the slot takes the maximum instead of the last value.
+__device__ __forceinline__ void redMaxReleaseSys(uint64_t* p, uint64_t v) {
+  asm volatile("red.release.sys.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 __device__ __forceinline__ uint64_t globalTimerNs() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 
-// Spin until *flag >= epoch. Gives up after timeout_ns and records the failure for the host: a peer that
-// never arrives (crashed rank, mismatched call sequence) must not wedge the GPU.
-__device__ __noinline__ void waitFlag(const uint64_t* flag, const SyncParams& s, uint32_t code) {
-  if (ldAcquireSys(flag) >= s.epoch) return;
+// Spin until *flag >= want. Gives up after timeout_ns and records the failure for the host: a peer that
+// never arrives (crashed rank, mismatched call sequence) must not wedge the GPU. Returns false on timeout; callers
+// then skip their data movement (the buffers of a peer that never confirmed must not be touched).
+__device__ __noinline__ bool waitFlagValue(const uint64_t* flag, uint64_t want, const SyncParams& s, uint32_t code) {
+  if (ldAcquireSys(flag) >= want) return true;
   const uint64_t t0 = globalTimerNs();
   uint32_t spins = 0;
-  while (ldAcquireSys(flag) < s.epoch) {
+  while (ldAcquireSys(flag) < want) {
     ++spins;
     if (spins > 32) __nanosleep(spins > 4096 ? 1000 : 50);
-    if ((spins & 255u) == 0 && globalTimerNs() - t0 > s.timeout_ns) {
+    if ((spins & 255u) == 0 && s.timeout_ns != 0 && globalTimerNs() - t0 > s.timeout_ns) {
       if (s.error_word) {
         *reinterpret_cast<volatile uint32_t*>(s.error_word) = code;
         __threadfence_system();
       }
-      return;
+      return false;
     }
   }
+  return true;
 }
 
-__device__ __forceinline__ void syncEntry(const SyncParams& s) {
-  if (s.my_pad == nullptr || s.npeers == 0 || !s.do_entry) return;
+__device__ __forceinline__ bool waitFlag(const uint64_t* flag, const SyncParams& s, uint32_t code) {
+  return waitFlagValue(flag, s.epoch, s, code);
+}
+
+// Returns false (for the whole CTA) when a peer did not arrive in time.
+__device__ __forceinline__ bool syncEntry(const SyncParams& s) {
+  if (s.my_pad == nullptr || s.npeers == 0 || !s.do_entry) return true;
   const int t = threadIdx.x;
+  int failed = 0;
   if (t < s.npeers) {
     if (blockIdx.x == 0) stReleaseSys(s.peer_pad[t] + kPadEntry + s.my_world, s.epoch);
-    waitFlag(s.my_pad + kPadEntry + s.peer_world[t], s, 1u);
+    failed = waitFlag(s.my_pad + kPadEntry + s.peer_world[t], s, 1u) ? 0 : 1;
   }
-  __syncthreads();
+  return __syncthreads_or(failed) == 0;
 }
 
 __device__ __forceinline__ void syncExit(const SyncParams& s) {
@@ -117,81 +131,149 @@ template <> __device__ __forceinline__ void storeStream<Vec32>(Vec32* p, const V
 // A tile is rows_per_tile rows x seg_vecs vectors (about 32 KiB); inside a tile each warp takes
 // 128-vector pieces (4 independent loads per lane in flight, then 4 stores).
 // ---------------------------------------------------------------------------------------------
-// kOrder: slot order (CopyParams::peer_order), a template parameter so that the default order keeps its register budget.
-template <typename V, int kOrder> __global__ void __launch_bounds__(256) rowCopyKernel(const __grid_constant__ CopyParams p) {
-  syncEntry(p.sync);
-
+// One tile of a ROWCOPY box, executed by the whole CTA.
+template <typename V> __device__ __forceinline__ void copyRowTile(const KBox& bx, uint32_t j, int64_t esz) {
+  constexpr uint32_t kUnroll = 4;
+  constexpr uint32_t kPiece = 32 * kUnroll;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t nwarps = blockDim.x >> 5;
-  const uint32_t total = p.nboxes * p.max_tiles;
-  constexpr uint32_t kUnroll = 4;
-  constexpr uint32_t kPiece = 32 * kUnroll;
+  const RowTile rt = decodeRowTile(bx, j);
+  const int64_t row0 = rt.row0;
+  const uint32_t c0 = rt.c0;
+  const uint32_t nvec = rt.nvec;
+  const uint32_t rows_here = rt.rows_here;
+  const uint32_t pieces_per_row = (nvec + kPiece - 1) / kPiece;
+  const uint32_t npieces = rows_here * pieces_per_row;
+
+  if (bx.row_vecs <= 32u) {
+    // Short rows (e.g. the 2-element faces of a halo along the contiguous axis): a warp per row would leave most
+    // lanes idle, so lanes take (row, vector) pairs of the tile instead.
+    const uint32_t total_vecs = rows_here * nvec;
+    for (uint32_t e0 = threadIdx.x; e0 < total_vecs; e0 += blockDim.x * kUnroll) {
+      V v[kUnroll];
+      V* dptr[kUnroll];
+#pragma unroll
+      for (uint32_t k = 0; k < kUnroll; ++k) {
+        const uint32_t e = e0 + k * blockDim.x;
+        dptr[k] = nullptr;
+        if (e < total_vecs) {
+          const uint32_t r = e / nvec;
+          const uint32_t c = e - r * nvec;
+          int64_t so, dof;
+          rowOffsets(bx, row0 + r, esz, so, dof);
+          v[k] = loadStream(reinterpret_cast<const V*>(bx.src + so) + c0 + c);
+          dptr[k] = reinterpret_cast<V*>(bx.dst + dof) + c0 + c;
+        }
+      }
+#pragma unroll
+      for (uint32_t k = 0; k < kUnroll; ++k)
+        if (dptr[k]) storeStream(dptr[k], v[k]);
+    }
+    return;
+  }
+
+  for (uint32_t pc = warp; pc < npieces; pc += nwarps) {
+    const uint32_t r = pc / pieces_per_row;
+    const uint32_t q = pc - r * pieces_per_row;
+    int64_t so, dof;
+    rowOffsets(bx, row0 + r, esz, so, dof);
+    const V* s = reinterpret_cast<const V*>(bx.src + so) + c0;
+    V* d = reinterpret_cast<V*>(bx.dst + dof) + c0;
+    const uint32_t base = q * kPiece + lane;
+    V v[kUnroll];
+#pragma unroll
+    for (uint32_t k = 0; k < kUnroll; ++k) {
+      const uint32_t idx = base + 32u * k;
+      if (idx < nvec) v[k] = loadStream(s + idx);
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < kUnroll; ++k) {
+      const uint32_t idx = base + 32u * k;
+      if (idx < nvec) storeStream(d + idx, v[k]);
+    }
+  }
+}
+
+// kOrder: slot order (CopyParams::peer_order), a template parameter so that the default order keeps its register budget.
+template <typename V, int kOrder> __global__ void __launch_bounds__(256) rowCopyKernel(const __grid_constant__ CopyParams p) {
+  const bool go = syncEntry(p.sync);
+  const uint32_t total = go ? p.nboxes * p.max_tiles : 0u; // a peer that never arrived: move nothing, leave through the exit
 
   for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
     uint32_t b, j;
     slotToBoxTile(t, p.nboxes, p.max_tiles, static_cast<uint32_t>(kOrder), b, j);
     const KBox& bx = p.box[b];
     if (j >= bx.tiles) continue;
-    const RowTile rt = decodeRowTile(bx, j);
-    const int64_t row0 = rt.row0;
-    const uint32_t c0 = rt.c0;
-    const uint32_t nvec = rt.nvec;
-    const uint32_t rows_here = rt.rows_here;
-    const uint32_t pieces_per_row = (nvec + kPiece - 1) / kPiece;
-    const uint32_t npieces = rows_here * pieces_per_row;
-    const int64_t esz = p.elem_size;
+    copyRowTile<V>(bx, j, p.elem_size);
+  }
 
-    if (bx.row_vecs <= 32u) {
-      // Short rows (e.g. the 2-element faces of a halo along the contiguous axis): a warp per row would leave most
-      // lanes idle, so lanes take (row, vector) pairs of the tile instead.
-      const uint32_t total_vecs = rows_here * nvec;
-      for (uint32_t e0 = threadIdx.x; e0 < total_vecs; e0 += blockDim.x * kUnroll) {
-        V v[kUnroll];
-        V* dptr[kUnroll];
-#pragma unroll
-        for (uint32_t k = 0; k < kUnroll; ++k) {
-          const uint32_t e = e0 + k * blockDim.x;
-          dptr[k] = nullptr;
-          if (e < total_vecs) {
-            const uint32_t r = e / nvec;
-            const uint32_t c = e - r * nvec;
-            int64_t so, dof;
-            rowOffsets(bx, row0 + r, esz, so, dof);
-            v[k] = loadStream(reinterpret_cast<const V*>(bx.src + so) + c0 + c);
-            dptr[k] = reinterpret_cast<V*>(bx.dst + dof) + c0 + c;
-          }
+  if (go) syncExit(p.sync);
+}
+
+// ---------------------------------------------------------------------------------------------
+// PHASED ROWCOPY: the fused staged / in-place schedule in one launch (kernels.h PhasedParams).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t stepKey(uint64_t epoch, uint32_t step) { return (epoch << 8) | (step + 1u); }
+
+template <typename V> __global__ void __launch_bounds__(256) rowCopyPhasedKernel(const __grid_constant__ PhasedParams p) {
+  __shared__ uint32_t sh_last;
+  const SyncParams& sy = p.sync;
+  if (!syncEntry(sy)) return;
+  unsigned long long* counters = reinterpret_cast<unsigned long long*>(sy.my_pad + kPadPhaseCounter);
+  int32_t known = -1; // highest step known to be exchanged by everybody (uniform over the CTA)
+
+  for (uint32_t s = 0; s < p.nphases; ++s) {
+    const PhaseDesc ph = p.phases[s];
+    const uint32_t total = ph.nboxes * ph.max_tiles;
+    for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+      const uint32_t b = t % ph.nboxes;
+      const uint32_t j = t / ph.nboxes;
+      const KBox& bx = p.boxes[ph.first_box + b];
+      if (j >= bx.tiles) continue;
+      const int32_t need = static_cast<int32_t>(bx.pad_) - 1;
+      if (need > known) {
+        // every peer's pushes of step `need` have landed here, and every local CTA has finished reading that chunk
+        int failed = 0;
+        const int tid = threadIdx.x;
+        if (tid < sy.npeers) {
+          failed = waitFlagValue(sy.my_pad + kPadStep + sy.peer_world[tid], stepKey(sy.epoch, need), sy, 4u) ? 0 : 1;
+        } else if (tid == sy.npeers) {
+          failed = waitFlagValue(reinterpret_cast<const uint64_t*>(counters + need), gridDim.x, sy, 5u) ? 0 : 1;
         }
-#pragma unroll
-        for (uint32_t k = 0; k < kUnroll; ++k)
-          if (dptr[k]) storeStream(dptr[k], v[k]);
+        if (__syncthreads_or(failed)) return;
+        known = need;
       }
-      continue;
+      copyRowTile<V>(bx, j, p.elem_size);
     }
-
-    for (uint32_t pc = warp; pc < npieces; pc += nwarps) {
-      const uint32_t r = pc / pieces_per_row;
-      const uint32_t q = pc - r * pieces_per_row;
-      int64_t so, dof;
-      rowOffsets(bx, row0 + r, esz, so, dof);
-      const V* s = reinterpret_cast<const V*>(bx.src + so) + c0;
-      V* d = reinterpret_cast<V*>(bx.dst + dof) + c0;
-      const uint32_t base = q * kPiece + lane;
-      V v[kUnroll];
-#pragma unroll
-      for (uint32_t k = 0; k < kUnroll; ++k) {
-        const uint32_t idx = base + 32u * k;
-        if (idx < nvec) v[k] = loadStream(s + idx);
+    if (s < p.npush_phases) {
+      // my share of this phase is done: fence it, count it; the last CTA tells the peers that chunk s has landed
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long old = atomicAdd(counters + s, 1ull);
+        sh_last = (old == static_cast<unsigned long long>(gridDim.x) - 1ull) ? 1u : 0u;
       }
-#pragma unroll
-      for (uint32_t k = 0; k < kUnroll; ++k) {
-        const uint32_t idx = base + 32u * k;
-        if (idx < nvec) storeStream(d + idx, v[k]);
+      __syncthreads();
+      if (sh_last) {
+        __threadfence_system();
+        if (static_cast<int>(threadIdx.x) < sy.npeers)
+          redMaxReleaseSys(sy.peer_pad[threadIdx.x] + kPadStep + sy.my_world, stepKey(sy.epoch, s));
       }
     }
   }
 
-  syncExit(p.sync);
+  // leave the phase counters zeroed for the next phased launch: the last CTA out resets them
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* ctr = reinterpret_cast<unsigned long long*>(sy.my_pad + kPadCounter);
+    const unsigned long long old = atomicAdd(ctr, 1ull);
+    if (old == static_cast<unsigned long long>(gridDim.x) - 1ull) {
+      for (uint32_t s = 0; s < p.npush_phases; ++s) counters[s] = 0ull;
+      *reinterpret_cast<volatile unsigned long long*>(ctr) = 0ull;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,11 +283,11 @@ template <typename V, int kOrder> __global__ void __launch_bounds__(256) rowCopy
 // ---------------------------------------------------------------------------------------------
 template <typename T, int kOrder> __global__ void __launch_bounds__(256) transposeKernel(const __grid_constant__ CopyParams p) {
   __shared__ T tile[32][33];
-  syncEntry(p.sync);
+  const bool go = syncEntry(p.sync);
 
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t wrow = threadIdx.x >> 5; // 0..7
-  const uint32_t total = p.nboxes * p.max_tiles;
+  const uint32_t total = go ? p.nboxes * p.max_tiles : 0u;
 
   for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
     uint32_t b, j;
@@ -239,7 +321,7 @@ template <typename T, int kOrder> __global__ void __launch_bounds__(256) transpo
     }
   }
 
-  syncExit(p.sync);
+  if (go) syncExit(p.sync);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -283,7 +365,7 @@ __global__ void __launch_bounds__(32) rowCopyBulkKernel(const __grid_constant__ 
   // dynamically indexed local array)
   __shared__ char* dst_of[kBulkStages];
   __shared__ uint32_t bytes_of[kBulkStages];
-  syncEntry(p.sync);
+  if (!syncEntry(p.sync)) return;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kBulkStages; ++s) bulk::mbarInit(&full[s], 1);
@@ -448,6 +530,27 @@ cudaError_t launchCopy(KernelKind kind, const CopyParams& p, const LaunchConfig&
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int dflt = (kind == KernelKind::ROWCOPY) ? (5 * sms) / 2 : 4 * sms;
   const int grid = chooseGrid(cfg.grid, dflt, resident, total, cfg.balance);
+  fn<<<grid, cfg.threads, 0, stream>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+cudaError_t launchPhased(const PhasedParams& p, uint64_t total_slots, const LaunchConfig& cfg, cudaStream_t stream) {
+  using Fn = void (*)(const PhasedParams);
+  Fn fn = nullptr;
+  switch (p.vec_size) {
+  case 16: fn = rowCopyPhasedKernel<uint4>; break;
+  case 8: fn = rowCopyPhasedKernel<uint2>; break;
+  case 4: fn = rowCopyPhasedKernel<uint32_t>; break;
+  }
+  if (!fn) return cudaErrorInvalidValue;
+  int sms = 0, dev = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, cfg.threads, 0) != cudaSuccess || per_sm <= 0)
+    return cudaErrorInvalidDevice;
+  // CTAs wait for each other inside the launch: every one of them must be resident
+  const int grid = chooseGrid(cfg.grid, (5 * sms) / 2, per_sm * sms, total_slots, 0);
   fn<<<grid, cfg.threads, 0, stream>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();

@@ -23,7 +23,10 @@ constexpr int kPadMaxRanks = 128;
 constexpr int kPadEntry = 0;                    // [r]: rank r has reached operation `epoch` in its stream
 constexpr int kPadExit = kPadMaxRanks;          // [r]: all of rank r's stores for operation `epoch` have landed here
 constexpr int kPadCounter = 2 * kPadMaxRanks;   // local: CTAs finished in the running launch
-constexpr int kPadWords = 2 * kPadMaxRanks + 8; // uint64 words
+constexpr int kPadStep = 2 * kPadMaxRanks + 8;  // [r]: phased launches, rank r's pushes of (epoch, step) have landed here
+constexpr int kPadPhaseCounter = 3 * kPadMaxRanks + 8; // local: per phase of a phased launch, CTAs that finished it
+constexpr int kMaxPhases = 64;                  // phases of one phased launch (chunks + lag)
+constexpr int kPadWords = 3 * kPadMaxRanks + 8 + kMaxPhases; // uint64 words (must fit the 4 KiB slot)
 
 struct KBox {
   const char* src;
@@ -68,6 +71,31 @@ struct CopyParams {
   uint32_t pad_[3];
 };
 
+// Phased launch (the fused in-place / staged schedule, see engine.cc runFusedStaged): ONE persistent launch walks
+// `nphases` phases in order. Phase s holds the push boxes of chunk s (stores into the peers' workspaces) and the unpack
+// boxes that may run once chunk `wait_step` has been exchanged by EVERY member (workspace -> my pencil). Slots of a
+// phase interleave its boxes, so link-bound pushes and HBM-bound unpacks are in flight together on every SM.
+// After its share of a phase a CTA fences and bumps the phase counter; the last one publishes (epoch, s) to the peers'
+// kPadStep slot. A CTA that reaches a box with wait_step >= 0 first waits until every peer has published that step
+// and every local CTA has finished it (all local reads of that chunk are done, all remote data of it has landed).
+// The tables live in device memory (too many boxes for the parameter space).
+struct PhaseDesc {
+  uint32_t first_box;
+  uint32_t nboxes;
+  uint32_t max_tiles;
+  uint32_t pad_;
+};
+
+struct PhasedParams {
+  const KBox* boxes;       // device table; KBox::pad_ holds wait_step + 1 (0: no dependency)
+  const PhaseDesc* phases; // device table
+  SyncParams sync;         // do_exit is ignored: the last phase's waits subsume the exit handshake
+  uint32_t nphases;
+  uint32_t npush_phases;   // phases [0, npush_phases) contain pushes and are published to the peers
+  uint32_t elem_size;
+  uint32_t vec_size;
+};
+
 // ROWCOPY_BULK: the row copy driven by the TMA unit instead of LDG/STG: one elected thread per CTA moves row segments
 // global -> shared -> global with cp.async.bulk and an mbarrier ring. Same boxes and tiling fields as ROWCOPY, but a
 // tile is ONE row segment of at most kBulkChunkBytes (rows_per_tile = 1) and everything must be 16-byte aligned.
@@ -91,6 +119,10 @@ cudaError_t launchCopy(KernelKind kind, const CopyParams& p, const LaunchConfig&
 
 // Upper bound on co-resident CTAs of the given kernel on the current device.
 int maxResidentCtas(KernelKind kind, int vec_or_elem_size, int threads, uint32_t peer_order = 0);
+
+// Enqueues a phased row-copy launch (all boxes ROWCOPY-shaped, vector width p.vec_size). `total_slots`: sum over the
+// phases of nboxes * max_tiles (sizes the grid).
+cudaError_t launchPhased(const PhasedParams& p, uint64_t total_slots, const LaunchConfig& cfg, cudaStream_t stream);
 
 // counts launches issued through launchCopy (bench.py reports it as gpu_launches)
 uint64_t launchCount();

@@ -133,6 +133,73 @@ std::vector<PreparedLaunch> prepareLaunches(const std::vector<LaunchBox>& boxes,
   return out;
 }
 
+bool preparePhased(const std::vector<std::vector<LaunchBox>>& push, const std::vector<std::vector<LaunchBox>>& unpack, int es,
+                   const LaunchTuning& tuning, int lag, PhasedLaunch* out) {
+  const size_t K = push.size();
+  if (K == 0 || unpack.size() != K || lag < 1 || K + static_cast<size_t>(lag) > static_cast<size_t>(kMaxPhases)) return false;
+  uint32_t tile_bytes = static_cast<uint32_t>(tuning.tile_bytes > 0 ? tuning.tile_bytes : kDefaultTileBytes);
+  tile_bytes = std::min<uint32_t>(std::max<uint32_t>(tile_bytes, kMinTileBytes), kMaxTileBytes);
+
+  struct Item {
+    CanonBox c;
+    const LaunchBox* b;
+    int wait; // step that must be complete, -1: none
+  };
+  std::vector<std::vector<Item>> phase(K + lag);
+  uint64_t a = 16;
+  auto add = [&](const LaunchBox& b, size_t ph, int wait) -> bool {
+    if (b.d.count() == 0) return true;
+    CanonBox c = canonicalize(b.d, true);
+    if (c.rowCopy() && c.n[0] * es / std::min(es, 16) >= (1ll << 31)) c = canonicalize(b.d, false);
+    if (!c.rowCopy()) return false;
+    const uint64_t sa = reinterpret_cast<uint64_t>(b.src_base) + static_cast<uint64_t>(b.d.src_off) * es;
+    const uint64_t da = reinterpret_cast<uint64_t>(b.dst_base) + static_cast<uint64_t>(b.d.dst_off) * es;
+    a = std::min({a, lowBit(sa), lowBit(da), lowBit(static_cast<uint64_t>(c.n[0]) * es)});
+    for (int k = 1; k < 3; ++k)
+      if (c.n[k] > 1) a = std::min({a, lowBit(static_cast<uint64_t>(c.ss[k]) * es), lowBit(static_cast<uint64_t>(c.ds[k]) * es)});
+    phase[ph].push_back({c, &b, wait});
+    return true;
+  };
+  for (size_t s = 0; s < K; ++s) {
+    for (auto& b : push[s])
+      if (!add(b, s, -1)) return false;
+    for (auto& b : unpack[s])
+      if (!add(b, s + lag, static_cast<int>(s))) return false;
+  }
+  if (a < 4) THROW_INVALID_USAGE("buffers must be aligned to the element size");
+  const int V = static_cast<int>(a);
+
+  out->boxes.clear();
+  out->phases.clear();
+  out->npush_phases = static_cast<uint32_t>(K);
+  out->vec_size = V;
+  out->total_slots = 0;
+  for (auto& items : phase) {
+    PhaseDesc pd{};
+    pd.first_box = static_cast<uint32_t>(out->boxes.size());
+    pd.nboxes = static_cast<uint32_t>(items.size());
+    for (auto& it : items) {
+      KBox kb;
+      std::memset(&kb, 0, sizeof(kb));
+      kb.src = it.b->src_base + it.b->d.src_off * es;
+      kb.dst = it.b->dst_base + it.b->d.dst_off * es;
+      for (int k = 0; k < 3; ++k) {
+        kb.n[k] = it.c.n[k];
+        kb.ss[k] = it.c.ss[k];
+        kb.ds[k] = it.c.ds[k];
+      }
+      fillRowCopy(kb, it.c, es, V, tile_bytes, false);
+      kb.pad_ = static_cast<uint32_t>(it.wait + 1);
+      pd.max_tiles = std::max(pd.max_tiles, kb.tiles);
+      out->boxes.push_back(kb);
+    }
+    if (static_cast<uint64_t>(pd.nboxes) * pd.max_tiles > 0xffffffffull) THROW_NOT_SUPPORTED("launch too large");
+    out->total_slots += static_cast<uint64_t>(pd.nboxes) * pd.max_tiles;
+    out->phases.push_back(pd);
+  }
+  return true;
+}
+
 int chooseGrid(int requested, int dflt, int resident, uint64_t total_slots, int balance) {
   int grid = requested > 0 ? requested : dflt;
   if (grid > resident) grid = resident;

@@ -41,6 +41,22 @@ struct PreparedLaunch {
 std::vector<PreparedLaunch> prepareLaunches(const std::vector<LaunchBox>& boxes, int es, const LaunchTuning& tuning, int me,
                                             int comm_size);
 
+// Tables of a phased launch (kernels.h PhasedParams), host copies.
+struct PhasedLaunch {
+  std::vector<KBox> boxes;
+  std::vector<PhaseDesc> phases;
+  uint32_t npush_phases = 0;
+  int vec_size = 16;
+  uint64_t total_slots = 0;
+};
+
+// push[s] / unpack[s]: the boxes of step s of a chunked staged schedule (plan.h PipelinedPlan), resolved to base
+// pointers. Phase s of the launch holds push[s] and unpack[s - lag] (which waits for step s - lag), lag >= 1; there are
+// push.size() + lag phases. Returns false when the schedule cannot run as one phased launch (a box that is not a row
+// copy, too many phases); the caller then falls back to separate launches.
+bool preparePhased(const std::vector<std::vector<LaunchBox>>& push, const std::vector<std::vector<LaunchBox>>& unpack, int es,
+                   const LaunchTuning& tuning, int lag, PhasedLaunch* out);
+
 } // namespace cdb
 
 #endif

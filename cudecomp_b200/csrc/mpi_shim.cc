@@ -190,8 +190,16 @@ int MPI_Comm_split(MPI_Comm comm, int color, int key, MPI_Comm* newcomm) {
 }
 
 int MPI_Comm_split_type(MPI_Comm comm, int, int key, MPI_Info, MPI_Comm* newcomm) {
-  // Single node: every rank shares memory, so SHARED == a copy of comm ordered by key.
-  return MPI_Comm_split(comm, 0, key, newcomm);
+  // Single node: every rank shares memory, so SHARED == a copy of comm ordered by key. Applications commonly pick their
+  // GPU as cudaSetDevice(rank in the SHARED communicator); CUDECOMP_B200_SHIM_RANKS_PER_NODE=n makes the shim report
+  // "nodes" of n consecutive ranks, the way a launcher placing n ranks per node would, so that more ranks than GPUs can
+  // share the devices of one box.
+  int per_node = 0;
+  if (const char* v = std::getenv("CUDECOMP_B200_SHIM_RANKS_PER_NODE")) per_node = std::atoi(v);
+  if (per_node <= 0) return MPI_Comm_split(comm, 0, key, newcomm);
+  int rank = 0;
+  if (MPI_Comm_rank(comm, &rank) != MPI_SUCCESS) return MPI_ERR_OTHER;
+  return MPI_Comm_split(comm, rank / per_node, key, newcomm);
 }
 
 int MPI_Comm_dup(MPI_Comm comm, MPI_Comm* newcomm) {

@@ -118,6 +118,8 @@ def transpose_case(gpu, handle, rank, case):
             cd.check(cd.set_pipeline_chunks(handle, gd, case["pipeline_chunks"]))
         if case.get("kernel_variant"):
             cd.check(cd.set_kernel_variant(handle, gd, case["kernel_variant"]))
+        if case.get("staged_mode") is not None or case.get("fused_lag"):
+            cd.check(cd.set_staged_mode(handle, gd, case.get("staged_mode") or 0, case.get("fused_lag") or 0))
         if case.get("pull"):
             cd.check(cd.set_transfer_mode(handle, gd, 1))
         if case.get("tile_bytes") or case.get("peer_order") or case.get("balance_grid"):
@@ -205,6 +207,63 @@ def transpose_case(gpu, handle, rank, case):
                     # the reference's legacy chain swaps the buffers (tests/cc/transpose_test.cc:523-545)
                     d_in, d_out = d_out, d_in
                     cur, other = other, cur
+    finally:
+        if work_ptr:
+            cd.cudecompFree(handle, gd, work_ptr)
+        cd.cudecompGridDescDestroy(handle, gd)
+    return out
+
+
+def stress_case(gpu, handle, rank, case):
+    """`reps` X->Y->Z->Y->X round trips enqueued back to back with NO host synchronisation in between (what a solver's
+    time loop does): consecutive operations overlap on the device as far as their handshakes allow, so a missing
+    dependency between them shows up here and not in the per-operation cases. The final pencil must equal the input
+    bit for bit (no halos, no padding: the round trip is the identity), and one extra X->Y must equal the oracle's."""
+    dt_enum, np_dtype = DTYPES[case.get("dtype", "double")]
+    es = np.dtype(np_dtype).itemsize
+    cfg = make_config(case)
+    res, gd = cd.cudecompGridDescCreate(handle, cfg)
+    cd.check(res, "cudecompGridDescCreate")
+    out = dict(ok=True, msg="", paths=[])
+    work_ptr = 0
+    try:
+        o = make_oracle(case)
+        inplace = not case.get("out_of_place", False)
+        if case.get("force_staged"):
+            cd.check(cd.set_tuning(handle, gd, 0, True))
+        if case.get("pipeline_chunks"):
+            cd.check(cd.set_pipeline_chunks(handle, gd, case["pipeline_chunks"]))
+        if case.get("staged_mode") is not None or case.get("fused_lag"):
+            cd.check(cd.set_staged_mode(handle, gd, case.get("staged_mode") or 0, case.get("fused_lag") or 0))
+        res, wsize = cd.cudecompGetTransposeWorkspaceSize(handle, gd)
+        res, work_ptr = cd.cudecompMalloc(handle, gd, wsize * es)
+        cd.check(res, "cudecompMalloc")
+        n = max(o.pencil_info(rank, ax).size for ax in range(3))
+        hosts = [seeded(max(o.pencil_info(r, ax).size for ax in range(3)), np_dtype, 31 * r + 5) for r in range(o.nranks)]
+        d_a = gpu.upload(hosts[rank])
+        d_b = d_a if inplace else gpu.empty(n * es)
+        for _ in range(case.get("reps", 10)):
+            x, y = d_a, d_b
+            for op in OPS:
+                cd.check(cd.TRANSPOSES[op](handle, gd, x, y, work_ptr, dt_enum, None, None, None, None, None), op)
+                out["paths"].append(cd.last_path(handle, gd))
+                if not inplace:
+                    x, y = y, x
+        got = gpu.download(d_a, np_dtype)
+        if cd.check_errors(handle, gd) != 0:
+            return dict(ok=False, msg="device-side handshake error")
+        nx = o.pencil_info(rank, 0).size
+        if not np.array_equal(got[:nx].view(np.uint8), hosts[rank][:nx].view(np.uint8)):
+            bad = np.flatnonzero(got[:nx] != hosts[rank][:nx])
+            return dict(ok=False, msg="round trips are not the identity: %d cells differ, first %d" % (bad.size, bad[0]))
+        others = [np.zeros_like(hh) for hh in hosts]
+        o.transpose("XY", hosts, hosts if inplace else others)
+        cd.check(cd.TRANSPOSES["XY"](handle, gd, d_a, d_b, work_ptr, dt_enum, None, None, None, None, None), "XY")
+        got = gpu.download(d_b, np_dtype)
+        ny = o.pencil_info(rank, 1).size
+        want = (hosts if inplace else others)[rank]
+        if not np.array_equal(got[:ny].view(np.uint8), want[:ny].view(np.uint8)):
+            return dict(ok=False, msg="X->Y after the round trips differs from the oracle")
     finally:
         if work_ptr:
             cd.cudecompFree(handle, gd, work_ptr)
@@ -547,6 +606,8 @@ def main():
                 results.append(nccl_crosscheck_case(gpu, handle, rank, case))
             elif case["kind"] == "autotune":
                 results.append(autotune_case(gpu, handle, rank, case))
+            elif case["kind"] == "stress":
+                results.append(stress_case(gpu, handle, rank, case))
             else:
                 results.append(transpose_case(gpu, handle, rank, case))
         except Exception as e:  # noqa: BLE001

@@ -83,6 +83,39 @@ def run_boxes(boxes, srcs, dsts, es, legal, me=-1, comm_size=0, peer_index=None,
                 balanced_grid=stats[6], longest_row=stats[7])
 
 
+def run_phased(boxes, srcs, dsts, es, legal, nsteps, lag, want_unpack, step, tile_bytes=0, grid=0, threads=256):
+    """One rank's fused staged schedule (engine.cc runFusedStaged) prepared by the product's preparePhased; executes the
+    push boxes of phase `step` or (want_unpack) the unpack boxes that wait for `step`. Returns the stats dict, or None
+    when the schedule cannot run as one phased launch."""
+    n = len(boxes)
+    arr = (cd.cudecompB200Box_t * max(n, 1))()
+    for i, b in enumerate(boxes):
+        arr[i].peer_rank = b["peer_rank"]
+        arr[i].is_unpack = b["is_unpack"]
+        arr[i].step = b.get("step", 0)
+        arr[i].src_offset = b["src_offset"]
+        arr[i].dst_offset = b["dst_offset"]
+        for k in range(3):
+            arr[i].extent[k] = b["extent"][k]
+            arr[i].src_stride[k] = b["src_stride"][k]
+            arr[i].dst_stride[k] = b["dst_stride"][k]
+    sb = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data for a in srcs])
+    db = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data for a in dsts])
+    lo = (ctypes.c_void_p * max(len(legal), 1))(*[a.ctypes.data for a in legal])
+    ln = (ctypes.c_int64 * max(len(legal), 1))(*[a.nbytes for a in legal])
+    stats = (ctypes.c_int64 * 8)()
+    err = ctypes.create_string_buffer(512)
+    fn = lib().cdb_emu_run_phased
+    fn.restype = ctypes.c_int
+    rc = fn(arr, n, nsteps, sb, db, lo, ln, len(legal), es, tile_bytes, lag, int(want_unpack), step, grid, threads, stats,
+            err, 512)
+    if rc < 0:
+        raise EmuError(err.value.decode())
+    if rc == 1:
+        return None
+    return dict(phases=stats[0], bytes_written=stats[1], accesses=stats[2], vec=stats[3], slots=stats[4], boxes=stats[5])
+
+
 def aligned_array(n, dtype, offset_bytes=0, fill=None):
     """numpy array of n elements whose first byte sits `offset_bytes` past a 256-byte boundary (device allocations are
     256-byte aligned; offsets exercise the narrower vector widths)."""

@@ -267,6 +267,113 @@ extern "C" int cdb_emu_run_boxes(const cudecompB200Box_t* boxes, const int32_t* 
   }
 }
 
+namespace {
+
+// rowCopyPhasedKernel: the tile body is copyRowTile (the same loops as walkRowCopy), slots of a phase interleave its boxes.
+// Walks the boxes selected by (want_unpack, step): the push boxes of phase `step`, or the unpack boxes that wait for
+// `step`, so that the caller can interleave the ranks in dependency order. Also checks the phase structure itself.
+void walkPhasedSelection(const PhasedLaunch& pl, int es, int lag, int want_unpack, int step, int grid, int threads, Walk& w) {
+  const uint32_t nwarps = static_cast<uint32_t>(threads) >> 5;
+  constexpr uint32_t kUnroll = 4, kPiece = 32 * kUnroll;
+  const int V = pl.vec_size;
+  for (uint32_t s = 0; s < pl.phases.size(); ++s) {
+    const PhaseDesc& ph = pl.phases[s];
+    const uint32_t total = ph.nboxes * ph.max_tiles;
+    for (uint32_t cta = 0; cta < static_cast<uint32_t>(grid); ++cta)
+      for (uint32_t t = cta; t < total; t += grid) {
+        const uint32_t b = t % ph.nboxes, j = t / ph.nboxes;
+        const KBox& bx = pl.boxes[ph.first_box + b];
+        if (j >= bx.tiles) continue;
+        const int need = static_cast<int>(bx.pad_) - 1;
+        if (need >= 0) {
+          if (static_cast<int>(s) != need + lag) throw Fail("unpack box in the wrong phase");
+          if (need >= static_cast<int>(pl.npush_phases)) throw Fail("unpack box waits for a step that is never published");
+        } else if (s >= pl.npush_phases) {
+          throw Fail("push box after the last published phase");
+        }
+        const bool sel = want_unpack ? (need == step) : (need < 0 && static_cast<int>(s) == step);
+        if (!sel) continue;
+        const RowTile rt = decodeRowTile(bx, j);
+        const uint32_t pieces_per_row = (rt.nvec + kPiece - 1) / kPiece;
+        const uint32_t npieces = rt.rows_here * pieces_per_row;
+        if (bx.row_vecs <= 32u) {
+          const uint32_t total_vecs = rt.rows_here * rt.nvec;
+          for (uint32_t e = 0; e < total_vecs; ++e) {
+            const uint32_t r = e / rt.nvec, c = e - r * rt.nvec;
+            int64_t so, dof;
+            rowOffsets(bx, rt.row0 + r, es, so, dof);
+            w.vec(bx.dst + dof + static_cast<int64_t>(rt.c0 + c) * V, bx.src + so + static_cast<int64_t>(rt.c0 + c) * V, V);
+          }
+          continue;
+        }
+        for (uint32_t warp = 0; warp < nwarps; ++warp)
+          for (uint32_t pc = warp; pc < npieces; pc += nwarps) {
+            const uint32_t r = pc / pieces_per_row, q = pc - r * pieces_per_row;
+            int64_t so, dof;
+            rowOffsets(bx, rt.row0 + r, es, so, dof);
+            for (uint32_t lane = 0; lane < 32; ++lane)
+              for (uint32_t k = 0; k < kUnroll; ++k) {
+                const uint32_t idx = q * kPiece + lane + 32u * k;
+                if (idx >= rt.nvec) continue;
+                w.vec(bx.dst + dof + static_cast<int64_t>(rt.c0 + idx) * V, bx.src + so + static_cast<int64_t>(rt.c0 + idx) * V, V);
+              }
+          }
+      }
+  }
+}
+
+} // namespace
+
+// The fused staged schedule of ONE rank (engine.cc runFusedStaged): boxes carry step and is_unpack (a chunked plan from
+// cudecompB200PlanPipelinedTransposeBoxes, or a plain staged plan with every step 0). nsteps = K. Executes only the
+// selection (want_unpack, step), see walkPhasedSelection. stats: [0] phases, [1] bytes written, [2] accesses,
+// [3] vector width, [4] total slots, [5] boxes. Returns 1 when the schedule cannot run as a phased launch.
+extern "C" int cdb_emu_run_phased(const cudecompB200Box_t* boxes, int nboxes, int nsteps, const void* const* src_bases,
+                                  void* const* dst_bases, const char* const* range_lo, const int64_t* range_len, int nranges,
+                                  int es, int tile_bytes, int lag, int want_unpack, int step, int grid, int threads,
+                                  int64_t* stats, char* err, int err_len) {
+  try {
+    std::vector<std::vector<LaunchBox>> push(nsteps), unpack(nsteps);
+    for (int i = 0; i < nboxes; ++i) {
+      LaunchBox lb;
+      BoxDesc& d = lb.d;
+      d.peer = 0;
+      d.peer_world = boxes[i].peer_rank;
+      d.src_off = boxes[i].src_offset;
+      d.dst_off = boxes[i].dst_offset;
+      for (int k = 0; k < 3; ++k) {
+        d.ext[k] = boxes[i].extent[k];
+        d.sstr[k] = boxes[i].src_stride[k];
+        d.dstr[k] = boxes[i].dst_stride[k];
+      }
+      lb.src_base = static_cast<const char*>(src_bases[i]);
+      lb.dst_base = static_cast<char*>(dst_bases[i]);
+      if (boxes[i].step < 0 || boxes[i].step >= nsteps) throw Fail("box with a step outside the schedule");
+      (boxes[i].is_unpack ? unpack : push)[boxes[i].step].push_back(lb);
+    }
+    LaunchTuning tuning;
+    tuning.tile_bytes = tile_bytes;
+    PhasedLaunch pl;
+    if (!preparePhased(push, unpack, es, tuning, lag, &pl)) return 1;
+    if (pl.phases.size() != static_cast<size_t>(nsteps + lag)) throw Fail("wrong number of phases");
+    Ranges ranges{range_lo, range_len, nranges};
+    Walk w{ranges};
+    walkPhasedSelection(pl, es, lag, want_unpack, step, grid > 0 ? grid : 370, threads > 0 ? threads : 256, w);
+    if (stats) {
+      stats[0] = static_cast<int64_t>(pl.phases.size());
+      stats[1] = w.bytes_written;
+      stats[2] = w.accesses;
+      stats[3] = pl.vec_size;
+      stats[4] = static_cast<int64_t>(pl.total_slots);
+      stats[5] = static_cast<int64_t>(pl.boxes.size());
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    if (err && err_len > 0) std::snprintf(err, static_cast<size_t>(err_len), "%s", e.what());
+    return -1;
+  }
+}
+
 // chooseGrid as the library computes it (kernels.h)
 extern "C" int cdb_emu_choose_grid(int requested, int dflt, int resident, uint64_t total_slots, int balance) {
   return chooseGrid(requested, dflt, resident, total_slots, balance);

@@ -203,6 +203,60 @@ def test_emulated_pipelined_schedule_equals_oracle(d, s, K, inplace, pull):
             assert np.array_equal(outs[r], ref_out[r]), (d, s, op, K, inplace, pull, r)
 
 
+@settings(max_examples=max(EXAMPLES // 3, 20), deadline=None, suppress_health_check=list(HealthCheck))
+@given(decompositions(), schedules(), st.sampled_from([1, 2, 3, 4, 8]), st.booleans(), st.sampled_from([1, 2, 3]),
+       st.booleans())
+def test_emulated_fused_staged_schedule_equals_oracle(d, s, K, inplace, lag, late):
+    """The fused staged schedule (engine.cc runFusedStaged, kernels.cu rowCopyPhasedKernel): every rank's phased launch
+    is prepared by the product's preparePhased and walked by the emulator. The kernel only orders an unpack box after
+    the step it waits for, so both extremes are executed: every unpack as EARLY as its dependency allows (right after
+    its step has been pushed by all ranks, before any later push has read its source), and as LATE as possible."""
+    cfg, o = make_config(d), make_oracle(d)
+    n = o.nranks
+    dt = DT[s["es"]]
+    for op, (ax, direction) in OPS.items():
+        a, b = orc.transpose_axes(op)
+        if o.has_empty_pencils(a) or o.has_empty_pencils(b):
+            continue
+        ha, hb, pa, pb = d["halos"][str(a)], d["halos"][str(b)], d["pads"][str(a)], d["pads"][str(b)]
+        if list(o.pencil_info(0, a).order) != list(o.pencil_info(0, b).order):
+            continue  # differing memory orders: the engine keeps separate launches (engine.cc runFusedStaged)
+        if K > 1:
+            plans = [cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, int(inplace), K) for r in range(n)]
+            nsteps = K
+        else:
+            plans = [cd.plan_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, staged=1) for r in range(n)]
+            nsteps = 1
+        if not any(plans):
+            continue
+        rng = np.random.default_rng(7)
+        sizes = [max(o.pencil_info(r, a, ha, pa).size, o.pencil_info(r, b, hb, pb).size) for r in range(n)]
+        bufs = [emu.aligned_array(sizes[r], dt, 0, -3) for r in range(n)]
+        for r in range(n):
+            rand_fill(bufs[r][:o.pencil_info(r, a, ha, pa).size], rng)
+        ref_in = [x.copy() for x in bufs]
+        ref_out = ref_in if inplace else [np.full(sizes[r], -3, dt) for r in range(n)]
+        o.transpose(op, ref_in, ref_out, ha, hb, pa, pb)
+        outs = bufs if inplace else [emu.aligned_array(sizes[r], dt, 0, -3) for r in range(n)]
+        works = [emu.aligned_array(max(o.transpose_workspace_size(), 1), dt, 0, -9) for _ in range(n)]
+        legal = bufs + outs + works
+
+        def run(r, want_unpack, step):
+            bx = plans[r]
+            srcs = [works[r] if x["is_unpack"] else bufs[r] for x in bx]
+            dsts = [outs[r] if x["is_unpack"] else works[x["peer_rank"]] for x in bx]
+            return emu.run_phased(bx, srcs, dsts, s["es"], legal, nsteps, lag, want_unpack, step, tile_bytes=s["tile_bytes"],
+                                  grid=s["grid"], threads=s["threads"])
+
+        order = [(False, k) for k in range(nsteps)] + [(True, k) for k in range(nsteps)] if late else \
+            [(u, k) for k in range(nsteps) for u in (False, True)]
+        for want_unpack, step in order:
+            for r in range(n):
+                assert run(r, want_unpack, step) is not None, "equal memory orders must always give a phased launch"
+        for r in range(n):
+            assert np.array_equal(outs[r], ref_out[r]), (d, s, op, K, inplace, lag, late, r)
+
+
 def test_kernel_selection_and_vector_width():
     """Default-layout transposes are row copies at the widest vector the alignment allows; differing memory orders go
     through the tiled transpose kernel; the bulk variant only takes over for 16-byte aligned rows of at least 2 KiB."""

@@ -26,11 +26,24 @@ with open(os.path.join(CASES, "index.n4.json")) as f:
 RUNS = [(name, dt) for name, info in sorted(INDEX.items()) for dt in info["dtypes"]]
 
 
-def run_mpi(nranks, argv, timeout):
+def device_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:  # noqa: BLE001
+        return 0
+
+
+def run_mpi(nranks, argv, timeout, extra_env=None):
     port = free_port()
     procs = []
+    ndev = device_count()
     for r in range(nranks):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(nranks), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        if 0 < ndev < nranks:
+            # executables that call cudaSetDevice(local rank): report "nodes" of ndev ranks so the ranks share the GPUs
+            env.setdefault("CUDECOMP_B200_SHIM_RANKS_PER_NODE", str(ndev))
+        env.update(extra_env or {})
         # rank 0 reports; the other ranks' output is kept for debugging when CUDECOMP_REF_LOG_DIR is set
         log_dir = os.environ.get("CUDECOMP_REF_LOG_DIR")
         sink = subprocess.DEVNULL

@@ -1,13 +1,12 @@
 """The reference's API contract tests (tests/ctest/api_tests.cc) on 4 ranks WITH a device behind every handle: adds the
 cudecompMalloc / cudecompFree parts of SupportsMultipleLiveHandlesWithIndependentResources (api_tests.cc:575-608) to
-what tests/test_api_contract.py checks on the host. Written after the round-1 GPU budget was spent: expected to pass,
-unconfirmed on hardware, so xfail(strict=False) keeps a surprise from masking the rest of the suite."""
+what tests/test_api_contract.py checks on the host. Confirmed on B200 by the round-1 driver run (GPUTEST_r01.json)."""
 import pytest
 
 from tests._api_battery import TEST_NAMES
 from tests._launcher import run_ranks
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet confirmed on hardware")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")

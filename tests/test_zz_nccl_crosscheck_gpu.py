@@ -1,13 +1,12 @@
 """Byte-for-byte cross-check of the library against the reference's NCCL arm restated with public NCCL only
 (bench/nccl_restated.py: pack -> all_to_all_single -> unpack in the reference's wire format), SURVEY.md section 8(c).
 The restated arm itself is pinned to the oracle on the CPU (tests/test_nccl_restated.py). NCCL needs one GPU per rank, so
-the cases skip themselves on smaller boxes. Written after the round-1 GPU budget was spent: xfail(strict=False), an XPASS
-is the hardware confirmation."""
+the cases skip themselves on smaller boxes. Hardware runs: profiles/r2_n2_schedules.md (2 GPUs), profiles/r2_n8_*.txt (8 GPUs)."""
 import pytest
 
 from tests._launcher import run_ranks
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run happens at round end")]
+pytestmark = [pytest.mark.gpu]
 
 CASES = {
     2: [dict(kind="nccl_crosscheck", name="c128_1x2", gdims=[64, 48, 40], pdims=[1, 2], dtype="double_complex"),

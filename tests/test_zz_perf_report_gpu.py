@@ -8,7 +8,7 @@ import pytest
 
 from tests._launcher import run_ranks
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet confirmed on hardware")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_performance_report_table_and_csv():

@@ -1,7 +1,8 @@
 """The reference's own FFT benchmark (benchmark/benchmark.cu: cuFFT per pencil + the four transposes, with its own
 max-error check against the input) built UNMODIFIED against this library by oracle/ref_tests.mk and run on 4 ranks.
-SURVEY.md section 8(f) row 1. The binaries were first built after the round-1 GPU budget was spent, hence
-xfail(strict=False): an XPASS is the hardware confirmation."""
+SURVEY.md section 8(f) row 1. The binary picks its device as cudaSetDevice(local rank of
+MPI_COMM_TYPE_SHARED) (benchmark.cu:135-139); on a box with fewer GPUs than ranks run_mpi tells the MPI shim to report
+"nodes" of device_count ranks (as a real launcher with one rank per GPU would), so every rank gets a valid device."""
 import os
 import re
 
@@ -9,7 +10,7 @@ import pytest
 
 from tests.test_ref_executables_gpu import REF_BIN, run_mpi
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run happens at round end")]
+pytestmark = [pytest.mark.gpu]
 
 RUNS = [
     ("benchmark_c2c", ["--gx", "64", "--gy", "64", "--gz", "64", "-r", "2", "-c", "2", "-b", "4", "-t", "2", "-w", "1"]),

@@ -6,8 +6,7 @@ the reference's CTest does (tests/ctest/CMakeLists.txt:102-196): 4 ranks, the ha
 The reference's harness refuses to let ranks share a GPU unless CUDA MPS is running (gpu_test_utils.cc:75-84: its
 MPI/NCCL backends deadlock under time slicing). This library's ranks may share a device, so on boxes with fewer than
 4 GPUs the test points CUDA_MPS_PIPE_DIRECTORY at a directory holding the pid file that harness looks for; the
-NCCL-labelled cases then skip themselves (they additionally want NCCL >= 2.30 for multi-rank-per-GPU).
-Built after the round-1 GPU budget was spent: xfail(strict=False), an XPASS is the hardware confirmation."""
+NCCL-labelled cases then skip themselves (they additionally want NCCL >= 2.30 for multi-rank-per-GPU)."""
 import os
 import re
 import tempfile
@@ -16,7 +15,7 @@ import pytest
 
 from tests.test_ref_executables_gpu import REF_BIN, run_mpi
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run happens at round end")]
+pytestmark = [pytest.mark.gpu]
 
 RUNS = [
     ("api", "ctest_api_tests", [], {}),

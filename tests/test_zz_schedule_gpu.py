@@ -1,12 +1,12 @@
 """Opt-in launch schedules on the GPU (cudecompB200SetSchedule): tile sizes, the pairwise slot order and the balanced
 grid must give byte-identical results to the default schedule. Their index arithmetic is property-tested on the host
-(tests/test_launch_emulation.py walks the same launches with the kernels' own decode functions); the device run was
-written after the round-1 GPU budget was spent, hence xfail(strict=False): an XPASS is the hardware confirmation."""
+(tests/test_launch_emulation.py walks the same launches with the kernels' own decode functions); confirmed on B200 by the
+round-1 driver run (GPUTEST_r01.json)."""
 import pytest
 
 from tests._launcher import run_ranks
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="device execution not yet confirmed on hardware")]
+pytestmark = [pytest.mark.gpu]
 
 BASE = dict(kind="transpose", ops=["XY", "YZ", "ZY", "YX"])
 CASES = [
