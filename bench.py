@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--chunks", type=int, default=0, help="chunks of staged (in-place) transposes, 0 = from the pencil size")
     ap.add_argument("--staged-mode", type=int, default=0, help="0 one phased launch per staged transpose, 1 separate launches")
     ap.add_argument("--lag", type=int, default=0, help="phases between a chunk's push and its unpack (0 = library default)")
+    ap.add_argument("--kernel-variant", type=int, default=0, help="cudecompB200SetKernelVariant value (3 = element-wise transpose)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed integer-pattern check after the timed region")
     ap.add_argument("--tile-bytes", type=int, default=0, help="row-copy tile size (0 = 32 KiB)")
     ap.add_argument("--peer-order", type=int, default=0, help="0 one-shot interleaved, 1 pairwise rounds")
@@ -304,6 +305,8 @@ def run_native(args, rank, world, local_rank):
         cd.check(cd.set_kernel_variant(handle, gd, 1))
     if args.wide:
         cd.check(cd.set_kernel_variant(handle, gd, 2))
+    if args.kernel_variant:
+        cd.check(cd.set_kernel_variant(handle, gd, args.kernel_variant))
     if args.pull:
         cd.check(cd.set_transfer_mode(handle, gd, 1))
     if args.chunks:

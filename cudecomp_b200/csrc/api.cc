@@ -704,7 +704,8 @@ cudecompResult_t cudecompB200SetKernelVariant(cudecompHandle_t handle, cudecompG
   API_TRY
   checkHandle(handle);
   checkGridDesc(handle, grid_desc);
-  if (variant < 0 || variant > 2) THROW_INVALID_USAGE("variant must be 0 (LDG/STG.128), 1 (TMA bulk) or 2 (LDG/STG.256)");
+  if (variant < 0 || variant > 3)
+    THROW_INVALID_USAGE("variant must be 0 (default), 1 (TMA bulk), 2 (LDG/STG.256) or 3 (element-wise transpose)");
   grid_desc->kernel_variant = variant;
   API_CATCH()
 }

@@ -291,16 +291,19 @@ bool runFusedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, 
     if (gd->fused_cache.size() >= 64) releaseFusedCache(gd);
     FusedPlanEntry e;
     e.key = key;
-    const size_t box_bytes = pl.boxes.size() * sizeof(KBox);
-    e.bytes = box_bytes + pl.phases.size() * sizeof(PhaseDesc);
+    const size_t box_bytes = (pl.boxes.size() * sizeof(KBox) + 15) / 16 * 16; // the tables behind it are 16-byte records
+    const size_t seg_bytes = pl.segs.size() * sizeof(SegDesc);
+    e.bytes = box_bytes + seg_bytes + pl.phases.size() * sizeof(PhaseDesc);
     CHECK_CUDA(cudaMalloc(&e.dev, std::max<size_t>(e.bytes, 256)));
     CHECK_CUDA(cudaHostAlloc(&e.host, std::max<size_t>(e.bytes, 256), cudaHostAllocDefault));
-    std::memcpy(e.host, pl.boxes.data(), box_bytes);
-    std::memcpy(static_cast<char*>(e.host) + box_bytes, pl.phases.data(), pl.phases.size() * sizeof(PhaseDesc));
+    std::memcpy(e.host, pl.boxes.data(), pl.boxes.size() * sizeof(KBox));
+    std::memcpy(static_cast<char*>(e.host) + box_bytes, pl.segs.data(), seg_bytes);
+    std::memcpy(static_cast<char*>(e.host) + box_bytes + seg_bytes, pl.phases.data(), pl.phases.size() * sizeof(PhaseDesc));
     CHECK_CUDA(cudaMemcpyAsync(e.dev, e.host, e.bytes, cudaMemcpyHostToDevice, stream));
     std::memset(&e.params, 0, sizeof(e.params));
     e.params.boxes = static_cast<const KBox*>(e.dev);
-    e.params.phases = reinterpret_cast<const PhaseDesc*>(static_cast<char*>(e.dev) + box_bytes);
+    e.params.segs = reinterpret_cast<const SegDesc*>(static_cast<char*>(e.dev) + box_bytes);
+    e.params.phases = reinterpret_cast<const PhaseDesc*>(static_cast<char*>(e.dev) + box_bytes + seg_bytes);
     e.params.nphases = static_cast<uint32_t>(pl.phases.size());
     e.params.npush_phases = pl.npush_phases;
     e.params.elem_size = static_cast<uint32_t>(es);

@@ -31,7 +31,7 @@ namespace cdb {
 // with the entry (so the upload is a plain asynchronous copy and the steady state does no host work but the lookup).
 struct FusedPlanEntry {
   std::string key;
-  void* dev = nullptr;     // [KBox boxes...][PhaseDesc phases...]
+  void* dev = nullptr;     // [KBox boxes...][SegDesc segments...][PhaseDesc phases...]
   void* host = nullptr;    // pinned copy
   size_t bytes = 0;
   PhasedParams params{};   // sync block filled per call

@@ -225,13 +225,14 @@ template <typename V> __global__ void __launch_bounds__(256) rowCopyPhasedKernel
 
   for (uint32_t s = 0; s < p.nphases; ++s) {
     const PhaseDesc ph = p.phases[s];
-    const uint32_t total = ph.nboxes * ph.max_tiles;
+    const uint32_t total = ph.nsegs * ph.seg_tiles;
     for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
-      const uint32_t b = t % ph.nboxes;
-      const uint32_t j = t / ph.nboxes;
-      const KBox& bx = p.boxes[ph.first_box + b];
-      if (j >= bx.tiles) continue;
-      const int32_t need = static_cast<int32_t>(bx.pad_) - 1;
+      const SegDesc sg = p.segs[ph.first_seg + t % ph.nsegs];
+      const uint32_t jj = t / ph.nsegs;
+      if (jj >= sg.count) continue;
+      const KBox& bx = p.boxes[sg.box];
+      const uint32_t j = sg.first_tile + jj;
+      const int32_t need = static_cast<int32_t>(sg.wait) - 1;
       if (need > known) {
         // every peer's pushes of step `need` have landed here, and every local CTA has finished reading that chunk
         int failed = 0;
@@ -316,6 +317,73 @@ template <typename T, int kOrder> __global__ void __launch_bounds__(256) transpo
           const int64_t i0 = static_cast<int64_t>(j0) * 32 + r + wrow;
           if (i0 < bx.n[0] && i1 < bx.n[1]) d[i0 * bx.ds[0] + i1 * bx.ds[1]] = tile[lane][r + wrow];
         }
+      }
+      __syncthreads();
+    }
+  }
+
+  if (go) syncExit(p.sync);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TRANSPOSE_VEC: same boxes as TRANSPOSE, 16-byte accesses on both sides (kernels.h, tiling.h TransVecGeom).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int kOrder> __global__ void __launch_bounds__(256) transposeVecKernel(const __grid_constant__ CopyParams p) {
+  using G = TransVecGeom<sizeof(T)>;
+  constexpr int VEC = G::kVec;
+  union Vec {
+    uint4 u;
+    T t[VEC];
+  };
+  __shared__ uint4 tile[1024];
+  const bool go = syncEntry(p.sync);
+  const uint32_t total = go ? p.nboxes * p.max_tiles : 0u;
+  const uint32_t tid = threadIdx.x;
+
+  for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+    uint32_t b, j;
+    slotToBoxTile(t, p.nboxes, p.max_tiles, static_cast<uint32_t>(kOrder), b, j);
+    const KBox& bx = p.box[b];
+    if (j < bx.tiles) { // uniform per CTA
+      const TransTile tt = decodeTransposeTile(bx, j);
+      const int64_t base0 = static_cast<int64_t>(tt.j0) * G::kE0;
+      const int64_t base1 = static_cast<int64_t>(tt.j1) * G::kE1;
+      const T* s = reinterpret_cast<const T*>(bx.src) + tt.i2 * bx.ss[2];
+      T* d = reinterpret_cast<T*>(bx.dst) + tt.i2 * bx.ds[2];
+      Vec in[G::kNM][VEC];
+#pragma unroll
+      for (int q = 0; q < G::kNM; ++q) {
+        const uint32_t m = tid + 256u * q;
+        const uint32_t c = m % G::kC0, g = m / G::kC0;
+        const int64_t i0 = base0 + c * VEC;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const int64_t i1 = base1 + g * VEC + k;
+          in[q][k].u = make_uint4(0u, 0u, 0u, 0u);
+          if (i0 < bx.n[0] && i1 < bx.n[1]) in[q][k].u = __ldcs(reinterpret_cast<const uint4*>(s + i0 + i1 * bx.ss[1]));
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < G::kNM; ++q) {
+        const uint32_t m = tid + 256u * q;
+        const uint32_t c = m % G::kC0, g = m / G::kC0;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          Vec out;
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) out.t[k] = in[q][k].t[e];
+          tile[transVecSlot(c * VEC + e, g, VEC, G::kG1)] = out.u;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int pass = 0; pass < VEC * G::kNM; ++pass) {
+        const uint32_t n = tid + 256u * pass;
+        const uint32_t v = n % G::kG1, row = n / G::kG1;
+        const int64_t i0 = base0 + row;
+        const int64_t i1 = base1 + v * VEC;
+        if (i0 < bx.n[0] && i1 < bx.n[1])
+          __stcs(reinterpret_cast<uint4*>(d + i0 * bx.ds[0] + i1), tile[transVecSlot(row, v, VEC, G::kG1)]);
       }
       __syncthreads();
     }
@@ -459,6 +527,12 @@ template <int kOrder> KernelFn pickKernelOrdered(KernelKind kind, int size) {
     case 8: return transposeKernel<uint2, kOrder>;
     case 4: return transposeKernel<uint32_t, kOrder>;
     }
+  } else if (kind == KernelKind::TRANSPOSE_VEC) {
+    switch (size) {
+    case 16: return transposeVecKernel<uint4, kOrder>;
+    case 8: return transposeVecKernel<uint2, kOrder>;
+    case 4: return transposeVecKernel<uint32_t, kOrder>;
+    }
   } else if (size == 16) {
     return rowCopyBulkKernel;
   }
@@ -472,7 +546,7 @@ KernelFn pickKernel(KernelKind kind, int size, uint32_t peer_order = 0) {
 } // namespace
 
 int maxResidentCtas(KernelKind kind, int size, int threads, uint32_t peer_order) {
-  static int cache[2][2][4] = {};
+  static int cache[2][3][4] = {};
   static int cache_dev = -1;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -482,7 +556,7 @@ int maxResidentCtas(KernelKind kind, int size, int threads, uint32_t peer_order)
   }
   if (kind == KernelKind::ROWCOPY_BULK) return 0; // not used: launchBulk sizes its own grid
   const int oi = peer_order ? 1 : 0;
-  const int ki = (kind == KernelKind::ROWCOPY) ? 0 : 1;
+  const int ki = (kind == KernelKind::ROWCOPY) ? 0 : (kind == KernelKind::TRANSPOSE ? 1 : 2);
   const int si = (size == 32) ? 3 : (size == 16) ? 2 : (size == 8 ? 1 : 0);
   if (threads == 256 && cache[oi][ki][si] > 0) return cache[oi][ki][si];
   KernelFn fn = pickKernel(kind, size, peer_order);

@@ -78,16 +78,30 @@ struct CopyParams {
 // After its share of a phase a CTA fences and bumps the phase counter; the last one publishes (epoch, s) to the peers'
 // kPadStep slot. A CTA that reaches a box with wait_step >= 0 first waits until every peer has published that step
 // and every local CTA has finished it (all local reads of that chunk are done, all remote data of it has landed).
+// The boxes of a phase differ widely in size (a push box is 1/K of a peer's share, an unpack piece may be 1/16 of
+// that), so a phase is cut into SEGMENTS of at most kSegTiles tiles of one box and its slots interleave the segments:
+// slot t -> segment t % nsegs, tile t / nsegs of it. Every window of nsegs slots then holds the boxes in proportion to
+// their sizes, and at most one segment per box is partly empty.
 // The tables live in device memory (too many boxes for the parameter space).
-struct PhaseDesc {
-  uint32_t first_box;
-  uint32_t nboxes;
-  uint32_t max_tiles;
+constexpr uint32_t kSegTiles = 64;
+
+struct alignas(16) SegDesc {
+  uint32_t box;        // index into PhasedParams::boxes
+  uint32_t first_tile; // of that box
+  uint32_t count;      // tiles in this segment (<= kSegTiles)
+  uint32_t wait;       // wait_step + 1 of the box (0: no dependency)
+};
+
+struct alignas(16) PhaseDesc {
+  uint32_t first_seg;
+  uint32_t nsegs;
+  uint32_t seg_tiles; // slots of the phase = nsegs * seg_tiles (seg_tiles = longest segment of the phase)
   uint32_t pad_;
 };
 
 struct PhasedParams {
   const KBox* boxes;       // device table; KBox::pad_ holds wait_step + 1 (0: no dependency)
+  const SegDesc* segs;     // device table
   const PhaseDesc* phases; // device table
   SyncParams sync;         // do_exit is ignored: the last phase's waits subsume the exit handshake
   uint32_t nphases;
@@ -99,7 +113,11 @@ struct PhasedParams {
 // ROWCOPY_BULK: the row copy driven by the TMA unit instead of LDG/STG: one elected thread per CTA moves row segments
 // global -> shared -> global with cp.async.bulk and an mbarrier ring. Same boxes and tiling fields as ROWCOPY, but a
 // tile is ONE row segment of at most kBulkChunkBytes (rows_per_tile = 1) and everything must be 16-byte aligned.
-enum class KernelKind { ROWCOPY, TRANSPOSE, ROWCOPY_BULK };
+// TRANSPOSE_VEC: the transpose with 16-byte global accesses on both sides (micro-tiles of VEC x VEC elements, VEC =
+// 16 / element size, are transposed in registers and exchanged through a swizzled shared-memory tile of 16-byte vectors;
+// see tiling.h TransVecGeom). Needs 16-byte aligned rows on both sides and extents that are multiples of VEC; other
+// launches keep the element-wise TRANSPOSE kernel.
+enum class KernelKind { ROWCOPY, TRANSPOSE, ROWCOPY_BULK, TRANSPOSE_VEC };
 
 constexpr int kBulkStages = 4;
 constexpr uint32_t kBulkChunkBytes = 16384;

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "errors.h"
+#include "tiling.h"
 
 namespace cdb {
 
@@ -26,6 +27,40 @@ void fillRowCopy(KBox& kb, const CanonBox& c, int es, int V, uint32_t tile_bytes
   if (tiles > 0x7fffffff) THROW_NOT_SUPPORTED("box too large for one launch");
   kb.tiles = static_cast<uint32_t>(tiles);
   kb.tiles0 = kb.tiles1 = 0;
+}
+
+// TRANSPOSE boxes: axis 0 = contiguous in the source, axis 1 = contiguous in the destination when there is one
+struct TransAxes {
+  int64_t n[3], ss[3], ds[3];
+};
+TransAxes transposeAxesOf(const CanonBox& c) {
+  int a1 = c.dstUnitAxis();
+  if (a1 <= 0) a1 = (c.nd > 1) ? 1 : -1;
+  int a2 = -1;
+  for (int k = 1; k < c.nd; ++k)
+    if (k != a1) a2 = k;
+  const int map[3] = {0, a1, a2};
+  TransAxes t;
+  for (int k = 0; k < 3; ++k) {
+    t.n[k] = (map[k] >= 0) ? c.n[map[k]] : 1;
+    t.ss[k] = (map[k] >= 0) ? c.ss[map[k]] : 0;
+    t.ds[k] = (map[k] >= 0) ? c.ds[map[k]] : 0;
+  }
+  return t;
+}
+
+// 16-byte accesses on both sides: unit strides where the kernel assumes them, every row start 16-byte aligned, whole
+// vectors only
+bool transposeVecOk(const TransAxes& t, const LaunchBox& b, int es) {
+  const int vec = 16 / es;
+  if (t.ss[0] != 1 || t.ds[1] != 1 || t.n[1] <= 1) return false;
+  if (t.n[0] % vec || t.n[1] % vec) return false;
+  const uint64_t sa = reinterpret_cast<uint64_t>(b.src_base) + static_cast<uint64_t>(b.d.src_off) * es;
+  const uint64_t da = reinterpret_cast<uint64_t>(b.dst_base) + static_cast<uint64_t>(b.d.dst_off) * es;
+  if (sa % 16 || da % 16) return false;
+  if ((t.ss[1] * es) % 16 || (t.ds[0] * es) % 16) return false;
+  if (t.n[2] > 1 && ((t.ss[2] * es) % 16 || (t.ds[2] * es) % 16)) return false;
+  return true;
 }
 
 } // namespace
@@ -80,6 +115,14 @@ std::vector<PreparedLaunch> prepareLaunches(const std::vector<LaunchBox>& boxes,
     if (ok) kind = KernelKind::ROWCOPY_BULK;
   }
 
+  // vectorised transpose where every box allows it (kernel_variant 3 keeps the element-wise kernel, for comparison)
+  if (kind == KernelKind::TRANSPOSE && tuning.kernel_variant != 3) {
+    bool ok = !canon.empty();
+    for (size_t i = 0; i < canon.size(); ++i)
+      if (!transposeVecOk(transposeAxesOf(canon[i]), *live[i], es)) ok = false;
+    if (ok) kind = KernelKind::TRANSPOSE_VEC;
+  }
+
   uint32_t tile_bytes = static_cast<uint32_t>(tuning.tile_bytes > 0 ? tuning.tile_bytes : kDefaultTileBytes);
   tile_bytes = std::min<uint32_t>(std::max<uint32_t>(tile_bytes, kMinTileBytes), kMaxTileBytes);
 
@@ -107,20 +150,16 @@ std::vector<PreparedLaunch> prepareLaunches(const std::vector<LaunchBox>& boxes,
         }
         fillRowCopy(kb, c, es, V, tile_bytes, kind == KernelKind::ROWCOPY_BULK);
       } else {
-        // axis 0: contiguous in the source; axis 1: contiguous in the destination when there is one
-        int a1 = c.dstUnitAxis();
-        if (a1 <= 0) a1 = (c.nd > 1) ? 1 : -1;
-        int a2 = -1;
-        for (int k = 1; k < c.nd; ++k)
-          if (k != a1) a2 = k;
-        const int map[3] = {0, a1, a2};
+        const TransAxes t = transposeAxesOf(c);
         for (int k = 0; k < 3; ++k) {
-          kb.n[k] = (map[k] >= 0) ? c.n[map[k]] : 1;
-          kb.ss[k] = (map[k] >= 0) ? c.ss[map[k]] : 0;
-          kb.ds[k] = (map[k] >= 0) ? c.ds[map[k]] : 0;
+          kb.n[k] = t.n[k];
+          kb.ss[k] = t.ss[k];
+          kb.ds[k] = t.ds[k];
         }
-        kb.tiles0 = static_cast<uint32_t>((kb.n[0] + 31) / 32);
-        kb.tiles1 = static_cast<uint32_t>((kb.n[1] + 31) / 32);
+        int e0 = 32, e1 = 32;
+        if (kind == KernelKind::TRANSPOSE_VEC) transVecTileExtents(es, e0, e1);
+        kb.tiles0 = static_cast<uint32_t>((kb.n[0] + e0 - 1) / e0);
+        kb.tiles1 = static_cast<uint32_t>((kb.n[1] + e1 - 1) / e1);
         const int64_t tiles = static_cast<int64_t>(kb.tiles0) * kb.tiles1 * kb.n[2];
         if (tiles > 0x7fffffff) THROW_NOT_SUPPORTED("box too large for one launch");
         kb.tiles = static_cast<uint32_t>(tiles);
@@ -170,14 +209,16 @@ bool preparePhased(const std::vector<std::vector<LaunchBox>>& push, const std::v
   const int V = static_cast<int>(a);
 
   out->boxes.clear();
+  out->segs.clear();
   out->phases.clear();
   out->npush_phases = static_cast<uint32_t>(K);
   out->vec_size = V;
   out->total_slots = 0;
   for (auto& items : phase) {
     PhaseDesc pd{};
-    pd.first_box = static_cast<uint32_t>(out->boxes.size());
-    pd.nboxes = static_cast<uint32_t>(items.size());
+    pd.first_seg = static_cast<uint32_t>(out->segs.size());
+    // segments of the phase, box by box; interleaved below so that neighbouring slots belong to different boxes
+    std::vector<std::vector<SegDesc>> per_box;
     for (auto& it : items) {
       KBox kb;
       std::memset(&kb, 0, sizeof(kb));
@@ -190,11 +231,29 @@ bool preparePhased(const std::vector<std::vector<LaunchBox>>& push, const std::v
       }
       fillRowCopy(kb, it.c, es, V, tile_bytes, false);
       kb.pad_ = static_cast<uint32_t>(it.wait + 1);
-      pd.max_tiles = std::max(pd.max_tiles, kb.tiles);
+      const uint32_t box_index = static_cast<uint32_t>(out->boxes.size());
       out->boxes.push_back(kb);
+      std::vector<SegDesc> segs;
+      for (uint32_t j0 = 0; j0 < kb.tiles; j0 += kSegTiles) {
+        const uint32_t cnt = std::min(kSegTiles, kb.tiles - j0);
+        segs.push_back({box_index, j0, cnt, kb.pad_});
+        pd.seg_tiles = std::max(pd.seg_tiles, cnt);
+      }
+      per_box.push_back(std::move(segs));
     }
-    if (static_cast<uint64_t>(pd.nboxes) * pd.max_tiles > 0xffffffffull) THROW_NOT_SUPPORTED("launch too large");
-    out->total_slots += static_cast<uint64_t>(pd.nboxes) * pd.max_tiles;
+    // round robin over the boxes: segment q of every box before segment q + 1 of any
+    for (size_t q = 0;; ++q) {
+      bool any = false;
+      for (auto& segs : per_box)
+        if (q < segs.size()) {
+          out->segs.push_back(segs[q]);
+          any = true;
+        }
+      if (!any) break;
+    }
+    pd.nsegs = static_cast<uint32_t>(out->segs.size()) - pd.first_seg;
+    if (static_cast<uint64_t>(pd.nsegs) * pd.seg_tiles > 0xffffffffull) THROW_NOT_SUPPORTED("launch too large");
+    out->total_slots += static_cast<uint64_t>(pd.nsegs) * pd.seg_tiles;
     out->phases.push_back(pd);
   }
   return true;

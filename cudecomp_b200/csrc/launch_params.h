@@ -44,6 +44,7 @@ std::vector<PreparedLaunch> prepareLaunches(const std::vector<LaunchBox>& boxes,
 // Tables of a phased launch (kernels.h PhasedParams), host copies.
 struct PhasedLaunch {
   std::vector<KBox> boxes;
+  std::vector<SegDesc> segs;
   std::vector<PhaseDesc> phases;
   uint32_t npush_phases = 0;
   int vec_size = 16;

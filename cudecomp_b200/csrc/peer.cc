@@ -296,7 +296,7 @@ void Mailbox::exchange(int channel, const std::vector<int>& members, int my_inde
         sched_yield();
         if ((spins & 1023) == 0) {
           if (t0 == 0) t0 = nowSeconds();
-          if (nowSeconds() - t0 > timeout_s_)
+          if (timeout_s_ > 0 && nowSeconds() - t0 > timeout_s_)
             THROW_INTERNAL_ERROR("timed out waiting for rank " + std::to_string(members[i]) +
                                  " to enter the same collective call");
         }

@@ -120,7 +120,10 @@ private:
   int me_ = 0;
   uint64_t seq_[2] = {0, 0};
   std::string name_;
-  double timeout_s_ = 120.0;
+  // A rank that arrives late (checkpoint I/O, load imbalance) is waited for, like the reference's MPI / NCCL backends
+  // do. CUDECOMP_B200_HOST_TIMEOUT=<seconds> turns a longer wait into INTERNAL_ERROR (a debugging aid for mismatched
+  // call sequences, which otherwise hang).
+  double timeout_s_ = 0.0;
 };
 
 // Device-side flag pages (see kernels.h). One arena per handle, exported/imported ONCE: CUDA IPC hands out one

@@ -163,6 +163,79 @@ void walkTranspose(const CopyParams& p, int grid, Walk& w) {
   }
 }
 
+// transposeVecKernel<T, order>: micro-tiles transposed in registers, swizzled shared tile of 16-byte vectors
+void walkTransposeVec(const CopyParams& p, int grid, Walk& w) {
+  const int T = static_cast<int>(p.elem_size);
+  const int VEC = 16 / T;
+  int E0, E1;
+  transVecTileExtents(T, E0, E1);
+  const uint32_t C0 = E0 / VEC, G1 = E1 / VEC, NM = C0 * G1 / 256;
+  const uint32_t total = p.nboxes * p.max_tiles;
+  std::vector<char> tile(1024 * 16);
+  std::vector<char> filled(1024);
+  for (uint32_t cta = 0; cta < static_cast<uint32_t>(grid); ++cta) {
+    for (uint32_t t = cta; t < total; t += grid) {
+      uint32_t b, j;
+      slotToBoxTile(t, p.nboxes, p.max_tiles, p.peer_order, b, j);
+      if (b >= p.nboxes) throw Fail("slot decodes to a box that does not exist");
+      const KBox& bx = p.box[b];
+      if (j >= bx.tiles) continue;
+      if (bx.ss[0] != 1 || bx.ds[1] != 1) throw Fail("vectorised transpose needs unit strides on its contiguous axes");
+      const TransTile tt = decodeTransposeTile(bx, j);
+      const int64_t base0 = static_cast<int64_t>(tt.j0) * E0, base1 = static_cast<int64_t>(tt.j1) * E1;
+      const char* s = bx.src + tt.i2 * bx.ss[2] * T;
+      char* d = bx.dst + tt.i2 * bx.ds[2] * T;
+      std::fill(filled.begin(), filled.end(), 0);
+      for (uint32_t tid = 0; tid < 256; ++tid)
+        for (uint32_t q = 0; q < NM; ++q) {
+          const uint32_t m = tid + 256u * q, c = m % C0, g = m / C0;
+          const int64_t i0 = base0 + c * VEC;
+          char in[4][16];
+          bool have[4] = {false, false, false, false};
+          for (int k = 0; k < VEC; ++k) {
+            const int64_t i1 = base1 + g * VEC + k;
+            std::memset(in[k], 0, 16);
+            if (i0 < bx.n[0] && i1 < bx.n[1]) {
+              const char* src = s + (i0 + i1 * bx.ss[1]) * T;
+              if (reinterpret_cast<uintptr_t>(src) % 16) throw Fail("misaligned 16-byte load");
+              w.ranges.check(src, 16, "load");
+              std::memcpy(in[k], src, 16);
+              have[k] = true;
+            }
+          }
+          for (int e = 0; e < VEC; ++e) {
+            char out[16];
+            bool all = true;
+            for (int k = 0; k < VEC; ++k) {
+              std::memcpy(out + k * T, in[k] + e * T, T);
+              all = all && have[k];
+            }
+            const uint32_t slot = transVecSlot(c * VEC + e, g, VEC, G1);
+            if (slot >= 1024) throw Fail("shared tile index out of range");
+            if (filled[slot] & 2) throw Fail("shared tile vector written twice");
+            std::memcpy(&tile[slot * 16], out, 16);
+            filled[slot] = static_cast<char>(2 | (all ? 1 : 0));
+          }
+        }
+      for (uint32_t tid = 0; tid < 256; ++tid)
+        for (uint32_t pass = 0; pass < static_cast<uint32_t>(VEC) * NM; ++pass) {
+          const uint32_t n = tid + 256u * pass, v = n % G1, row = n / G1;
+          const int64_t i0 = base0 + row, i1 = base1 + static_cast<int64_t>(v) * VEC;
+          if (i0 < bx.n[0] && i1 < bx.n[1]) {
+            const uint32_t slot = transVecSlot(row, v, VEC, G1);
+            if (!(filled[slot] & 1)) throw Fail("transpose tile vector read before it was completely written");
+            char* dst = d + (i0 * bx.ds[0] + i1) * T;
+            if (reinterpret_cast<uintptr_t>(dst) % 16) throw Fail("misaligned 16-byte store");
+            w.ranges.check(dst, 16, "store");
+            std::memcpy(dst, &tile[slot * 16], 16);
+            w.bytes_written += 16;
+            ++w.accesses;
+          }
+        }
+    }
+  }
+}
+
 // rowCopyBulkKernel: one thread per CTA, one bulk copy per slot
 void walkBulk(const CopyParams& p, int grid, Walk& w) {
   const uint32_t total = p.nboxes * p.max_tiles;
@@ -232,12 +305,12 @@ extern "C" int cdb_emu_run_boxes(const cudecompB200Box_t* boxes, const int32_t* 
     int64_t kinds = 0, slots = 0, longest_row = 0;
     for (auto& l : launches) {
       const CopyParams& p = l.params;
-      if (l.kind != KernelKind::TRANSPOSE)
+      if (l.kind != KernelKind::TRANSPOSE && l.kind != KernelKind::TRANSPOSE_VEC)
         for (uint32_t b = 0; b < p.nboxes; ++b)
           longest_row = std::max<int64_t>(longest_row, static_cast<int64_t>(p.box[b].row_vecs) * p.vec_size);
       const uint64_t total = static_cast<uint64_t>(p.nboxes) * p.max_tiles;
       slots += static_cast<int64_t>(total);
-      const int dflt = (l.kind == KernelKind::ROWCOPY) ? 370 : (l.kind == KernelKind::TRANSPOSE ? 592 : 148);
+      const int dflt = (l.kind == KernelKind::ROWCOPY) ? 370 : (l.kind == KernelKind::ROWCOPY_BULK ? 148 : 592);
       const int g = chooseGrid(grid, dflt, 1 << 20, total, 0);
       if (l.kind == KernelKind::ROWCOPY) {
         kinds |= 1;
@@ -245,6 +318,9 @@ extern "C" int cdb_emu_run_boxes(const cudecompB200Box_t* boxes, const int32_t* 
       } else if (l.kind == KernelKind::TRANSPOSE) {
         kinds |= 2;
         walkTranspose(p, g, w);
+      } else if (l.kind == KernelKind::TRANSPOSE_VEC) {
+        kinds |= 8;
+        walkTransposeVec(p, g, w);
       } else {
         kinds |= 4;
         walkBulk(p, g, w);
@@ -278,13 +354,19 @@ void walkPhasedSelection(const PhasedLaunch& pl, int es, int lag, int want_unpac
   const int V = pl.vec_size;
   for (uint32_t s = 0; s < pl.phases.size(); ++s) {
     const PhaseDesc& ph = pl.phases[s];
-    const uint32_t total = ph.nboxes * ph.max_tiles;
+    const uint32_t total = ph.nsegs * ph.seg_tiles;
     for (uint32_t cta = 0; cta < static_cast<uint32_t>(grid); ++cta)
       for (uint32_t t = cta; t < total; t += grid) {
-        const uint32_t b = t % ph.nboxes, j = t / ph.nboxes;
-        const KBox& bx = pl.boxes[ph.first_box + b];
-        if (j >= bx.tiles) continue;
-        const int need = static_cast<int>(bx.pad_) - 1;
+        if (ph.first_seg + t % ph.nsegs >= pl.segs.size()) throw Fail("slot decodes to a segment that does not exist");
+        const SegDesc& sg = pl.segs[ph.first_seg + t % ph.nsegs];
+        const uint32_t jj = t / ph.nsegs;
+        if (jj >= sg.count) continue;
+        if (sg.box >= pl.boxes.size()) throw Fail("segment of a box that does not exist");
+        const KBox& bx = pl.boxes[sg.box];
+        const uint32_t j = sg.first_tile + jj;
+        if (j >= bx.tiles) throw Fail("segment reaches past the last tile of its box");
+        if (sg.wait != bx.pad_) throw Fail("segment and box disagree on the dependency");
+        const int need = static_cast<int>(sg.wait) - 1;
         if (need >= 0) {
           if (static_cast<int>(s) != need + lag) throw Fail("unpack box in the wrong phase");
           if (need >= static_cast<int>(pl.npush_phases)) throw Fail("unpack box waits for a step that is never published");

@@ -205,7 +205,7 @@ def test_schedule_knobs_validate_their_arguments(handle):
     assert cd.set_schedule(handle, gd, 1 << 20, 0, False) == INV   # above 256 KiB
     assert cd.set_schedule(handle, gd, 0, 2, False) == INV
     assert cd.set_schedule(None, gd, 0, 0, False) == INV
-    assert cd.set_kernel_variant(handle, gd, 2) == 0 and cd.set_kernel_variant(handle, gd, 3) == INV
+    assert cd.set_kernel_variant(handle, gd, 3) == 0 and cd.set_kernel_variant(handle, gd, 4) == INV
     assert cd.set_pipeline_chunks(handle, gd, 65) == INV
     assert cd.set_pipeline_chunks(handle, gd, 8) == 0
     cd.cudecompGridDescDestroy(handle, gd)

@@ -55,6 +55,20 @@ FOUR = C.transpose_baseline((2, 2)) + C.transpose_coverage_2x2() + C.halo_baseli
              halo=[0, 6, 0], periods=[True] * 3, expect=1, fills=["pattern"], dims=[1]),
         dict(kind="transpose", name="FewCtas_XY", gdims=[40, 36, 44], pdims=[2, 2], dtype="double", op="XY",
              out_of_place=True, grid_ctas=3),
+        # extents that keep every row 16-byte aligned: the vectorised transpose kernel (transposeVecKernel) runs
+        dict(kind="transpose", name="VecTranspose_float_axis_contiguous_oop", gdims=[136, 72, 64], pdims=[2, 2],
+             dtype="float", ops=["XY", "YZ", "ZY", "YX"], out_of_place=True, axis_contiguous=[True] * 3),
+        dict(kind="transpose", name="VecTranspose_double_axis_contiguous_inplace", gdims=[64, 72, 136], pdims=[2, 2],
+             dtype="double", ops=["XY", "YZ", "ZY", "YX"], axis_contiguous=[True] * 3),
+        dict(kind="transpose", name="VecTranspose_c128_mem_order_halo", gdims=[48, 64, 40], pdims=[2, 2],
+             dtype="double_complex", ops=["XY", "YZ", "ZY", "YX"], out_of_place=True,
+             mem_order=[[1, 2, 0], [2, 0, 1], [0, 1, 2]],
+             halos={"0": [1, 1, 1], "1": [1, 1, 1], "2": [1, 1, 1]}),
+        dict(kind="transpose", name="VecTranspose_float_halo4_pairwise", gdims=[72, 64, 48], pdims=[4, 1], dtype="float",
+             ops=["XY", "YZ", "ZY", "YX"], out_of_place=True, axis_contiguous=[True] * 3, peer_order=1,
+             halos={"0": [4, 4, 4], "1": [4, 4, 4], "2": [4, 4, 4]}),
+        dict(kind="transpose", name="ElementwiseTranspose_variant3_float", gdims=[136, 72, 64], pdims=[2, 2],
+             dtype="float", ops=["XY", "YZ", "ZY", "YX"], out_of_place=True, axis_contiguous=[True] * 3, kernel_variant=3),
         dict(kind="autotune", name="AutotuneTransposeGrid", gdims=[24, 20, 28], dtype="double", n_trials=2),
         dict(kind="autotune", name="AutotuneTransposeBackend", gdims=[24, 20, 28], dtype="float_complex",
              autotune_backend=True, n_trials=1),

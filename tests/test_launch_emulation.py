@@ -78,6 +78,54 @@ def test_emulated_transposes_with_long_rows_equal_oracle(d, s):
     check_transposes(d, s)
 
 
+@st.composite
+def vector_transpose_decompositions(draw):
+    """Permuting layouts whose extents keep every row 16-byte aligned: what the vectorised transpose kernel takes."""
+    pd = draw(st.sampled_from([(1, 1), (1, 2), (2, 1), (2, 2), (4, 1), (1, 4)]))
+    gdims = [draw(st.sampled_from([8, 16, 32, 48, 64, 72, 136])) for _ in range(3)]
+    layout = draw(st.sampled_from(["axis_contiguous", "explicit"]))
+    ac, mo = [False] * 3, None
+    if layout == "axis_contiguous":
+        ac = [True, True, draw(st.booleans())]
+    else:
+        mo = [draw(st.sampled_from([(0, 1, 2), (1, 2, 0), (2, 0, 1), (1, 0, 2), (2, 1, 0), (0, 2, 1)])) for _ in range(3)]
+    zero = {str(a): [0, 0, 0] for a in range(3)}
+    halos = zero if draw(st.booleans()) else {str(a): [4 * draw(st.integers(0, 1)) for _ in range(3)] for a in range(3)}
+    return dict(gdims=gdims, pdims=list(pd), axis_contiguous=ac, mem_order=mo, gdims_dist=None, col_major=False,
+                halos=halos, pads=zero)
+
+
+@settings(max_examples=max(EXAMPLES // 2, 30), deadline=None, suppress_health_check=list(HealthCheck))
+@given(vector_transpose_decompositions(), st.sampled_from([4, 8, 16]), st.sampled_from([0, 1, 5, 64]), st.sampled_from([0, 1]))
+def test_emulated_vectorised_transposes_equal_oracle(d, es, grid, peer_order):
+    s = dict(es=es, tile_bytes=0, peer_order=peer_order, kernel_variant=0, grid=grid, threads=256, misalign=0)
+    check_transposes(d, s)
+
+
+def test_vectorised_transpose_is_selected_and_falls_back():
+    """Aligned permuting boxes take the 16-byte kernel (kind bit 8); odd extents, misaligned buffers and kernel variant 3
+    keep the element-wise one (bit 2) -- with identical results (checked by the property tests above)."""
+    zero = {str(a): [0, 0, 0] for a in range(3)}
+
+    def kinds(gdims, es, misalign=0, variant=0):
+        d = dict(gdims=gdims, pdims=[2, 1], axis_contiguous=[True] * 3, mem_order=None, gdims_dist=None, col_major=False,
+                 halos=zero, pads=zero)
+        cfg, o = make_config(d), make_oracle(d)
+        dt = DT[es]
+        ins = [emu.aligned_array(o.pencil_info(r, 0).size, dt, misalign) for r in range(2)]
+        outs = [emu.aligned_array(o.pencil_info(r, 1).size, dt, misalign) for r in range(2)]
+        push = cd.plan_transpose_boxes(cfg, 0, 0, 1)
+        return emu.run_boxes(push, [ins[0]] * len(push), [outs[bx["peer_rank"]] for bx in push], es, ins + outs,
+                             kernel_variant=variant, me=0, comm_size=2, peer_index=[0, 1])["kinds"]
+
+    for es in (4, 8, 16):
+        assert kinds([64, 32, 16], es) == 8
+        assert kinds([64, 32, 16], es, variant=3) == 2
+    assert kinds([62, 30, 16], 4) == 2   # extents that are not multiples of 4 elements
+    assert kinds([64, 32, 16], 4, misalign=4) == 2
+    assert kinds([64, 32, 16], 16, misalign=16) == 8  # 16-byte elements are always aligned
+
+
 def check_transposes(d, s):
     cfg, o = make_config(d), make_oracle(d)
     n = o.nranks
@@ -282,10 +330,12 @@ def test_kernel_selection_and_vector_width():
     assert run(16, 2)["vec"] == 32         # variant 2: 256-bit accesses, everything here is 32-byte aligned
     assert run(16, 2, misalign=16)["vec"] == 16  # ... unless a buffer is only 16-byte aligned
     assert run(16, 1)["accesses"] == 2 * 4 * 6   # one bulk copy per row segment: 2 peers x (4 x 6) rows of my pencil
-    # axis-contiguous layouts permute: the tiled transpose kernel
+    # axis-contiguous layouts permute: the tiled transpose kernels (16-byte accesses when rows are aligned, bit 8)
     d2 = dict(d, axis_contiguous=[True] * 3)
     cfg2, o2 = make_config(d2), make_oracle(d2)
-    assert run(8, 0, dd=d2, cfg_=cfg2, o_=o2)["kinds"] == 2
+    assert run(8, 0, dd=d2, cfg_=cfg2, o_=o2)["kinds"] == 8
+    assert run(8, 3, dd=d2, cfg_=cfg2, o_=o2)["kinds"] == 2
+    assert run(8, 0, misalign=8, dd=d2, cfg_=cfg2, o_=o2)["kinds"] == 2
 
 
 def test_contiguous_axes_are_merged_into_long_rows():
