@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--staged-mode", type=int, default=0, help="0 one phased launch per staged transpose, 1 separate launches")
     ap.add_argument("--lag", type=int, default=0, help="phases between a chunk's push and its unpack (0 = library default)")
     ap.add_argument("--kernel-variant", type=int, default=0, help="cudecompB200SetKernelVariant value (3 = element-wise transpose)")
+    ap.add_argument("--no-wire-wide", action="store_true", help="128-bit accesses also in launches that store into peers")
+    ap.add_argument("--phase-head", type=int, default=-1, help="percent of a step's pushes ahead of the unpacks (fused staged)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed integer-pattern check after the timed region")
     ap.add_argument("--tile-bytes", type=int, default=0, help="row-copy tile size (0 = 32 KiB)")
     ap.add_argument("--peer-order", type=int, default=0, help="0 one-shot interleaved, 1 pairwise rounds")
@@ -287,6 +289,10 @@ def run_native(args, rank, world, local_rank):
                "double_complex": cd.CUDECOMP_DOUBLE_COMPLEX}[args.dtype]
     es = cd.DTYPE_SIZES[dt_enum]
 
+    if args.no_wire_wide:
+        os.environ["CUDECOMP_B200_WIRE_WIDE"] = "0"
+    if args.phase_head >= 0:
+        os.environ["CUDECOMP_B200_PHASE_HEAD"] = str(args.phase_head)
     assert cd.MPI_Init() == 0
     res, handle = cd.cudecompInit(cd.MPI_COMM_WORLD)
     cd.check(res, "cudecompInit")

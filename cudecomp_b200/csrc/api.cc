@@ -274,6 +274,8 @@ static void initHandle(cudecompHandle_t h, const CommPtr& parent) {
   if (const char* v = std::getenv("CUDECOMP_B200_TRANSFER")) h->pull_mode = (std::strcmp(v, "pull") == 0) ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_STAGED")) h->staged_mode = (std::strcmp(v, "launches") == 0) ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_FUSED_LAG")) h->fused_lag = std::min(8, std::max(1, std::atoi(v)));
+  if (const char* v = std::getenv("CUDECOMP_B200_PHASE_HEAD")) h->phase_head_percent = std::min(90, std::max(0, std::atoi(v)));
+  if (const char* v = std::getenv("CUDECOMP_B200_WIRE_WIDE")) h->wire_wide = std::atoi(v) != 0 ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_DIRECT")) h->allow_direct = std::strcmp(v, "0") != 0;
   double spin_s = 60.0;
   if (const char* v = std::getenv("CUDECOMP_B200_DEVICE_TIMEOUT")) spin_s = std::atof(v);
@@ -381,6 +383,8 @@ cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudeco
   gd->pull_mode = handle->pull_mode;
   gd->staged_mode = handle->staged_mode;
   gd->fused_lag = handle->fused_lag;
+  gd->phase_head_percent = handle->phase_head_percent;
+  gd->wire_wide = handle->wire_wide;
   if (gd->config.rank_order == CUDECOMP_RANK_ORDER_DEFAULT)
     gd->config.rank_order = handle->env_col_major ? CUDECOMP_RANK_ORDER_COL_MAJOR : CUDECOMP_RANK_ORDER_ROW_MAJOR;
 

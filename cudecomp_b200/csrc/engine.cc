@@ -20,6 +20,10 @@ int64_t dtypeSize(cudecompDataType_t dtype) {
   THROW_INVALID_USAGE("unknown data type");
 }
 
+// Epochs one collective call owns: (epoch - stride, epoch]. Single-launch paths use the last one, the chunked
+// separate-launch schedule one per step. A function of the descriptor's settings only, never of the path taken.
+uint64_t epochStride(const cudecompGridDesc_t gd) { return static_cast<uint64_t>(std::max(1, gd->pipeline_chunks)); }
+
 int autoFusedChunks(int64_t pencil_bytes) {
   const int64_t k = pencil_bytes / (int64_t(8) << 20);
   return static_cast<int>(std::min<int64_t>(std::max<int64_t>(k, 1), 16));
@@ -106,6 +110,9 @@ void launchBoxes(cudecompGridDesc_t gd, const std::vector<ResolvedBox>& boxes, i
   tuning.tile_bytes = gd->tile_bytes;
   tuning.peer_order = gd->peer_order;
   tuning.kernel_variant = gd->kernel_variant;
+  // Launches that store into peers: 256-bit accesses where the alignment allows (measured on B200, profiles/
+  // r2_n2_schedules.md: +3 % on the wire; local HBM-bound copies are 8 % SLOWER with them and keep 128-bit accesses)
+  if (tuning.kernel_variant == 0 && sync.npeers > 0 && gd->wire_wide) tuning.kernel_variant = 2;
   std::vector<PreparedLaunch> launches = prepareLaunches(boxes, es, tuning, me, comm_size);
 
   LaunchConfig cfg;
@@ -161,8 +168,9 @@ uint32_t haloOpcode(int ax, int dim) { return 0x200u + static_cast<uint32_t>(ax)
 // Chunked schedule of the staged path (plan.h PipelinedPlan): K push launches on the caller's stream, each with its
 // own handshake epoch; the unpack pieces that become writable after push s run on a side stream beside push s+1.
 // The caller's stream rejoins the side stream at the end, so stream semantics are unchanged. Returns false when
-// chunking does not apply (the caller then runs the unchunked schedule). Every rank of the job takes the same
-// decision and advances the epoch by the same amount: it only depends on the geometry and on K.
+// chunking does not apply (the caller then runs the unchunked schedule). The steps use the sub-epochs the call owns
+// (epochStride): the descriptor's epoch itself advances by the same amount on every rank whichever path a row or column
+// group takes (the path depends on that group's buffers, the epoch is shared by both communicators).
 bool runPipelinedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, void* input, void* output, void* work,
                         int es, const int32_t in_halo[], const int32_t out_halo[], const int32_t in_pad[],
                         const int32_t out_pad[], bool inplace, const std::vector<CallMsg>& msgs,
@@ -184,9 +192,10 @@ bool runPipelinedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int d
   SyncParams nosync;
   std::memset(&nosync, 0, sizeof(nosync));
   bool used_side = false;
+  const uint64_t first_epoch = gd->epoch - epochStride(gd) + 1; // K <= stride
   for (size_t s = 0; s < K; ++s) {
-    if (s > 0) gd->epoch++; // the first step uses the epoch the call was given
     SyncParams sync = makeSync(gd, peers);
+    sync.epoch = first_epoch + s;
     // Peers only have to be met on the way in once per call: after step 0 everybody is inside this operation and the
     // chunks land in disjoint parts of the workspace. The way out is needed per step (unpack(s) reads what peers pushed).
     if (s > 0) sync.do_entry = 0;
@@ -250,7 +259,8 @@ bool runFusedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, 
   std::string key;
   auto put = [&](const void* p, size_t n) { key.append(static_cast<const char*>(p), n); };
   const int32_t zero3[3] = {0, 0, 0};
-  const int32_t head[8] = {ax, dir, es, K, lag, gd->tile_bytes, inplace ? 1 : 0, P};
+  const int32_t head[10] = {ax, dir, es, K, lag, gd->tile_bytes, inplace ? 1 : 0, P, gd->phase_head_percent,
+                            gd->kernel_variant * 2 + gd->wire_wide};
   put(head, sizeof(head));
   put(&input, sizeof(input));
   put(&output, sizeof(output));
@@ -284,6 +294,8 @@ bool runFusedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, 
     }
     LaunchTuning tuning;
     tuning.tile_bytes = gd->tile_bytes;
+    tuning.phase_head_percent = gd->phase_head_percent;
+    tuning.kernel_variant = (gd->kernel_variant == 2 || (gd->kernel_variant == 0 && gd->wire_wide)) ? 2 : 0;
     PhasedLaunch pl;
     if (!preparePhased(push, unpack, es, tuning, lag, &pl))
       THROW_INTERNAL_ERROR("staged schedule with equal memory orders is not a row copy");
@@ -305,7 +317,7 @@ bool runFusedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, 
     e.params.segs = reinterpret_cast<const SegDesc*>(static_cast<char*>(e.dev) + box_bytes);
     e.params.phases = reinterpret_cast<const PhaseDesc*>(static_cast<char*>(e.dev) + box_bytes + seg_bytes);
     e.params.nphases = static_cast<uint32_t>(pl.phases.size());
-    e.params.npush_phases = pl.npush_phases;
+    e.params.nsteps = pl.nsteps;
     e.params.elem_size = static_cast<uint32_t>(es);
     e.params.vec_size = static_cast<uint32_t>(pl.vec_size);
     e.total_slots = pl.total_slots;
@@ -328,7 +340,7 @@ bool runFusedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, 
 void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, void* input, void* output, void* work,
                   cudecompDataType_t dtype, const int32_t in_halo[], const int32_t out_halo[], const int32_t in_pad[],
                   const int32_t out_pad[], cudaStream_t stream) {
-  gd->epoch++; // one epoch per collective call, advanced identically on every rank
+  gd->epoch += epochStride(gd); // advanced identically on every rank, whatever path the call takes
   const int es = static_cast<int>(dtypeSize(dtype));
   const bool inplace = (input == output);
 
@@ -479,7 +491,7 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
 
 void runHalo(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, void* input, void* work, cudecompDataType_t dtype,
              const int32_t halo[], const bool periods[], int dim, const int32_t pad[], cudaStream_t stream) {
-  gd->epoch++;
+  gd->epoch += epochStride(gd);
   const int es = static_cast<int>(dtypeSize(dtype));
 
   // Make the "halo wider than a neighbour's slab" error collective: the reference raises it only on the

@@ -66,7 +66,9 @@ struct cudecompHandle {
   int balance_grid = 0;          // CUDECOMP_B200_BALANCE_GRID=1
   int pull_mode = 0;             // CUDECOMP_B200_TRANSFER=pull
   int staged_mode = 0;           // CUDECOMP_B200_STAGED=launches -> 1 (separate push / unpack launches)
-  int fused_lag = 2;             // CUDECOMP_B200_FUSED_LAG
+  int fused_lag = 1;             // CUDECOMP_B200_FUSED_LAG
+  int phase_head_percent = 25;   // CUDECOMP_B200_PHASE_HEAD
+  int wire_wide = 1;             // CUDECOMP_B200_WIRE_WIDE=0: 128-bit accesses on the wire too
   uint64_t release_count = 0;    // buffers freed through cudecompFree so far
   uint64_t released[cdb::kReleaseSlots] = {0}; // ids of the most recent ones, newest first
 };
@@ -101,7 +103,9 @@ struct cudecompGridDesc {
   // unpacks chunk s - lag (kernels.h PhasedParams; the default), 1 = separate launches (push, unpack; chunked: K pushes
   // on the caller's stream, unpacks on a side stream).
   int staged_mode = 0;
-  int fused_lag = 2;
+  int fused_lag = 1;
+  int wire_wide = 1;           // 256-bit accesses in launches that store into peers (kernel_variant 0 only)
+  int phase_head_percent = 25; // share of a step's pushes that runs before the unpacks of the earlier chunk join in
   std::vector<cdb::FusedPlanEntry> fused_cache; // device tables of phased launches, keyed by everything they depend on
 };
 
@@ -111,6 +115,7 @@ namespace cdb {
 int autoFusedChunks(int64_t pencil_bytes);
 
 void releaseFusedCache(cudecompGridDesc_t gd);
+uint64_t epochStride(const cudecompGridDesc_t gd);
 
 void setGeometry(cudecompGridDesc_t gd, const std::array<int32_t, 2>& pdims);
 

@@ -87,9 +87,9 @@ __device__ __forceinline__ bool syncEntry(const SyncParams& s) {
 __device__ __forceinline__ void syncExit(const SyncParams& s) {
   if (s.my_pad == nullptr || s.npeers == 0 || !s.do_exit) return;
   __shared__ uint32_t is_last;
-  __threadfence_system(); // my stores (local and peer) are performed before anything that follows
-  __syncthreads();
+  __syncthreads(); // every warp's stores (local and peer) are issued ...
   if (threadIdx.x == 0) {
+    __threadfence_system(); // ... and performed before the count below (the barrier makes the fence cover the whole CTA)
     unsigned long long* ctr = reinterpret_cast<unsigned long long*>(s.my_pad + kPadCounter);
     const unsigned long long old = atomicAdd(ctr, 1ull);
     is_last = (old == static_cast<unsigned long long>(gridDim.x) - 1ull) ? 1u : 0u;
@@ -217,7 +217,6 @@ template <typename V, int kOrder> __global__ void __launch_bounds__(256) rowCopy
 __device__ __forceinline__ uint64_t stepKey(uint64_t epoch, uint32_t step) { return (epoch << 8) | (step + 1u); }
 
 template <typename V> __global__ void __launch_bounds__(256) rowCopyPhasedKernel(const __grid_constant__ PhasedParams p) {
-  __shared__ uint32_t sh_last;
   const SyncParams& sy = p.sync;
   if (!syncEntry(sy)) return;
   unsigned long long* counters = reinterpret_cast<unsigned long long*>(sy.my_pad + kPadPhaseCounter);
@@ -247,20 +246,19 @@ template <typename V> __global__ void __launch_bounds__(256) rowCopyPhasedKernel
       }
       copyRowTile<V>(bx, j, p.elem_size);
     }
-    if (s < p.npush_phases) {
-      // my share of this phase is done: fence it, count it; the last CTA tells the peers that chunk s has landed
-      __threadfence_system();
+    if (ph.publish) {
+      // My share of this step's pushes is issued. One thread fences for the CTA (the barrier orders every warp's stores
+      // before it, the fence is cumulative), counts the CTA, and the last CTA of the grid tells the peers that the
+      // chunk has landed; the other warps go straight on to the next phase.
       __syncthreads();
       if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned long long old = atomicAdd(counters + s, 1ull);
-        sh_last = (old == static_cast<unsigned long long>(gridDim.x) - 1ull) ? 1u : 0u;
-      }
-      __syncthreads();
-      if (sh_last) {
+        const uint32_t step = ph.publish - 1u;
         __threadfence_system();
-        if (static_cast<int>(threadIdx.x) < sy.npeers)
-          redMaxReleaseSys(sy.peer_pad[threadIdx.x] + kPadStep + sy.my_world, stepKey(sy.epoch, s));
+        const unsigned long long old = atomicAdd(counters + step, 1ull);
+        if (old == static_cast<unsigned long long>(gridDim.x) - 1ull) {
+          __threadfence_system();
+          for (int i = 0; i < sy.npeers; ++i) redMaxReleaseSys(sy.peer_pad[i] + kPadStep + sy.my_world, stepKey(sy.epoch, step));
+        }
       }
     }
   }
@@ -271,7 +269,7 @@ template <typename V> __global__ void __launch_bounds__(256) rowCopyPhasedKernel
     unsigned long long* ctr = reinterpret_cast<unsigned long long*>(sy.my_pad + kPadCounter);
     const unsigned long long old = atomicAdd(ctr, 1ull);
     if (old == static_cast<unsigned long long>(gridDim.x) - 1ull) {
-      for (uint32_t s = 0; s < p.npush_phases; ++s) counters[s] = 0ull;
+      for (uint32_t s = 0; s < p.nsteps; ++s) counters[s] = 0ull;
       *reinterpret_cast<volatile unsigned long long*>(ctr) = 0ull;
     }
   }
@@ -613,6 +611,7 @@ cudaError_t launchPhased(const PhasedParams& p, uint64_t total_slots, const Laun
   using Fn = void (*)(const PhasedParams);
   Fn fn = nullptr;
   switch (p.vec_size) {
+  case 32: fn = rowCopyPhasedKernel<Vec32>; break;
   case 16: fn = rowCopyPhasedKernel<uint4>; break;
   case 8: fn = rowCopyPhasedKernel<uint2>; break;
   case 4: fn = rowCopyPhasedKernel<uint32_t>; break;

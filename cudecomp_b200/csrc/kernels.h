@@ -96,7 +96,7 @@ struct alignas(16) PhaseDesc {
   uint32_t first_seg;
   uint32_t nsegs;
   uint32_t seg_tiles; // slots of the phase = nsegs * seg_tiles (seg_tiles = longest segment of the phase)
-  uint32_t pad_;
+  uint32_t publish;   // step + 1 whose pushes are complete (on this CTA) at the end of this phase, 0: none
 };
 
 struct PhasedParams {
@@ -105,7 +105,7 @@ struct PhasedParams {
   const PhaseDesc* phases; // device table
   SyncParams sync;         // do_exit is ignored: the last phase's waits subsume the exit handshake
   uint32_t nphases;
-  uint32_t npush_phases;   // phases [0, npush_phases) contain pushes and are published to the peers
+  uint32_t nsteps;         // chunks: steps [0, nsteps) are published to the peers, one counter each
   uint32_t elem_size;
   uint32_t vec_size;
 };

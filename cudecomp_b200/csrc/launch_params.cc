@@ -175,7 +175,7 @@ std::vector<PreparedLaunch> prepareLaunches(const std::vector<LaunchBox>& boxes,
 bool preparePhased(const std::vector<std::vector<LaunchBox>>& push, const std::vector<std::vector<LaunchBox>>& unpack, int es,
                    const LaunchTuning& tuning, int lag, PhasedLaunch* out) {
   const size_t K = push.size();
-  if (K == 0 || unpack.size() != K || lag < 1 || K + static_cast<size_t>(lag) > static_cast<size_t>(kMaxPhases)) return false;
+  if (K == 0 || unpack.size() != K || lag < 1 || K > static_cast<size_t>(kMaxPhases)) return false;
   uint32_t tile_bytes = static_cast<uint32_t>(tuning.tile_bytes > 0 ? tuning.tile_bytes : kDefaultTileBytes);
   tile_bytes = std::min<uint32_t>(std::max<uint32_t>(tile_bytes, kMinTileBytes), kMaxTileBytes);
 
@@ -184,9 +184,9 @@ bool preparePhased(const std::vector<std::vector<LaunchBox>>& push, const std::v
     const LaunchBox* b;
     int wait; // step that must be complete, -1: none
   };
-  std::vector<std::vector<Item>> phase(K + lag);
-  uint64_t a = 16;
-  auto add = [&](const LaunchBox& b, size_t ph, int wait) -> bool {
+  std::vector<std::vector<Item>> pushes(K), unpacks(K);
+  uint64_t a = (tuning.kernel_variant == 2) ? 32 : 16;
+  auto add = [&](const LaunchBox& b, std::vector<Item>& list, int wait) -> bool {
     if (b.d.count() == 0) return true;
     CanonBox c = canonicalize(b.d, true);
     if (c.rowCopy() && c.n[0] * es / std::min(es, 16) >= (1ll << 31)) c = canonicalize(b.d, false);
@@ -196,14 +196,14 @@ bool preparePhased(const std::vector<std::vector<LaunchBox>>& push, const std::v
     a = std::min({a, lowBit(sa), lowBit(da), lowBit(static_cast<uint64_t>(c.n[0]) * es)});
     for (int k = 1; k < 3; ++k)
       if (c.n[k] > 1) a = std::min({a, lowBit(static_cast<uint64_t>(c.ss[k]) * es), lowBit(static_cast<uint64_t>(c.ds[k]) * es)});
-    phase[ph].push_back({c, &b, wait});
+    list.push_back({c, &b, wait});
     return true;
   };
   for (size_t s = 0; s < K; ++s) {
     for (auto& b : push[s])
-      if (!add(b, s, -1)) return false;
+      if (!add(b, pushes[s], -1)) return false;
     for (auto& b : unpack[s])
-      if (!add(b, s + lag, static_cast<int>(s))) return false;
+      if (!add(b, unpacks[s], static_cast<int>(s))) return false;
   }
   if (a < 4) THROW_INVALID_USAGE("buffers must be aligned to the element size");
   const int V = static_cast<int>(a);
@@ -211,13 +211,12 @@ bool preparePhased(const std::vector<std::vector<LaunchBox>>& push, const std::v
   out->boxes.clear();
   out->segs.clear();
   out->phases.clear();
-  out->npush_phases = static_cast<uint32_t>(K);
+  out->nsteps = static_cast<uint32_t>(K);
   out->vec_size = V;
   out->total_slots = 0;
-  for (auto& items : phase) {
-    PhaseDesc pd{};
-    pd.first_seg = static_cast<uint32_t>(out->segs.size());
-    // segments of the phase, box by box; interleaved below so that neighbouring slots belong to different boxes
+
+  // the segments of one box list, box by box
+  auto segmentsOf = [&](const std::vector<Item>& items) {
     std::vector<std::vector<SegDesc>> per_box;
     for (auto& it : items) {
       KBox kb;
@@ -234,27 +233,63 @@ bool preparePhased(const std::vector<std::vector<LaunchBox>>& push, const std::v
       const uint32_t box_index = static_cast<uint32_t>(out->boxes.size());
       out->boxes.push_back(kb);
       std::vector<SegDesc> segs;
-      for (uint32_t j0 = 0; j0 < kb.tiles; j0 += kSegTiles) {
-        const uint32_t cnt = std::min(kSegTiles, kb.tiles - j0);
-        segs.push_back({box_index, j0, cnt, kb.pad_});
-        pd.seg_tiles = std::max(pd.seg_tiles, cnt);
-      }
+      for (uint32_t j0 = 0; j0 < kb.tiles; j0 += kSegTiles) segs.push_back({box_index, j0, std::min(kSegTiles, kb.tiles - j0), kb.pad_});
       per_box.push_back(std::move(segs));
     }
-    // round robin over the boxes: segment q of every box before segment q + 1 of any
-    for (size_t q = 0;; ++q) {
-      bool any = false;
-      for (auto& segs : per_box)
-        if (q < segs.size()) {
-          out->segs.push_back(segs[q]);
-          any = true;
+    return per_box;
+  };
+  // one phase from segment lists: round robin over the boxes (segment q of every box before segment q + 1 of any)
+  auto emitPhase = [&](const std::vector<std::vector<SegDesc>>& a_, size_t a_from, size_t a_to_frac_num, size_t a_to_frac_den,
+                       bool take_tail, const std::vector<std::vector<SegDesc>>* b_, uint32_t publish) {
+    PhaseDesc pd{};
+    pd.first_seg = static_cast<uint32_t>(out->segs.size());
+    pd.publish = publish;
+    size_t longest = 0;
+    for (auto& segs : a_) longest = std::max(longest, segs.size());
+    if (b_)
+      for (auto& segs : *b_) longest = std::max(longest, segs.size());
+    for (size_t q = 0; q < longest; ++q) {
+      for (auto& segs : a_) {
+        // head: segments [0, n * num / den); tail: the rest
+        const size_t cut = segs.size() * a_to_frac_num / a_to_frac_den;
+        const size_t lo = take_tail ? cut : a_from, hi = take_tail ? segs.size() : cut;
+        if (lo + q < hi) {
+          out->segs.push_back(segs[lo + q]);
+          pd.seg_tiles = std::max(pd.seg_tiles, segs[lo + q].count);
         }
-      if (!any) break;
+      }
+      if (b_)
+        for (auto& segs : *b_)
+          if (q < segs.size()) {
+            out->segs.push_back(segs[q]);
+            pd.seg_tiles = std::max(pd.seg_tiles, segs[q].count);
+          }
     }
     pd.nsegs = static_cast<uint32_t>(out->segs.size()) - pd.first_seg;
     if (static_cast<uint64_t>(pd.nsegs) * pd.seg_tiles > 0xffffffffull) THROW_NOT_SUPPORTED("launch too large");
     out->total_slots += static_cast<uint64_t>(pd.nsegs) * pd.seg_tiles;
     out->phases.push_back(pd);
+  };
+
+  // Step s = the pushes of chunk s and the unpacks of chunk s - lag. Unpack tiles wait for chunk s - lag to be complete
+  // on every member; CTAs drift apart by about a tile within a phase, so with a short lag the step opens with a head of
+  // pushes only (head_percent of every push box) and the unpacks join for the rest: by then the slowest CTA anywhere
+  // has long finished the earlier chunk and nobody waits.
+  const int head = std::min(90, std::max(0, tuning.phase_head_percent));
+  std::vector<std::vector<std::vector<SegDesc>>> unpack_segs(K);
+  const std::vector<std::vector<SegDesc>> none;
+  for (size_t s = 0; s < K + static_cast<size_t>(lag); ++s) {
+    const std::vector<std::vector<SegDesc>> ps = (s < K) ? segmentsOf(pushes[s]) : none;
+    if (s < K) unpack_segs[s] = segmentsOf(unpacks[s]);
+    const std::vector<std::vector<SegDesc>>* us = (s >= static_cast<size_t>(lag)) ? &unpack_segs[s - lag] : nullptr;
+    const bool have_unpack = us && !us->empty();
+    const uint32_t publish = (s < K) ? static_cast<uint32_t>(s + 1) : 0u;
+    if (have_unpack && s < K && head > 0) {
+      emitPhase(ps, 0, static_cast<size_t>(head), 100, false, nullptr, 0u);
+      emitPhase(ps, 0, static_cast<size_t>(head), 100, true, us, publish);
+    } else {
+      emitPhase(ps, 0, 1, 1, false, us, publish);
+    }
   }
   return true;
 }

@@ -21,6 +21,7 @@ struct LaunchBox {
 struct LaunchTuning {
   int tile_bytes = 0;     // bytes of a ROWCOPY tile (0: kDefaultTileBytes); power of two in [4 KiB, 256 KiB]
   int peer_order = 0;     // CopyParams::peer_order
+  int phase_head_percent = 25; // phased launches: share of a step's pushes that runs before its unpacks join in
   int kernel_variant = 0; // 1: TMA bulk row copy where every row is 16-byte aligned and at least 2 KiB long;
                           // 2: 256-bit LDG/STG where every address and stride is 32-byte aligned (else 128-bit)
 };
@@ -46,14 +47,14 @@ struct PhasedLaunch {
   std::vector<KBox> boxes;
   std::vector<SegDesc> segs;
   std::vector<PhaseDesc> phases;
-  uint32_t npush_phases = 0;
+  uint32_t nsteps = 0; // chunks (each published to the peers once)
   int vec_size = 16;
   uint64_t total_slots = 0;
 };
 
 // push[s] / unpack[s]: the boxes of step s of a chunked staged schedule (plan.h PipelinedPlan), resolved to base
-// pointers. Phase s of the launch holds push[s] and unpack[s - lag] (which waits for step s - lag), lag >= 1; there are
-// push.size() + lag phases. Returns false when the schedule cannot run as one phased launch (a box that is not a row
+// pointers. Step s of the launch holds push[s] and unpack[s - lag] (which waits for step s - lag), lag >= 1; a step is
+// one phase, or two when a head of pushes runs before the unpacks join (LaunchTuning::phase_head_percent). Returns false when the schedule cannot run as one phased launch (a box that is not a row
 // copy, too many phases); the caller then falls back to separate launches.
 bool preparePhased(const std::vector<std::vector<LaunchBox>>& push, const std::vector<std::vector<LaunchBox>>& unpack, int es,
                    const LaunchTuning& tuning, int lag, PhasedLaunch* out);

@@ -76,7 +76,8 @@ cudecompResult_t cudecompB200SetPipelineChunks(cudecompHandle_t handle, cudecomp
  * ONE phased launch pushes chunk s into the peers' workspaces while it unpacks chunk s - lag from the local one, with
  * per-chunk flags in the signal pad (the chunk count is cudecompB200SetPipelineChunks, 0 = chosen from the pencil size);
  * mode 1: separate push and unpack launches (chunked: unpacks on a side stream). lag in [1, 8], 0 keeps the current
- * value (default 2). Same values on every rank. Also CUDECOMP_B200_STAGED=launches, CUDECOMP_B200_FUSED_LAG. */
+ * value (default 1). Same values on every rank. Also CUDECOMP_B200_STAGED=launches, CUDECOMP_B200_FUSED_LAG, and
+ * CUDECOMP_B200_PHASE_HEAD (percent of a step's pushes that run before the previous chunk's unpacks join, default 25). */
 cudecompResult_t cudecompB200SetStagedMode(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t mode, int32_t lag);
 
 /* Reports (and clears) a device-side handshake timeout of an earlier operation. */

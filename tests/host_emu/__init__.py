@@ -83,7 +83,8 @@ def run_boxes(boxes, srcs, dsts, es, legal, me=-1, comm_size=0, peer_index=None,
                 balanced_grid=stats[6], longest_row=stats[7])
 
 
-def run_phased(boxes, srcs, dsts, es, legal, nsteps, lag, want_unpack, step, tile_bytes=0, grid=0, threads=256):
+def run_phased(boxes, srcs, dsts, es, legal, nsteps, lag, want_unpack, step, tile_bytes=0, grid=0, threads=256,
+               kernel_variant=0, head_percent=25):
     """One rank's fused staged schedule (engine.cc runFusedStaged) prepared by the product's preparePhased; executes the
     push boxes of phase `step` or (want_unpack) the unpack boxes that wait for `step`. Returns the stats dict, or None
     when the schedule cannot run as one phased launch."""
@@ -107,8 +108,8 @@ def run_phased(boxes, srcs, dsts, es, legal, nsteps, lag, want_unpack, step, til
     err = ctypes.create_string_buffer(512)
     fn = lib().cdb_emu_run_phased
     fn.restype = ctypes.c_int
-    rc = fn(arr, n, nsteps, sb, db, lo, ln, len(legal), es, tile_bytes, lag, int(want_unpack), step, grid, threads, stats,
-            err, 512)
+    rc = fn(arr, n, nsteps, sb, db, lo, ln, len(legal), es, tile_bytes, lag, int(want_unpack), step, grid, threads,
+            kernel_variant, head_percent, stats, err, 512)
     if rc < 0:
         raise EmuError(err.value.decode())
     if rc == 1:

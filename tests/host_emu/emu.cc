@@ -367,13 +367,25 @@ void walkPhasedSelection(const PhasedLaunch& pl, int es, int lag, int want_unpac
         if (j >= bx.tiles) throw Fail("segment reaches past the last tile of its box");
         if (sg.wait != bx.pad_) throw Fail("segment and box disagree on the dependency");
         const int need = static_cast<int>(sg.wait) - 1;
+        // the step a phase belongs to = the next publication at or after it (phases behind the last one: drain)
+        int phase_step = static_cast<int>(pl.nsteps);
+        for (size_t q = s; q < pl.phases.size(); ++q)
+          if (pl.phases[q].publish) {
+            phase_step = static_cast<int>(pl.phases[q].publish) - 1;
+            break;
+          }
         if (need >= 0) {
-          if (static_cast<int>(s) != need + lag) throw Fail("unpack box in the wrong phase");
-          if (need >= static_cast<int>(pl.npush_phases)) throw Fail("unpack box waits for a step that is never published");
-        } else if (s >= pl.npush_phases) {
+          if (need >= static_cast<int>(pl.nsteps)) throw Fail("unpack box waits for a step that is never published");
+          // its step must have been published by an EARLIER phase
+          bool published = false;
+          for (size_t q = 0; q < s; ++q)
+            if (static_cast<int>(pl.phases[q].publish) == need + 1) published = true;
+          if (!published) throw Fail("unpack box scheduled before the phase that publishes its step");
+          if (phase_step < static_cast<int>(pl.nsteps) && phase_step != need + lag) throw Fail("unpack box in the wrong step");
+        } else if (phase_step >= static_cast<int>(pl.nsteps)) {
           throw Fail("push box after the last published phase");
         }
-        const bool sel = want_unpack ? (need == step) : (need < 0 && static_cast<int>(s) == step);
+        const bool sel = want_unpack ? (need == step) : (need < 0 && phase_step == step);
         if (!sel) continue;
         const RowTile rt = decodeRowTile(bx, j);
         const uint32_t pieces_per_row = (rt.nvec + kPiece - 1) / kPiece;
@@ -413,7 +425,7 @@ void walkPhasedSelection(const PhasedLaunch& pl, int es, int lag, int want_unpac
 extern "C" int cdb_emu_run_phased(const cudecompB200Box_t* boxes, int nboxes, int nsteps, const void* const* src_bases,
                                   void* const* dst_bases, const char* const* range_lo, const int64_t* range_len, int nranges,
                                   int es, int tile_bytes, int lag, int want_unpack, int step, int grid, int threads,
-                                  int64_t* stats, char* err, int err_len) {
+                                  int kernel_variant, int head_percent, int64_t* stats, char* err, int err_len) {
   try {
     std::vector<std::vector<LaunchBox>> push(nsteps), unpack(nsteps);
     for (int i = 0; i < nboxes; ++i) {
@@ -435,9 +447,12 @@ extern "C" int cdb_emu_run_phased(const cudecompB200Box_t* boxes, int nboxes, in
     }
     LaunchTuning tuning;
     tuning.tile_bytes = tile_bytes;
+    tuning.kernel_variant = kernel_variant;
+    tuning.phase_head_percent = head_percent;
     PhasedLaunch pl;
     if (!preparePhased(push, unpack, es, tuning, lag, &pl)) return 1;
-    if (pl.phases.size() != static_cast<size_t>(nsteps + lag)) throw Fail("wrong number of phases");
+    if (pl.nsteps != static_cast<uint32_t>(nsteps) || pl.phases.size() < static_cast<size_t>(nsteps + lag))
+      throw Fail("wrong number of steps / phases");
     Ranges ranges{range_lo, range_len, nranges};
     Walk w{ranges};
     walkPhasedSelection(pl, es, lag, want_unpack, step, grid > 0 ? grid : 370, threads > 0 ? threads : 256, w);

@@ -294,7 +294,8 @@ def test_emulated_fused_staged_schedule_equals_oracle(d, s, K, inplace, lag, lat
             srcs = [works[r] if x["is_unpack"] else bufs[r] for x in bx]
             dsts = [outs[r] if x["is_unpack"] else works[x["peer_rank"]] for x in bx]
             return emu.run_phased(bx, srcs, dsts, s["es"], legal, nsteps, lag, want_unpack, step, tile_bytes=s["tile_bytes"],
-                                  grid=s["grid"], threads=s["threads"])
+                                  grid=s["grid"], threads=s["threads"], kernel_variant=s["kernel_variant"] & 2,
+                                  head_percent=[0, 25, 60][s["peer_order"] + (s["misalign"] > 1)])
 
         order = [(False, k) for k in range(nsteps)] + [(True, k) for k in range(nsteps)] if late else \
             [(u, k) for k in range(nsteps) for u in (False, True)]
