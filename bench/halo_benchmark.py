@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--staged", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed known-answer check")
     args = ap.parse_args()
 
     import torch
@@ -50,6 +51,33 @@ def main():
     periods = [not args.nonperiodic] * 3
     stream = torch.cuda.current_stream()
     rows = []
+    parity = {"checked_pencils": 0, "ok": True, "pattern": "global linear index per cell as integer bits (mod 2^32 for "
+              "4-byte elements); after updating dims 0, 1, 2 every cell of the halo-inclusive pencil must hold the index "
+              "of the (periodically wrapped) global cell it mirrors, -1 where there is none: the comparator of the "
+              "reference's tests/ctest/halo_tests.cc:229-272, on the device, on every rank"}
+    idt = torch.int32 if es == 4 else torch.int64
+    gstride = [1, args.grid[0], args.grid[0] * args.grid[1]]
+
+    def pattern(p, halo_cells):
+        """halo_cells False: interior = index, halo cells unset (-1); True: the expected state after all three updates."""
+        terms, masks = [], []
+        for k in range(3):
+            ax_g = p.order[k]
+            g = torch.arange(p.shape[k], device=dev, dtype=torch.int64) + (p.lo[k] - args.halo[ax_g])
+            inside = (g >= p.lo[k]) & (g <= p.hi[k])
+            if halo_cells:
+                valid = torch.ones_like(inside) if periods[ax_g] else ((g >= 0) & (g < args.grid[ax_g]))
+                g = torch.remainder(g, args.grid[ax_g])
+            else:
+                valid = inside
+            terms.append(g * gstride[ax_g])
+            masks.append(valid)
+        idx = terms[2][:, None, None] + terms[1][None, :, None] + terms[0][None, None, :]
+        ok = masks[2][:, None, None] & masks[1][None, :, None] & masks[0][None, None, :]
+        out = torch.where(ok, idx, torch.full_like(idx, -1)).to(idt).reshape(-1)
+        if es == 16:
+            out = torch.stack([out, ~out], dim=1).reshape(-1)
+        return out
     for ax in range(3):
         res, p = cd.cudecompGetPencilInfo(handle, gd, ax, args.halo)
         cd.check(res)
@@ -58,6 +86,17 @@ def main():
         cd.check(res)
         data = torch.zeros(p.size * es // 4, dtype=torch.float32, device=dev)
         shape_g = {p.order[i]: p.shape[i] for i in range(3)}
+        if not args.no_parity:
+            view = data.view(idt)
+            view.copy_(pattern(p, False))
+            for dim in range(3):
+                cd.check(cd.UPDATE_HALOS[ax](handle, gd, data, work, dt_enum, args.halo, periods, dim, None, stream))
+            want = pattern(p, True)
+            good = bool(torch.equal(view, want))
+            del want
+            torch.cuda.synchronize()
+            parity["checked_pencils"] += 1
+            parity["ok"] = parity["ok"] and good
         for dim in range(3):
             face = args.halo[dim] * shape_g[(dim + 1) % 3] * shape_g[(dim + 2) % 3]
             call = lambda: cd.check(cd.UPDATE_HALOS[ax](handle, gd, data, work, dt_enum, args.halo, periods, dim,  # noqa: E731
@@ -79,9 +118,15 @@ def main():
                              bytes_sent_per_gpu=sent, moved_bytes=2 * face * es,
                              gbs=(2 * face * es / (ms * 1e-3) / 1e9) if ms > 0 else None))
         cd.check(cd.cudecompFree(handle, gd, work))
+    if not args.no_parity:
+        parity["ok"] = cd.MPI_Allreduce_max(0.0 if parity["ok"] else 1.0) == 0.0
+        parity["ranks"] = world
     if rank == 0:
-        print(json.dumps({"benchmark": "halo update", "grid": args.grid, "pdims": pd, "halo": args.halo, "dtype": args.dtype,
-                          "periodic": not args.nonperiodic, "n_gpus": world, "calls": rows}), flush=True)
+        line = {"benchmark": "halo update", "grid": args.grid, "pdims": pd, "halo": args.halo, "dtype": args.dtype,
+                "periodic": not args.nonperiodic, "n_gpus": world, "calls": rows}
+        if not args.no_parity:
+            line["parity"] = parity
+        print(json.dumps(line), flush=True)
     cd.cudecompGridDescDestroy(handle, gd)
     cd.cudecompFinalize(handle)
     cd.MPI_Finalize()

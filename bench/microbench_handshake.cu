@@ -1,7 +1,9 @@
 // How long does the in-kernel cross-GPU entry/exit handshake of cdb::rowCopyKernel take?
 // Single process, 2 GPUs with peer access; both GPUs launch the same (almost empty) kernel with handshake in a loop.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I include -I include/mpi_shim -I cudecomp_b200/csrc \
-//        bench/microbench_handshake.cu -o /tmp/hs && /tmp/hs
+//        bench/microbench_handshake.cu cudecomp_b200/csrc/{launch_params,plan,geometry}.cc -o /tmp/hs && /tmp/hs
+// --profile-remote: three launches without handshake for ncu (kernel replay is safe): the product's row-copy kernel
+// storing 1 GiB into the peer GPU with 128-bit and with 256-bit accesses, then the same box locally.
 #include "../cudecomp_b200/csrc/kernels.cu"
 
 #include <cstdio>
@@ -50,7 +52,7 @@ int main(int argc, char** argv) {
     CK(cudaDeviceSynchronize());
   }
   uint64_t epoch = 0;
-  auto run = [&](const char* name, int tiles, bool handshake, bool remote, int grid, int iters) {
+  auto run = [&](const char* name, int tiles, bool handshake, bool remote, int grid, int iters, int vec = 16) {
     for (int rep = 0; rep < 2; ++rep) {
       for (int d = 0; d < 2; ++d) {
         CK(cudaSetDevice(d));
@@ -63,15 +65,15 @@ int main(int argc, char** argv) {
           CopyParams p;
           memset(&p, 0, sizeof(p));
           p.elem_size = 16;
-          p.vec_size = 16;
+          p.vec_size = vec;
           if (tiles > 0) {
             KBox& b = p.box[0];
             b.src = src[d];
             b.dst = remote ? dst[1 - d] : dst[d];
             b.n[0] = 2048ll * tiles;
             b.n[1] = b.n[2] = 1;
-            b.row_vecs = 2048u * tiles;
-            b.seg_vecs = 2048;
+            b.row_vecs = 2048u * 16u / vec * tiles;
+            b.seg_vecs = 2048u * 16u / vec;
             b.segs_per_row = tiles;
             b.rows_per_tile = 1;
             b.tiles = tiles;
@@ -111,8 +113,10 @@ int main(int argc, char** argv) {
   if (profile_remote) {
     // for ncu (single process, no handshake so that kernel replay is safe): cdb::rowCopyKernel<uint4> storing 1 GiB
     // into the peer GPU, then the same box locally
-    run("remote copy 32768 tiles (1 GiB), no handshake, default grid", 32768, false, true, 0, 3);
-    run("local copy 32768 tiles (1 GiB), no handshake, default grid", 32768, false, false, 0, 3);
+    // 4 launches each (2 repetitions x 2 GPUs): launches 0-3, 4-7, 8-11 of the process
+    run("remote copy 32768 tiles (1 GiB), no handshake, default grid", 32768, false, true, 0, 1);
+    run("remote copy 32768 tiles (1 GiB), 256-bit accesses, no handshake, default grid", 32768, false, true, 0, 1, 32);
+    run("local copy 32768 tiles (1 GiB), no handshake, default grid", 32768, false, false, 0, 1);
     return 0;
   }
   const int it = 300;

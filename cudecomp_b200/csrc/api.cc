@@ -171,6 +171,9 @@ void checkConfig(cudecompHandle_t h, const cudecompGridDescConfig_t* c, bool aut
     if (c->pdims[0] != 0 || c->pdims[1] != 0) THROW_INVALID_USAGE("pdims values are invalid");
   } else if (prod != h->nranks) {
     THROW_INVALID_USAGE("product of pdims values must equal number of ranks");
+  } else if (h->have_device && (c->pdims[0] > kMaxPeers + 1 || c->pdims[1] > kMaxPeers + 1)) {
+    // said here rather than at the first transpose: a launch handshakes with at most kMaxPeers peers
+    THROW_NOT_SUPPORTED("row / column communicators with more than 72 ranks are not supported");
   }
   const bool set = c->transpose_mem_order[0][0] >= 0;
   for (int i = 0; i < 3; ++i)
@@ -215,6 +218,7 @@ void destroyGridDescResources(cudecompGridDesc_t gd, bool collective) {
   }
   gd->mbox.destroy();
   releaseFusedCache(gd);
+  if (collective) drainReleases(h);
   for (cudaEvent_t e : gd->side_events) cudaEventDestroy(e);
   gd->side_events.clear();
   if (gd->side_stream) cudaStreamDestroy(gd->side_stream);
@@ -275,6 +279,7 @@ static void initHandle(cudecompHandle_t h, const CommPtr& parent) {
   if (const char* v = std::getenv("CUDECOMP_B200_STAGED")) h->staged_mode = (std::strcmp(v, "launches") == 0) ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_FUSED_LAG")) h->fused_lag = std::min(8, std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("CUDECOMP_B200_PHASE_HEAD")) h->phase_head_percent = std::min(90, std::max(0, std::atoi(v)));
+  if (const char* v = std::getenv("CUDECOMP_B200_TRANSPOSE_GEOM")) h->transpose_geometry = std::atoi(v) != 0 ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_WIRE_WIDE")) h->wire_wide = std::atoi(v) != 0 ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_DIRECT")) h->allow_direct = std::strcmp(v, "0") != 0;
   double spin_s = 60.0;
@@ -330,6 +335,12 @@ cudecompResult_t cudecompFinalize(cudecompHandle_t handle) {
   API_TRY
   checkHandle(handle);
   handle->peers.clear();
+  if (!handle->released_pending.empty() || handle->acks.valid()) {
+    // every rank has closed all its imports above; after the barrier nothing of mine is mapped anywhere
+    if (handle->nranks > 1 && handle->acks.valid()) barrier(*handle->comm);
+    reapReleased(handle, true);
+    handle->acks.destroy();
+  }
   if (handle->arena.valid()) handle->arena.destroy(handle->comm.get());
   handle->initialized = false;
   liveHandles().erase(handle);
@@ -406,6 +417,7 @@ cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudeco
   // Device-side plumbing shared by every operation on this descriptor (collective).
   if (handle->have_device) {
     if (!handle->arena.valid()) handle->arena.create(*handle->comm);
+    if (!handle->acks.valid() && handle->nranks > 1) handle->acks.create(*handle->comm, handle->token);
     if (!handle->free_slots.empty()) {
       gd->pad_slot = handle->free_slots.back();
       handle->free_slots.pop_back();
@@ -614,15 +626,24 @@ cudecompResult_t cudecompFree(cudecompHandle_t handle, cudecompGridDesc_t grid_d
     // Not collective: the reference's own test drivers free and re-allocate workspaces on the ranks that need a
     // larger one only (tests/cc/halo_test.cc workspace reuse). The release is announced to the peers with the next
     // operation's descriptor exchange, where they drop their imports of this allocation (peer.h, CallMsg).
+    // The memory itself is only returned to the driver once every rank that may have imported it has closed its
+    // mapping (freeing an allocation that another process still has open through CUDA IPC is undefined): those ranks
+    // acknowledge on the handle's AckBoard, and the pending frees are retried at every later exchange, free and
+    // descriptor destruction.
     CHECK_CUDA(cudaDeviceSynchronize());
     BufDesc d;
     describeBuffer(buffer, &d);
-    if (d.exportable && d.offset == 0) {
+    std::vector<int> shown;
+    if (d.exportable && d.offset == 0) shown = takeDescribedTo(buffer);
+    if (shown.empty()) {
+      CHECK_CUDA(cudaFree(buffer));
+    } else {
       for (int k = kReleaseSlots - 1; k > 0; --k) handle->released[k] = handle->released[k - 1];
       handle->released[0] = d.buffer_id;
       handle->release_count++;
+      handle->released_pending.push_back({buffer, handle->release_count, std::move(shown)});
     }
-    CHECK_CUDA(cudaFree(buffer));
+    reapReleased(handle);
   }
   grid_desc->allocations.erase(buffer);
   API_CATCH()

@@ -142,6 +142,7 @@ std::vector<std::array<int32_t, 2>> autotunePdims(cudecompHandle_t h, cudecompGr
 
 bool gridUsable(const cudecompGridDesc_t gd, const std::array<int32_t, 2>& p, bool allow_uneven) {
   const auto& d = gd->config.gdims_dist;
+  if (p[0] > kMaxPeers + 1 || p[1] > kMaxPeers + 1) return false; // larger than a launch can handshake with
   if (p[0] > std::min(d[0], d[1]) || p[1] > std::min(d[1], d[2])) return false; // empty pencils
   if (!allow_uneven && (d[0] % p[0] != 0 || d[1] % p[0] != 0 || d[1] % p[1] != 0 || d[2] % p[1] != 0)) return false;
   return true;

@@ -103,7 +103,10 @@ void recvMsg(int peer, const Comm& c, void* buf, size_t bytes) {
   if (bytes) recvAll(g_world.fds[peer], buf, bytes);
 }
 
-int listenOn(const std::string& addr, int port, int* bound_port) {
+// Listens on `ip_be` only (network byte order; the library is single-node, there is no reason to accept connections on
+// every interface). 0 or an address that is not local to this host (NAT, container port mapping) falls back to all
+// interfaces.
+int listenOn(uint32_t ip_be, int port, int* bound_port) {
   int fd = ::socket(AF_INET, SOCK_STREAM, 0);
   if (fd < 0) fail("socket");
   int one = 1;
@@ -111,9 +114,12 @@ int listenOn(const std::string& addr, int port, int* bound_port) {
   sockaddr_in sa{};
   sa.sin_family = AF_INET;
   sa.sin_port = htons(static_cast<uint16_t>(port));
-  sa.sin_addr.s_addr = htonl(INADDR_ANY);
-  (void)addr;
-  if (::bind(fd, reinterpret_cast<sockaddr*>(&sa), sizeof(sa)) < 0) fail("bind to port " + std::to_string(port));
+  sa.sin_addr.s_addr = ip_be ? ip_be : htonl(INADDR_ANY);
+  if (::bind(fd, reinterpret_cast<sockaddr*>(&sa), sizeof(sa)) < 0) {
+    if (!ip_be) fail("bind to port " + std::to_string(port));
+    sa.sin_addr.s_addr = htonl(INADDR_ANY);
+    if (::bind(fd, reinterpret_cast<sockaddr*>(&sa), sizeof(sa)) < 0) fail("bind to port " + std::to_string(port));
+  }
   if (::listen(fd, 512) < 0) fail("listen");
   socklen_t len = sizeof(sa);
   getsockname(fd, reinterpret_cast<sockaddr*>(&sa), &len);
@@ -133,6 +139,23 @@ uint32_t resolve(const std::string& host) {
   uint32_t ip = reinterpret_cast<sockaddr_in*>(res->ai_addr)->sin_addr.s_addr;
   freeaddrinfo(res);
   return ip;
+}
+
+// Every rendezvous and mesh connection opens with this word: ranks of another job (or anything else that finds the
+// port) are turned away instead of being taken for a rank. CUDECOMP_B200_BOOTSTRAP_TOKEN supplies a secret; without one
+// the word is derived from what the launcher gave every rank of THIS job (not a secret, a mix-up guard).
+uint64_t jobToken(const std::string& addr, int port, int size) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const std::string& s) {
+    for (unsigned char ch : s) h = (h ^ ch) * 1099511628211ull;
+    h = (h ^ 0xffu) * 1099511628211ull;
+  };
+  if (const char* t = std::getenv("CUDECOMP_B200_BOOTSTRAP_TOKEN")) mix(t);
+  if (const char* t = std::getenv("TORCHELASTIC_RUN_ID")) mix(t);
+  mix(addr);
+  mix(std::to_string(port));
+  mix(std::to_string(size));
+  return h;
 }
 
 int connectTo(uint32_t ip_be, int port, double timeout_s) {
@@ -214,14 +237,25 @@ void worldInitExplicit(int rank, int size, const std::string& addr, int port) {
     int my_port = 0;
     int lfd = -1;
     std::vector<PeerAddr> table(w.size);
+    const uint64_t token = jobToken(addr, port, w.size);
+    struct Hello {
+      uint64_t token;
+      int32_t rank;
+      int32_t port;
+    };
     if (w.rank == 0) {
-      lfd = listenOn(addr, port, nullptr);
+      lfd = listenOn(resolve(addr), port, nullptr);
       // every other rank dials in and reports the port of its own listening socket
       for (int k = 1; k < w.size; ++k) {
         int fd = acceptOne(lfd);
-        int32_t hello[2];
-        recvAll(fd, hello, sizeof(hello));
-        int r = hello[0];
+        Hello hello{};
+        recvAll(fd, &hello, sizeof(hello));
+        if (hello.token != token) { // not a rank of this job
+          ::close(fd);
+          --k;
+          continue;
+        }
+        int r = hello.rank;
         if (r <= 0 || r >= w.size || w.fds[r] != -1) {
           errno = 0;
           fail("unexpected rank " + std::to_string(r) + " at rendezvous");
@@ -230,28 +264,38 @@ void worldInitExplicit(int rank, int size, const std::string& addr, int port) {
         sockaddr_in pa{};
         socklen_t len = sizeof(pa);
         getpeername(fd, reinterpret_cast<sockaddr*>(&pa), &len);
-        table[r] = PeerAddr{pa.sin_addr.s_addr, hello[1]};
+        table[r] = PeerAddr{pa.sin_addr.s_addr, hello.port};
       }
       table[0] = PeerAddr{0, port};
       for (int r = 1; r < w.size; ++r) sendAll(w.fds[r], table.data(), sizeof(PeerAddr) * w.size);
     } else {
-      lfd = listenOn(addr, 0, &my_port);
       int fd = connectTo(resolve(addr), port, timeout_s);
-      int32_t hello[2] = {w.rank, my_port};
-      sendAll(fd, hello, sizeof(hello));
+      // my mesh listener: on the interface that reaches rank 0
+      sockaddr_in la{};
+      socklen_t llen = sizeof(la);
+      getsockname(fd, reinterpret_cast<sockaddr*>(&la), &llen);
+      lfd = listenOn(la.sin_addr.s_addr, 0, &my_port);
+      Hello hello{token, w.rank, my_port};
+      sendAll(fd, &hello, sizeof(hello));
       w.fds[0] = fd;
       recvAll(fd, table.data(), sizeof(PeerAddr) * w.size);
       // mesh among the non-zero ranks: the higher rank dials the lower one
       for (int r = 1; r < w.rank; ++r) {
         int pfd = connectTo(table[r].ip_be, table[r].port, timeout_s);
-        int32_t me = w.rank;
+        Hello me{token, w.rank, 0};
         sendAll(pfd, &me, sizeof(me));
         w.fds[r] = pfd;
       }
       for (int k = w.rank + 1; k < w.size; ++k) {
         int pfd = acceptOne(lfd);
-        int32_t who;
-        recvAll(pfd, &who, sizeof(who));
+        Hello other{};
+        recvAll(pfd, &other, sizeof(other));
+        if (other.token != token) {
+          ::close(pfd);
+          --k;
+          continue;
+        }
+        const int32_t who = other.rank;
         if (who <= w.rank || who >= w.size || w.fds[who] != -1) {
           errno = 0;
           fail("unexpected rank in mesh setup");
@@ -277,7 +321,7 @@ void worldInitExplicit(int rank, int size, const std::string& addr, int port) {
 
 int pickFreePort() {
   int port = 0;
-  int fd = listenOn("", 0, &port);
+  int fd = listenOn(htonl(INADDR_LOOPBACK), 0, &port);
   ::close(fd);
   return port;
 }

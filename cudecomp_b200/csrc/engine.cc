@@ -40,6 +40,46 @@ void releaseFusedCache(cudecompGridDesc_t gd) {
   (void)cudaGetLastError();
 }
 
+void reapReleased(cudecompHandle_t h, bool everything) {
+  auto& list = h->released_pending;
+  for (size_t i = 0; i < list.size();) {
+    bool ready = true;
+    if (!everything)
+      for (int r : list[i].waiting_for)
+        if (h->acks.seen(r, h->rank) < list[i].stamp) ready = false;
+    if (ready) {
+      cudaFree(list[i].ptr);
+      list.erase(list.begin() + i);
+    } else {
+      ++i;
+    }
+  }
+  (void)cudaGetLastError();
+}
+
+void drainReleases(cudecompHandle_t h) {
+  if (h->nranks == 1 || !h->have_device) {
+    reapReleased(h, true);
+    return;
+  }
+  struct Note {
+    uint64_t release_count;
+    uint64_t released[kReleaseSlots];
+  } mine;
+  mine.release_count = h->release_count;
+  for (int k = 0; k < kReleaseSlots; ++k) mine.released[k] = h->released[k];
+  std::vector<Note> all(h->nranks);
+  allgather(*h->comm, &mine, sizeof(Note), all.data());
+  bool any = false;
+  for (int r = 0; r < h->nranks; ++r) {
+    if (all[r].release_count) any = true;
+    if (r != h->rank && h->peers.noteReleases(r, all[r].release_count, all[r].released)) h->acks.publish(r, all[r].release_count);
+  }
+  if (!any) return; // nobody has ever released anything: nothing can be pending anywhere
+  barrier(*h->comm);
+  reapReleased(h);
+}
+
 void setGeometry(cudecompGridDesc_t gd, const std::array<int32_t, 2>& pdims) {
   releaseFusedCache(gd); // plans depend on the process grid
   gd->config.pdims[0] = pdims[0];
@@ -85,7 +125,7 @@ SyncParams makeSync(cudecompGridDesc_t gd, const std::vector<int>& peers) {
   SignalArena& arena = gd->handle->arena;
   if (!arena.valid() || gd->pad_slot < 0) THROW_INTERNAL_ERROR("signal pads are not initialised");
   if (peers.size() > static_cast<size_t>(kMaxPeers))
-    THROW_NOT_SUPPORTED("communicators with more than 17 ranks are not supported yet");
+    THROW_NOT_SUPPORTED("row / column communicators with more than 72 ranks are not supported");
   s.my_pad = arena.mine(gd->pad_slot);
   s.npeers = static_cast<int32_t>(peers.size());
   for (size_t i = 0; i < peers.size(); ++i) {
@@ -113,6 +153,7 @@ void launchBoxes(cudecompGridDesc_t gd, const std::vector<ResolvedBox>& boxes, i
   // Launches that store into peers: 256-bit accesses where the alignment allows (measured on B200, profiles/
   // r2_n2_schedules.md: +3 % on the wire; local HBM-bound copies are 8 % SLOWER with them and keep 128-bit accesses)
   if (tuning.kernel_variant == 0 && sync.npeers > 0 && gd->wire_wide) tuning.kernel_variant = 2;
+  tuning.transpose_geometry = gd->handle->transpose_geometry;
   std::vector<PreparedLaunch> launches = prepareLaunches(boxes, es, tuning, me, comm_size);
 
   LaunchConfig cfg;
@@ -142,7 +183,10 @@ void fillReleases(cudecompHandle_t h, CallMsg* m) {
 
 void processReleases(cudecompHandle_t h, const std::vector<int>& group_world, int me, const std::vector<CallMsg>& msgs) {
   for (size_t i = 0; i < msgs.size(); ++i)
-    if (static_cast<int>(i) != me) h->peers.noteReleases(group_world[i], msgs[i].release_count, msgs[i].released);
+    if (static_cast<int>(i) != me &&
+        h->peers.noteReleases(group_world[i], msgs[i].release_count, msgs[i].released))
+      h->acks.publish(group_world[i], msgs[i].release_count); // my imports of what that rank freed are closed
+  if (!h->released_pending.empty()) reapReleased(h);
 }
 
 // Ends the current performance sample on every way out of a call (including exceptions).
@@ -395,6 +439,9 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
   std::vector<CallMsg> msgs;
   gd->mbox.exchange(probe.axes.comm == COMM_COL ? 0 : 1, probe.group_world, probe.me, mine, msgs);
   processReleases(h, probe.group_world, probe.me, msgs);
+  noteDescribed(mine.data, output, probe.group_world, probe.me);
+  noteDescribed(mine.work, work, probe.group_world, probe.me);
+  noteDescribed(mine.src, input, probe.group_world, probe.me);
 
   bool direct = h->allow_direct && !gd->force_staged &&
                 gd->config.transpose_comm_backend < CUDECOMP_TRANSPOSE_COMM_NVSHMEM; // NVSHMEM* values = staged schedule
@@ -542,6 +589,8 @@ void runHalo(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, void* input, voi
   std::vector<CallMsg> msgs;
   gd->mbox.exchange(probe.comm == COMM_COL ? 0 : 1, probe.group_world, probe.me, mine, msgs);
   processReleases(h, probe.group_world, probe.me, msgs);
+  noteDescribed(mine.data, input, probe.group_world, probe.me);
+  noteDescribed(mine.work, work, probe.group_world, probe.me);
 
   bool direct = h->allow_direct && !gd->force_staged && gd->config.halo_comm_backend < CUDECOMP_HALO_COMM_NVSHMEM;
   bool work_ok = true;

@@ -69,6 +69,14 @@ struct cudecompHandle {
   int fused_lag = 1;             // CUDECOMP_B200_FUSED_LAG
   int phase_head_percent = 25;   // CUDECOMP_B200_PHASE_HEAD
   int wire_wide = 1;             // CUDECOMP_B200_WIRE_WIDE=0: 128-bit accesses on the wire too
+  int transpose_geometry = 0;    // CUDECOMP_B200_TRANSPOSE_GEOM=1: 64 x 32 tiles for 8-byte vectorised transposes
+  cdb::AckBoard acks;            // which of my release announcements every rank has processed
+  struct Released {              // freed by the caller, still mapped by peers: the real cudaFree waits for their acks
+    void* ptr;
+    uint64_t stamp;              // my release_count right after announcing it
+    std::vector<int> waiting_for;
+  };
+  std::vector<Released> released_pending;
   uint64_t release_count = 0;    // buffers freed through cudecompFree so far
   uint64_t released[cdb::kReleaseSlots] = {0}; // ids of the most recent ones, newest first
 };
@@ -115,6 +123,11 @@ namespace cdb {
 int autoFusedChunks(int64_t pencil_bytes);
 
 void releaseFusedCache(cudecompGridDesc_t gd);
+// cudaFree every released allocation whose importers have all acknowledged (all of them when `everything`).
+void reapReleased(cudecompHandle_t h, bool everything = false);
+// Collective over the handle's communicator: every rank processes every rank's release announcements, then the owners
+// free what was pending (used where the API is collective anyway: cudecompGridDescDestroy).
+void drainReleases(cudecompHandle_t h);
 uint64_t epochStride(const cudecompGridDesc_t gd);
 
 void setGeometry(cudecompGridDesc_t gd, const std::array<int32_t, 2>& pdims);

@@ -326,8 +326,9 @@ template <typename T, int kOrder> __global__ void __launch_bounds__(256) transpo
 // ---------------------------------------------------------------------------------------------
 // TRANSPOSE_VEC: same boxes as TRANSPOSE, 16-byte accesses on both sides (kernels.h, tiling.h TransVecGeom).
 // ---------------------------------------------------------------------------------------------
-template <typename T, int kOrder> __global__ void __launch_bounds__(256) transposeVecKernel(const __grid_constant__ CopyParams p) {
-  using G = TransVecGeom<sizeof(T)>;
+template <typename T, int kOrder, int kAlt = 0>
+__global__ void __launch_bounds__(256) transposeVecKernel(const __grid_constant__ CopyParams p) {
+  using G = TransVecGeom<sizeof(T), kAlt>;
   constexpr int VEC = G::kVec;
   union Vec {
     uint4 u;
@@ -511,7 +512,7 @@ namespace {
 
 using KernelFn = void (*)(const CopyParams);
 
-template <int kOrder> KernelFn pickKernelOrdered(KernelKind kind, int size) {
+template <int kOrder> KernelFn pickKernelOrdered(KernelKind kind, int size, uint32_t geometry) {
   if (kind == KernelKind::ROWCOPY) {
     switch (size) {
     case 32: return rowCopyKernel<Vec32, kOrder>;
@@ -528,7 +529,7 @@ template <int kOrder> KernelFn pickKernelOrdered(KernelKind kind, int size) {
   } else if (kind == KernelKind::TRANSPOSE_VEC) {
     switch (size) {
     case 16: return transposeVecKernel<uint4, kOrder>;
-    case 8: return transposeVecKernel<uint2, kOrder>;
+    case 8: return geometry ? transposeVecKernel<uint2, kOrder, 1> : transposeVecKernel<uint2, kOrder, 0>;
     case 4: return transposeVecKernel<uint32_t, kOrder>;
     }
   } else if (size == 16) {
@@ -537,8 +538,8 @@ template <int kOrder> KernelFn pickKernelOrdered(KernelKind kind, int size) {
   return nullptr;
 }
 
-KernelFn pickKernel(KernelKind kind, int size, uint32_t peer_order = 0) {
-  return peer_order ? pickKernelOrdered<1>(kind, size) : pickKernelOrdered<0>(kind, size);
+KernelFn pickKernel(KernelKind kind, int size, uint32_t peer_order = 0, uint32_t geometry = 0) {
+  return peer_order ? pickKernelOrdered<1>(kind, size, geometry) : pickKernelOrdered<0>(kind, size, geometry);
 }
 
 } // namespace
@@ -589,7 +590,7 @@ static cudaError_t launchBulk(const CopyParams& p, const LaunchConfig& cfg, cuda
 cudaError_t launchCopy(KernelKind kind, const CopyParams& p, const LaunchConfig& cfg, cudaStream_t stream) {
   if (kind == KernelKind::ROWCOPY_BULK) return launchBulk(p, cfg, stream);
   const int size = (kind == KernelKind::ROWCOPY) ? static_cast<int>(p.vec_size) : static_cast<int>(p.elem_size);
-  KernelFn fn = pickKernel(kind, size, p.peer_order);
+  KernelFn fn = pickKernel(kind, size, p.peer_order, p.geometry);
   if (!fn) return cudaErrorInvalidValue;
   const uint64_t total = static_cast<uint64_t>(p.nboxes) * p.max_tiles;
   const int resident = maxResidentCtas(kind, size, cfg.threads, p.peer_order);

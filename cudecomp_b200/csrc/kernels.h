@@ -15,7 +15,8 @@
 namespace cdb {
 
 constexpr int kMaxBoxes = 16; // boxes per launch (one per peer of a row/column communicator)
-constexpr int kMaxPeers = 16; // peers a launch can handshake with
+constexpr int kMaxPeers = 71; // peers a launch can handshake with: a row / column communicator of up to 72 ranks (one
+                              // NVLink domain); the parameter block stays under the 4 KiB every launch path accepts
 
 // Signal pad: one 4 KiB page per grid descriptor on every rank, mapped into every peer.
 // Slots are indexed by GLOBAL rank and hold monotonically increasing epochs, so they never need a reset.
@@ -68,7 +69,8 @@ struct CopyParams {
   uint32_t elem_size; // 4, 8 or 16
   uint32_t vec_size;  // ROWCOPY: 4, 8, 16 or 32
   uint32_t peer_order; // slot order: 0 interleaved over the boxes (one-shot), 1 rounds, one peer after the other (pairwise)
-  uint32_t pad_[3];
+  uint32_t geometry;   // TRANSPOSE_VEC: tile geometry (tiling.h TransVecGeom kAlt)
+  uint32_t pad_[2];
 };
 
 // Phased launch (the fused in-place / staged schedule, see engine.cc runFusedStaged): ONE persistent launch walks

@@ -136,6 +136,7 @@ std::vector<PreparedLaunch> prepareLaunches(const std::vector<LaunchBox>& boxes,
     p.elem_size = static_cast<uint32_t>(es);
     p.vec_size = static_cast<uint32_t>(V);
     p.peer_order = (tuning.peer_order == 1) ? 1u : 0u;
+    p.geometry = (kind == KernelKind::TRANSPOSE_VEC && es == 8 && tuning.transpose_geometry) ? 1u : 0u;
     const size_t lo = l * kMaxBoxes, hi = std::min(canon.size(), lo + kMaxBoxes);
     for (size_t i = lo; i < hi; ++i) {
       const CanonBox& c = canon[i];
@@ -157,7 +158,7 @@ std::vector<PreparedLaunch> prepareLaunches(const std::vector<LaunchBox>& boxes,
           kb.ds[k] = t.ds[k];
         }
         int e0 = 32, e1 = 32;
-        if (kind == KernelKind::TRANSPOSE_VEC) transVecTileExtents(es, e0, e1);
+        if (kind == KernelKind::TRANSPOSE_VEC) transVecTileExtents(es, tuning.transpose_geometry, e0, e1);
         kb.tiles0 = static_cast<uint32_t>((kb.n[0] + e0 - 1) / e0);
         kb.tiles1 = static_cast<uint32_t>((kb.n[1] + e1 - 1) / e1);
         const int64_t tiles = static_cast<int64_t>(kb.tiles0) * kb.tiles1 * kb.n[2];

@@ -21,6 +21,7 @@ struct LaunchBox {
 struct LaunchTuning {
   int tile_bytes = 0;     // bytes of a ROWCOPY tile (0: kDefaultTileBytes); power of two in [4 KiB, 256 KiB]
   int peer_order = 0;     // CopyParams::peer_order
+  int transpose_geometry = 0;  // vectorised transpose of 8-byte elements: 0 = 32 x 64 tiles, 1 = 64 x 32 (tiling.h)
   int phase_head_percent = 25; // phased launches: share of a step's pushes that runs before its unpacks join in
   int kernel_variant = 0; // 1: TMA bulk row copy where every row is 16-byte aligned and at least 2 KiB long;
                           // 2: 256-bit LDG/STG where every address and stride is 32-byte aligned (else 128-bit)

@@ -8,6 +8,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -56,6 +57,7 @@ struct ExportEntry {
   uint64_t size;
   cudaIpcMemHandle_t handle;
   bool exportable;
+  std::vector<int> described_to; // world ranks that have been shown this allocation in a CallMsg
 };
 std::map<uint64_t, ExportEntry> g_exports; // by allocation base
 
@@ -112,6 +114,89 @@ void describeBuffer(const void* ptr, BufDesc* d) {
   d->exportable = e.exportable ? 1u : 0u;
 }
 
+void noteDescribed(const BufDesc& d, const void* ptr, const std::vector<int>& group_world, int me) {
+  if (!d.exportable || !ptr) return;
+  auto it = g_exports.find(reinterpret_cast<uint64_t>(ptr) - d.offset);
+  if (it == g_exports.end() || it->second.buffer_id != d.buffer_id) return;
+  std::vector<int>& to = it->second.described_to;
+  for (size_t i = 0; i < group_world.size(); ++i) {
+    if (static_cast<int>(i) == me) continue;
+    if (std::find(to.begin(), to.end(), group_world[i]) == to.end()) to.push_back(group_world[i]);
+  }
+}
+
+std::vector<int> takeDescribedTo(const void* alloc_base) {
+  std::vector<int> out;
+  auto it = g_exports.find(reinterpret_cast<uint64_t>(alloc_base));
+  if (it == g_exports.end()) return out;
+  out = std::move(it->second.described_to);
+  g_exports.erase(it);
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------- AckBoard
+
+AckBoard::~AckBoard() {
+  if (base_) munmap(base_, bytes_);
+}
+
+std::atomic<uint64_t>* AckBoard::cell(int reader, int owner) const {
+  return reinterpret_cast<std::atomic<uint64_t>*>(base_) + static_cast<size_t>(reader) * nranks_ + owner;
+}
+
+void AckBoard::create(Comm& comm, uint64_t token) {
+  nranks_ = comm.size();
+  me_ = comm.rank();
+  bytes_ = static_cast<size_t>(nranks_) * nranks_ * sizeof(uint64_t);
+  char name[96];
+  std::snprintf(name, sizeof(name), "/cudecomp_b200_%016llx_acks", static_cast<unsigned long long>(token));
+  int32_t ok = 1;
+  if (me_ == 0) {
+    int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, static_cast<off_t>(bytes_)) != 0) ok = 0;
+    if (ok) {
+      base_ = mmap(nullptr, bytes_, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+      if (base_ == MAP_FAILED) {
+        base_ = nullptr;
+        ok = 0;
+      } else {
+        std::memset(base_, 0, bytes_);
+      }
+    }
+    if (fd >= 0) close(fd);
+  }
+  bcast(comm, &ok, sizeof(ok), 0);
+  if (ok && me_ != 0) {
+    int fd = shm_open(name, O_RDWR, 0600);
+    if (fd >= 0) {
+      base_ = mmap(nullptr, bytes_, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+      if (base_ == MAP_FAILED) base_ = nullptr;
+      close(fd);
+    }
+  }
+  int64_t all_ok = (ok && base_) ? 1 : 0;
+  allreduceI64(comm, &all_ok, 1, ReduceOp::MIN);
+  if (me_ == 0) shm_unlink(name);
+  if (!all_ok) {
+    if (base_) munmap(base_, bytes_);
+    base_ = nullptr;
+    THROW_INTERNAL_ERROR("cannot create the shared-memory acknowledgement board (is /dev/shm available to all ranks?)");
+  }
+}
+
+void AckBoard::destroy() {
+  if (base_) munmap(base_, bytes_);
+  base_ = nullptr;
+}
+
+void AckBoard::publish(int owner, uint64_t count) {
+  if (base_) cell(me_, owner)->store(count, std::memory_order_release);
+}
+
+uint64_t AckBoard::seen(int reader, int owner) const {
+  return base_ ? cell(reader, owner)->load(std::memory_order_acquire) : ~0ull;
+}
+
 // ------------------------------------------------------------------------------------------ PeerCache
 
 PeerCache::~PeerCache() { clear(); }
@@ -163,9 +248,9 @@ void PeerCache::forgetOwner(int owner) {
 // No in-flight kernel of this process can still target a released buffer: its owner only frees it after every
 // operation that used it has completed there, and the owner's kernel completes only after it has received this
 // rank's "all my stores have landed" flag.
-void PeerCache::noteReleases(int owner, uint64_t release_count, const uint64_t* recent_ids) {
+bool PeerCache::noteReleases(int owner, uint64_t release_count, const uint64_t* recent_ids) {
   uint64_t& seen = releases_seen_[owner];
-  if (release_count <= seen) return;
+  if (release_count <= seen) return false;
   const uint64_t fresh = release_count - seen;
   if (fresh > static_cast<uint64_t>(kReleaseSlots)) {
     forgetOwner(owner); // missed some announcements: drop everything, imports are re-created on demand
@@ -173,6 +258,7 @@ void PeerCache::noteReleases(int owner, uint64_t release_count, const uint64_t* 
     for (uint64_t k = 0; k < fresh; ++k) forgetBuffer(owner, recent_ids[k]);
   }
   seen = release_count;
+  return true;
 }
 
 void PeerCache::evictIfNeeded() {

@@ -53,6 +53,33 @@ struct CallMsg {
 // Fills `d` for a local device pointer. Never throws: failure means exportable = 0.
 void describeBuffer(const void* ptr, BufDesc* d);
 
+// Bookkeeping for cudecompFree: an exported allocation must outlive every peer's import of it (freeing memory that
+// another process still has open with cudaIpcOpenMemHandle is undefined). noteDescribed records which ranks were shown a
+// buffer (the only ones that can have imported it); takeDescribedTo hands that set over when the buffer is freed and
+// forgets the export.
+void noteDescribed(const BufDesc& d, const void* ptr, const std::vector<int>& group_world, int me);
+std::vector<int> takeDescribedTo(const void* alloc_base);
+
+// Per-handle board in shared memory: cell (reader, owner) = how many of `owner`'s release announcements `reader` has
+// processed, i.e. closed its imports for. An owner frees a released allocation once every rank it was described to has
+// caught up (engine.cc reapReleased).
+class AckBoard {
+public:
+  ~AckBoard();
+  void create(Comm& comm, uint64_t token); // collective
+  void destroy();
+  bool valid() const { return base_ != nullptr; }
+  void publish(int owner, uint64_t count);
+  uint64_t seen(int reader, int owner) const;
+
+private:
+  std::atomic<uint64_t>* cell(int reader, int owner) const;
+  void* base_ = nullptr;
+  size_t bytes_ = 0;
+  int nranks_ = 0;
+  int me_ = 0;
+};
+
 // Imported peer allocations, keyed by (rank, buffer id, handle bytes).
 class PeerCache {
 public:
@@ -60,7 +87,8 @@ public:
   // Pointer in MY address space for `d` owned by world rank `owner`. Throws CUDA_ERROR if the import fails.
   void* resolve(int owner, const BufDesc& d);
   // Drop the imports of buffers the owner has released (see CallMsg::release_count).
-  void noteReleases(int owner, uint64_t release_count, const uint64_t* recent_ids);
+  // Returns true when something new was processed (the caller then acknowledges on the AckBoard).
+  bool noteReleases(int owner, uint64_t release_count, const uint64_t* recent_ids);
   void forgetBuffer(int owner, uint64_t buffer_id);
   void forgetOwner(int owner);
   void clear();

@@ -82,18 +82,20 @@ struct TransTile {
 // vector each), kNM per thread of a 256-thread CTA, and written out as kE0 rows of kG1 16-byte vectors. The shared tile
 // holds those rows; vector v of row i0 sits at v ^ ((i0 / VEC) & 7), which makes both the micro-tile stores (8
 // consecutive lanes = 8 consecutive vector columns c = i0 / VEC) and the row reads (8 consecutive v) conflict-free.
-template <int kElemBytes> struct TransVecGeom {
+// kAlt (8-byte elements only): the tile is 64 x 32 instead of 32 x 64 elements, i.e. 512-byte row segments on the LOAD
+// side and 256-byte ones on the store side instead of the other way round.
+template <int kElemBytes, int kAlt = 0> struct TransVecGeom {
   static constexpr int kVec = 16 / kElemBytes;
-  static constexpr int kE0 = (kElemBytes == 16) ? 32 : 16 * kVec;
-  static constexpr int kE1 = (kElemBytes == 16) ? 32 : 64;
+  static constexpr int kE0 = (kElemBytes == 16) ? 32 : ((kElemBytes == 8 && kAlt) ? 64 : 16 * kVec);
+  static constexpr int kE1 = (kElemBytes == 16) ? 32 : ((kElemBytes == 8 && kAlt) ? 32 : 64);
   static constexpr int kC0 = kE0 / kVec;
   static constexpr int kG1 = kE1 / kVec;
   static constexpr int kNM = kC0 * kG1 / 256;
   static_assert(kC0 * kG1 % 256 == 0 && kE0 * kG1 == 1024 && kC0 % 8 == 0 && kG1 % 8 == 0, "tile geometry");
 };
-CDB_HD void transVecTileExtents(int elem_bytes, int& e0, int& e1) {
-  e0 = (elem_bytes == 16) ? 32 : 16 * (16 / elem_bytes);
-  e1 = (elem_bytes == 16) ? 32 : 64;
+CDB_HD void transVecTileExtents(int elem_bytes, int alt, int& e0, int& e1) {
+  e0 = (elem_bytes == 16) ? 32 : ((elem_bytes == 8 && alt) ? 64 : 16 * (16 / elem_bytes));
+  e1 = (elem_bytes == 16) ? 32 : ((elem_bytes == 8 && alt) ? 32 : 64);
 }
 CDB_HD uint32_t transVecSlot(uint32_t row, uint32_t v, uint32_t vec, uint32_t g1) { return row * g1 + (v ^ ((row / vec) & 7u)); }
 

@@ -168,7 +168,7 @@ void walkTransposeVec(const CopyParams& p, int grid, Walk& w) {
   const int T = static_cast<int>(p.elem_size);
   const int VEC = 16 / T;
   int E0, E1;
-  transVecTileExtents(T, E0, E1);
+  transVecTileExtents(T, static_cast<int>(p.geometry), E0, E1);
   const uint32_t C0 = E0 / VEC, G1 = E1 / VEC, NM = C0 * G1 / 256;
   const uint32_t total = p.nboxes * p.max_tiles;
   std::vector<char> tile(1024 * 16);
@@ -298,7 +298,8 @@ extern "C" int cdb_emu_run_boxes(const cudecompB200Box_t* boxes, const int32_t* 
     LaunchTuning tuning;
     tuning.tile_bytes = tile_bytes;
     tuning.peer_order = peer_order;
-    tuning.kernel_variant = kernel_variant;
+    tuning.kernel_variant = kernel_variant & 0xff;
+    tuning.transpose_geometry = (kernel_variant >> 8) & 1; // bit 8: alternate tile geometry of the vectorised transpose
     std::vector<PreparedLaunch> launches = prepareLaunches(lb, es, tuning, me, comm_size);
     Ranges ranges{range_lo, range_len, nranges};
     Walk w{ranges};

@@ -96,9 +96,10 @@ def vector_transpose_decompositions(draw):
 
 
 @settings(max_examples=max(EXAMPLES // 2, 30), deadline=None, suppress_health_check=list(HealthCheck))
-@given(vector_transpose_decompositions(), st.sampled_from([4, 8, 16]), st.sampled_from([0, 1, 5, 64]), st.sampled_from([0, 1]))
-def test_emulated_vectorised_transposes_equal_oracle(d, es, grid, peer_order):
-    s = dict(es=es, tile_bytes=0, peer_order=peer_order, kernel_variant=0, grid=grid, threads=256, misalign=0)
+@given(vector_transpose_decompositions(), st.sampled_from([4, 8, 16]), st.sampled_from([0, 1, 5, 64]), st.sampled_from([0, 1]),
+       st.sampled_from([0, 0x100]))
+def test_emulated_vectorised_transposes_equal_oracle(d, es, grid, peer_order, geometry):
+    s = dict(es=es, tile_bytes=0, peer_order=peer_order, kernel_variant=geometry, grid=grid, threads=256, misalign=0)
     check_transposes(d, s)
 
 
