@@ -24,8 +24,11 @@ int64_t dtypeSize(cudecompDataType_t dtype) {
 // separate-launch schedule one per step. A function of the descriptor's settings only, never of the path taken.
 uint64_t epochStride(const cudecompGridDesc_t gd) { return static_cast<uint64_t>(std::max(1, gd->pipeline_chunks)); }
 
+// Measured on B200 (profiles/r2_n2_schedules.md): a chunk costs about 10 us of pipeline bubbles (CTAs drift apart by a
+// tile within a step and wait for the slowest one anywhere before they unpack), so chunks are kept at >= 128 MiB of
+// pencil: 16 chunks for the 2 GiB pencils of 1024^3 complex128 on 8 GPUs, 4 for the 512 MiB ones of 512^3 complex64 on 2.
 int autoFusedChunks(int64_t pencil_bytes) {
-  const int64_t k = pencil_bytes / (int64_t(8) << 20);
+  const int64_t k = pencil_bytes / (int64_t(128) << 20);
   return static_cast<int>(std::min<int64_t>(std::max<int64_t>(k, 1), 16));
 }
 

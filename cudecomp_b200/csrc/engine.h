@@ -119,7 +119,7 @@ struct cudecompGridDesc {
 
 namespace cdb {
 
-// chunks of the fused staged schedule when pipeline_chunks == 0 (auto): about 8 MiB of pencil per chunk, 1..16
+// chunks of the fused staged schedule when pipeline_chunks == 0 (auto): at least 128 MiB of pencil per chunk, 1..16
 int autoFusedChunks(int64_t pencil_bytes);
 
 void releaseFusedCache(cudecompGridDesc_t gd);

@@ -172,7 +172,8 @@ def _run_script(nranks, argv, timeout=600):
     return out, codes
 
 
-@pytest.mark.parametrize("layout", [[], ["--axis-contiguous"]], ids=["default", "axis_contiguous"])
+@pytest.mark.parametrize("layout", [[], ["--axis-contiguous"], ["--inplace"], ["--inplace", "--axis-contiguous"]],
+                         ids=["default", "axis_contiguous", "inplace", "inplace_axis_contiguous"])
 def test_distributed_fft_matches_numpy_fftn(layout):
     """benchmark/benchmark.cu's sequence (FFT per pencil + 4 transposes) on 4 ranks: forward transform equals
     numpy.fft.fftn of the whole field, forward + backward reproduces the input (tolerance 1e-10, benchmark.cu:21-27)."""
