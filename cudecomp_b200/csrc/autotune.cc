@@ -244,17 +244,20 @@ std::string describeSchedule(const Schedule& s) {
 }
 
 // CUDECOMP_B200_AUTOTUNE_SCHEDULES: which schedule dimensions the second tuning phase explores on the winning
-// (grid, family): comma list of tile, order, balance, chunks, bulk, pull, or "all". The CTA count is always swept (phase 1).
-// Default: none -- the dimensions below were added after the round-1 hardware budget was spent and join the default
-// sweep once confirmed on hardware.
+// (grid, family): comma list of tile, order, balance, chunks, bulk, pull, or "all" / "none". The CTA count is always
+// swept (phase 1). Default: tile, order, chunks -- the north star's "tile shape / CTA count / one-shot-vs-pairwise", plus
+// the chunk count of staged (in-place) calls. The other three are measured (profiles/r2_n2_schedules.md: balanced grid
+// within noise, TMA bulk equal on the wire and slower locally, receiver-driven slower in both directions at once) and
+// stay opt-in.
 struct ScheduleDims {
-  bool tile = false, order = false, balance = false, chunks = false, bulk = false, pull = false;
+  bool tile = true, order = true, balance = false, chunks = true, bulk = false, pull = false;
 };
 
 ScheduleDims scheduleDimsFromEnvironment() {
   ScheduleDims d;
   const char* v = std::getenv("CUDECOMP_B200_AUTOTUNE_SCHEDULES");
   if (!v) return d;
+  d.tile = d.order = d.chunks = false; // an explicit list replaces the default
   const std::string s(v);
   size_t start = 0;
   while (start <= s.size()) {
@@ -262,6 +265,7 @@ ScheduleDims scheduleDimsFromEnvironment() {
     if (end == std::string::npos) end = s.size();
     const std::string name = s.substr(start, end - start);
     if (name == "all") d.tile = d.order = d.balance = d.chunks = d.bulk = d.pull = true;
+    else if (name == "none") d = ScheduleDims{false, false, false, false, false, false};
     else if (name == "pull") d.pull = true;
     else if (name == "tile") d.tile = true;
     else if (name == "order") d.order = true;
@@ -502,7 +506,11 @@ void autotuneTransposes(cudecompHandle_t h, cudecompGridDesc_t gd, const cudecom
         tryAlternatives();
       }
       if (dims.chunks && (any_inplace || backendIsStaged(best_backend))) {
-        for (int k : {4, 8, 16}) {
+        // around what the library would pick from the pencil size (engine.cc autoFusedChunks): half and double
+        const int auto_k = autoFusedChunks(static_cast<int64_t>(gd->geom.gdims[0]) * gd->geom.gdims[1] * gd->geom.gdims[2] /
+                                           std::max(1, h->nranks) * es);
+        for (int k : {std::max(1, auto_k / 2), std::min(32, auto_k * 2)}) {
+          if (k == auto_k) continue;
           Schedule a = best_schedule;
           a.chunks = k;
           alternatives.push_back(a);
