@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--lag", type=int, default=0, help="phases between a chunk's push and its unpack (0 = library default)")
     ap.add_argument("--kernel-variant", type=int, default=0, help="cudecompB200SetKernelVariant value (3 = element-wise transpose)")
     ap.add_argument("--no-wire-wide", action="store_true", help="128-bit accesses also in launches that store into peers")
+    ap.add_argument("--no-column-chunks", action="store_true", help="fused staged schedule: plane chunks only")
     ap.add_argument("--phase-head", type=int, default=-1, help="percent of a step's pushes ahead of the unpacks (fused staged)")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed integer-pattern check after the timed region")
     ap.add_argument("--tile-bytes", type=int, default=0, help="row-copy tile size (0 = 32 KiB)")
@@ -291,6 +292,8 @@ def run_native(args, rank, world, local_rank):
 
     if args.no_wire_wide:
         os.environ["CUDECOMP_B200_WIRE_WIDE"] = "0"
+    if args.no_column_chunks:
+        os.environ["CUDECOMP_B200_COLUMN_CHUNKS"] = "0"
     if args.phase_head >= 0:
         os.environ["CUDECOMP_B200_PHASE_HEAD"] = str(args.phase_head)
     assert cd.MPI_Init() == 0

@@ -280,6 +280,7 @@ static void initHandle(cudecompHandle_t h, const CommPtr& parent) {
   if (const char* v = std::getenv("CUDECOMP_B200_FUSED_LAG")) h->fused_lag = std::min(8, std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("CUDECOMP_B200_PHASE_HEAD")) h->phase_head_percent = std::min(90, std::max(0, std::atoi(v)));
   if (const char* v = std::getenv("CUDECOMP_B200_TRANSPOSE_GEOM")) h->transpose_geometry = std::atoi(v) != 0 ? 1 : 0;
+  if (const char* v = std::getenv("CUDECOMP_B200_COLUMN_CHUNKS")) h->column_chunks = std::atoi(v) != 0 ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_WIRE_WIDE")) h->wire_wide = std::atoi(v) != 0 ? 1 : 0;
   if (const char* v = std::getenv("CUDECOMP_B200_DIRECT")) h->allow_direct = std::strcmp(v, "0") != 0;
   double spin_s = 60.0;
@@ -396,6 +397,7 @@ cudecompResult_t cudecompGridDescCreateVersioned(cudecompHandle_t handle, cudeco
   gd->fused_lag = handle->fused_lag;
   gd->phase_head_percent = handle->phase_head_percent;
   gd->wire_wide = handle->wire_wide;
+  gd->column_chunks = handle->column_chunks;
   if (gd->config.rank_order == CUDECOMP_RANK_ORDER_DEFAULT)
     gd->config.rank_order = handle->env_col_major ? CUDECOMP_RANK_ORDER_COL_MAJOR : CUDECOMP_RANK_ORDER_ROW_MAJOR;
 
@@ -943,10 +945,13 @@ int32_t cudecompB200PlanPipelinedTransposeBoxes(const cudecompGridDescConfig_t* 
   try {
     GridGeom g = geomFromConfig(config);
     if (rank < 0 || rank >= g.pdims[0] * g.pdims[1]) THROW_INVALID_USAGE("rank out of range");
-    // inplace: bit 0 = in place, bit 1 = receiver-driven (peer_rank of a push box then owns the SOURCE)
+    // inplace: bit 0 = in place, bit 1 = receiver-driven (peer_rank of a push box then owns the SOURCE), bits 8-15 =
+    // element size in bytes (0: plane chunks only; else column chunks where they apply, as the engine plans them),
+    // bit 2 = column chunks whatever the row length (tests on small grids)
     PipelinedPlan pp = buildPipelinedTransposePlan(g, pidxOfRank(g, rank), ax, dir, input_halo_extents,
                                                    output_halo_extents, input_padding, output_padding, (inplace & 1) != 0,
-                                                   nchunks, (inplace & 2) != 0);
+                                                   nchunks, (inplace & 2) != 0, (inplace >> 8) & 0xff,
+                                                   (inplace & 4) ? 1 : kMinChunkRowBytes);
     int32_t n = 0, total = 0;
     for (size_t s = 0; s < pp.steps.size(); ++s) {
       for (int pass = 0; pass < 2; ++pass) {

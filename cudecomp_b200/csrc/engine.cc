@@ -25,10 +25,11 @@ int64_t dtypeSize(cudecompDataType_t dtype) {
 uint64_t epochStride(const cudecompGridDesc_t gd) { return static_cast<uint64_t>(std::max(1, gd->pipeline_chunks)); }
 
 // Measured on B200 (profiles/r2_n2_schedules.md): a chunk costs about 10 us of pipeline bubbles (CTAs drift apart by a
-// tile within a step and wait for the slowest one anywhere before they unpack), so chunks are kept at >= 128 MiB of
-// pencil: 16 chunks for the 2 GiB pencils of 1024^3 complex128 on 8 GPUs, 4 for the 512 MiB ones of 512^3 complex64 on 2.
+// tile within a step and wait for the slowest one anywhere before they unpack), so chunks are kept at >= 256 MiB of
+// pencil: 8 chunks for the 2 GiB pencils of 1024^3 complex128 on 8 GPUs (9.01 ms per round trip against 9.34 with 16 and
+// 10.5 with 32, profiles/r2_n8_*.json), 2 for the 512 MiB ones of 512^3 complex64 on 2 GPUs.
 int autoFusedChunks(int64_t pencil_bytes) {
-  const int64_t k = pencil_bytes / (int64_t(128) << 20);
+  const int64_t k = pencil_bytes / (int64_t(256) << 20);
   return static_cast<int>(std::min<int64_t>(std::max<int64_t>(k, 1), 16));
 }
 
@@ -307,7 +308,7 @@ bool runFusedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, 
   auto put = [&](const void* p, size_t n) { key.append(static_cast<const char*>(p), n); };
   const int32_t zero3[3] = {0, 0, 0};
   const int32_t head[10] = {ax, dir, es, K, lag, gd->tile_bytes, inplace ? 1 : 0, P, gd->phase_head_percent,
-                            gd->kernel_variant * 2 + gd->wire_wide};
+                            gd->kernel_variant * 4 + gd->wire_wide * 2 + gd->column_chunks};
   put(head, sizeof(head));
   put(&input, sizeof(input));
   put(&output, sizeof(output));
@@ -323,7 +324,9 @@ bool runFusedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, 
     if (e.key == key) entry = &e;
   if (!entry) {
     PipelinedPlan pp;
-    if (K > 1) pp = buildPipelinedTransposePlan(gd->geom, gd->pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, inplace, K, false);
+    if (K > 1)
+      pp = buildPipelinedTransposePlan(gd->geom, gd->pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, inplace, K, false,
+                                       gd->column_chunks ? es : 0);
     std::vector<std::vector<ResolvedBox>> push, unpack;
     if (K > 1 && !pp.steps.empty()) {
       push.resize(pp.steps.size());

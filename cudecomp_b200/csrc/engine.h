@@ -69,6 +69,7 @@ struct cudecompHandle {
   int fused_lag = 1;             // CUDECOMP_B200_FUSED_LAG
   int phase_head_percent = 25;   // CUDECOMP_B200_PHASE_HEAD
   int wire_wide = 1;             // CUDECOMP_B200_WIRE_WIDE=0: 128-bit accesses on the wire too
+  int column_chunks = 1;         // CUDECOMP_B200_COLUMN_CHUNKS=0: plane chunks only
   int transpose_geometry = 0;    // CUDECOMP_B200_TRANSPOSE_GEOM=1: 64 x 32 tiles for 8-byte vectorised transposes
   cdb::AckBoard acks;            // which of my release announcements every rank has processed
   struct Released {              // freed by the caller, still mapped by peers: the real cudaFree waits for their acks
@@ -113,13 +114,14 @@ struct cudecompGridDesc {
   int staged_mode = 0;
   int fused_lag = 1;
   int wire_wide = 1;           // 256-bit accesses in launches that store into peers (kernel_variant 0 only)
+  int column_chunks = 1;       // fused staged schedule: chunk along the fastest axis when it takes no part (plan.cc)
   int phase_head_percent = 25; // share of a step's pushes that runs before the unpacks of the earlier chunk join in
   std::vector<cdb::FusedPlanEntry> fused_cache; // device tables of phased launches, keyed by everything they depend on
 };
 
 namespace cdb {
 
-// chunks of the fused staged schedule when pipeline_chunks == 0 (auto): at least 128 MiB of pencil per chunk, 1..16
+// chunks of the fused staged schedule when pipeline_chunks == 0 (auto): at least 256 MiB of pencil per chunk, 1..16
 int autoFusedChunks(int64_t pencil_bytes);
 
 void releaseFusedCache(cudecompGridDesc_t gd);

@@ -135,9 +135,11 @@ inline std::pair<int64_t, int64_t> chunkRange(int64_t n, int K, int k) { return 
 
 PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dir,
                                           const int32_t in_halo[3], const int32_t out_halo[3], const int32_t in_pad[3],
-                                          const int32_t out_pad[3], bool inplace, int nchunks, bool pull) {
+                                          const int32_t out_pad[3], bool inplace, int nchunks, bool pull, int elem_bytes,
+                                          int64_t min_row_bytes) {
   if (pull) {
-    PipelinedPlan mine = buildPipelinedTransposePlan(g, pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, inplace, nchunks);
+    PipelinedPlan mine = buildPipelinedTransposePlan(g, pidx, ax, dir, in_halo, out_halo, in_pad, out_pad, inplace, nchunks,
+                                                     false, elem_bytes, min_row_bytes);
     if (mine.steps.empty()) return mine;
     const int ci = mine.base.axes.comm;
     for (auto& st : mine.steps) st.push.clear();
@@ -145,7 +147,8 @@ PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<in
       auto pj = pidx;
       pj[ci] = j;
       const PipelinedPlan theirs =
-          buildPipelinedTransposePlan(g, pj, ax, dir, in_halo, out_halo, in_pad, out_pad, inplace, nchunks);
+          buildPipelinedTransposePlan(g, pj, ax, dir, in_halo, out_halo, in_pad, out_pad, inplace, nchunks, false, elem_bytes,
+                                      min_row_bytes);
       for (size_t s = 0; s < theirs.steps.size() && s < mine.steps.size(); ++s)
         for (BoxDesc b : theirs.steps[s].push) {
           if (b.peer != mine.base.me) continue;
@@ -167,7 +170,21 @@ PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<in
   const Pencil pa_h = pencilInfo(g, pidx, a, in_halo, in_pad);
   const Pencil pb = pencilInfo(g, pidx, b, nullptr, nullptr);
   const Pencil pb_h = pencilInfo(g, pidx, b, out_halo, out_pad);
-  const int G = pa.order[2]; // slowest axis of the source: chunks are ranges of source planes
+  // Chunk axis. Default: the slowest axis of the source, so that chunks are ranges of source planes and the in-place
+  // hazard analysis below works on address intervals. Better where it applies: the axis c that takes no part in the
+  // transpose, when it is the FASTEST axis of both pencils (same memory order, same halo and padding along c). Both
+  // pencils then consist of rows of one length, chunk k is the same column range of every row on both sides, and what
+  // chunk k writes lies inside what chunk k has read (or outside the source pencil): every piece can be unpacked in the
+  // step it arrives, with nothing piling up behind the last push. (With the default layout that is Y<->Z, chunked along
+  // x; for X<->Y the planes along z coincide already.) Rows must stay at least kMinChunkRowBytes long.
+  const int c_axis = pp.base.axes.c;
+  bool column_chunks = false;
+  if (pa.order == pb.order && pa.order[0] == c_axis && pa_h.halo[c_axis] == pb_h.halo[c_axis] &&
+      pa_h.pad[c_axis] == pb_h.pad[c_axis]) {
+    const int64_t row_bytes = pa.shapeG()[c_axis] * static_cast<int64_t>(elem_bytes > 0 ? elem_bytes : 1);
+    column_chunks = elem_bytes > 0 && row_bytes / K >= min_row_bytes;
+  }
+  const int G = column_chunks ? c_axis : pa.order[2];
   pp.chunk_axis = G;
   const auto splits_a = getSplits(g.gdims_dist[a], P, g.gdims[a] - g.gdims_dist[a]);
   const auto splits_b = getSplits(g.gdims_dist[b], P, g.gdims[b] - g.gdims_dist[b]);
@@ -263,7 +280,7 @@ PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<in
         return st;
       };
       int step = k;
-      if (inplace) {
+      if (inplace && !column_chunks) {
         step = firstFreeStep(piece);
         // A piece that has to wait is cut along the slowest axis of the destination layout and every part waits only
         // for the source planes IT overwrites: a piece spans P source slices' worth of memory when G is the split

@@ -83,9 +83,13 @@ struct PipelinedPlan {
 // pushed to me in its step s (its source strides, `peer` = j); the unpack lists are unchanged, because the same data
 // lands in my workspace at the same step and the planes of my pencil that are still unread after step s are the same
 // (they are now read by the peers' later steps instead of by mine).
+// elem_bytes > 0 allows column chunks (chunks along the fastest axis when it takes no part in the transpose, see
+// plan.cc) as long as a chunk's rows stay kMinChunkRowBytes long; 0 keeps plane chunks.
+constexpr int64_t kMinChunkRowBytes = 1024;
 PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dir,
                                           const int32_t in_halo[3], const int32_t out_halo[3], const int32_t in_pad[3],
-                                          const int32_t out_pad[3], bool inplace, int nchunks, bool pull = false);
+                                          const int32_t out_pad[3], bool inplace, int nchunks, bool pull = false,
+                                          int elem_bytes = 0, int64_t min_row_bytes = kMinChunkRowBytes);
 
 struct HaloPlan {
   bool nothing = false; // zero halo width, or no neighbour in this dimension

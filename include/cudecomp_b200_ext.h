@@ -111,7 +111,9 @@ int32_t cudecompB200PlanHaloBoxes(const cudecompGridDescConfig_t* config, int32_
 
 /* The chunked (pipelined) variant of the staged schedule for `nchunks` chunks (csrc/plan.h PipelinedPlan): boxes carry
  * the step they run in. Returns 0 boxes when chunking does not apply. `inplace`: bit 0 = in place, bit 1 = receiver-
- * driven (cudecompB200SetTransferMode; peer_rank of a push box is then the rank whose input it is loaded from). */
+ * driven (cudecompB200SetTransferMode; peer_rank of a push box is then the rank whose input it is loaded from),
+ * bits 8-15 = element size in bytes: non-zero allows column chunks (chunks along the fastest axis when it takes no part
+ * in the transpose) the way the engine plans them, bit 2 = ... whatever the row length. */
 int32_t cudecompB200PlanPipelinedTransposeBoxes(const cudecompGridDescConfig_t* config, int32_t rank, int32_t ax,
                                                 int32_t dir, const int32_t input_halo_extents[],
                                                 const int32_t output_halo_extents[], const int32_t input_padding[],

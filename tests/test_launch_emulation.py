@@ -271,7 +271,9 @@ def test_emulated_fused_staged_schedule_equals_oracle(d, s, K, inplace, lag, lat
         if list(o.pencil_info(0, a).order) != list(o.pencil_info(0, b).order):
             continue  # differing memory orders: the engine keeps separate launches (engine.cc runFusedStaged)
         if K > 1:
-            plans = [cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, int(inplace), K) for r in range(n)]
+            # column chunks (plan.cc) on every other example: element size in bits 8-15, bit 2 lifts the row-length floor
+            flags = int(inplace) + ((s["es"] << 8) + 4 if s["grid"] in (0, 3) else 0)
+            plans = [cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, flags, K) for r in range(n)]
             nsteps = K
         else:
             plans = [cd.plan_transpose_boxes(cfg, r, ax, direction, ha, hb, pa, pb, staged=1) for r in range(n)]

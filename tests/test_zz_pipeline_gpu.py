@@ -35,6 +35,11 @@ CASES = CASES + [dict(c, name=c["name"] + "_launches", staged_mode=1) for c in C
          ops=["XY", "YZ", "ZY", "YX"] * 2, pipeline_chunks=16),
     dict(kind="transpose", name="Fused_oop_forced_staging_4x1", gdims=[96, 128, 64], pdims=[4, 1], dtype="double",
          ops=["XY", "YZ", "ZY", "YX"], out_of_place=True, force_staged=True, pipeline_chunks=5),
+    # rows of 8 KiB: Y<->Z is chunked along x (column chunks, plan.cc), X<->Y along z
+    dict(kind="transpose", name="Fused_column_chunks_inplace_2x2_c128", gdims=[1024, 24, 20], pdims=[2, 2],
+         dtype="double_complex", ops=["XY", "YZ", "ZY", "YX"] * 2, pipeline_chunks=4),
+    dict(kind="transpose", name="Fused_column_chunks_inplace_1x4_uneven_f64", gdims=[1030, 18, 22], pdims=[1, 4],
+         dtype="double", ops=["XY", "YZ", "ZY", "YX"], pipeline_chunks=3),
 ]
 
 
@@ -57,6 +62,8 @@ STRESS = [
     dict(kind="stress", name="Stress_fused_inplace_lag1_1x4", gdims=[96, 64, 128], pdims=[1, 4], dtype="double", reps=12,
          pipeline_chunks=6, fused_lag=1),
     dict(kind="stress", name="Stress_fused_inplace_auto_4x1_uneven", gdims=[101, 99, 67], pdims=[4, 1], dtype="float", reps=12),
+    dict(kind="stress", name="Stress_fused_column_chunks_2x2", gdims=[1024, 32, 24], pdims=[2, 2], dtype="double_complex",
+         reps=12, pipeline_chunks=8),
     dict(kind="stress", name="Stress_launches_inplace_2x2", gdims=[128, 96, 64], pdims=[2, 2], dtype="double", reps=6,
          pipeline_chunks=4, staged_mode=1),
     dict(kind="stress", name="Stress_direct_oop_2x2", gdims=[128, 96, 64], pdims=[2, 2], dtype="double_complex", reps=12,
