@@ -84,8 +84,8 @@ struct PipelinedPlan {
 // lands in my workspace at the same step and the planes of my pencil that are still unread after step s are the same
 // (they are now read by the peers' later steps instead of by mine).
 // elem_bytes > 0 allows column chunks (chunks along the fastest axis when it takes no part in the transpose, see
-// plan.cc) as long as a chunk's rows stay kMinChunkRowBytes long; 0 keeps plane chunks.
-constexpr int64_t kMinChunkRowBytes = 1024;
+// plan.cc) with the largest chunk count <= nchunks whose rows are whole multiples of min_row_bytes; 0 keeps plane chunks.
+constexpr int64_t kMinChunkRowBytes = 2048;
 PipelinedPlan buildPipelinedTransposePlan(const GridGeom& g, const std::array<int, 2>& pidx, int ax, int dir,
                                           const int32_t in_halo[3], const int32_t out_halo[3], const int32_t in_pad[3],
                                           const int32_t out_pad[3], bool inplace, int nchunks, bool pull = false,
