@@ -218,7 +218,12 @@ void destroyGridDescResources(cudecompGridDesc_t gd, bool collective) {
   }
   gd->mbox.destroy();
   releaseFusedCache(gd);
-  if (collective) drainReleases(h);
+  if (collective) {
+    // Drop every mapping of peer memory (imports are re-created on demand by the descriptors that stay alive): buffers
+    // the CALLER owns may be freed once the descriptor they were used with is gone, and nothing may still map them then.
+    if (h->have_device) h->peers.clear();
+    drainReleases(h);
+  }
   for (cudaEvent_t e : gd->side_events) cudaEventDestroy(e);
   gd->side_events.clear();
   if (gd->side_stream) cudaStreamDestroy(gd->side_stream);

@@ -1,9 +1,12 @@
 #!/usr/bin/env python
 """What the engine will do for a configuration, computed on the host (no GPU): per operation the boxes each rank
-pushes, their tiling and grid-stride rounds, and -- for staged / in-place calls -- the chunked schedule: which peers every
-step talks to and how much of the local unpack overlaps later pushes. A design aid; every number here is arithmetic on
-the plans (cudecompB200Plan* entry points), not a measurement. The time model at the end uses the measured rates of
-profiles/ (HBM copy 6.5 TB/s, SM stores over NVLink 0.66 TB/s per direction, ~5 us per in-kernel handshake).
+pushes, their tiling and grid-stride rounds, and -- for staged / in-place calls -- the chunked schedule of the fused launch:
+which peers every step talks to and how much of the local unpack overlaps later pushes. A design aid; every number here
+is arithmetic on the plans (cudecompB200Plan* entry points), not a measurement. The time model at the end uses the rates
+measured in round 2 (profiles/r2_*): HBM copy 6.45 TB/s, 5.0 TB/s for the five-stream read/write mix of a fused staged
+launch, SM stores over NVLink 0.69 TB/s per direction (256-bit stores), 4 us per in-kernel handshake, 10 us per chunk.
+It gives 7.81 / 10.48 / 8.9 ms for the 1024^3 complex128 2x4 round trip out of place / in place with separate launches /
+in place fused; measured 7.83 / 10.5 / 9.0-9.1 ms (profiles/r2_n8_results.md).
 
     python scripts/explain_plan.py --grid 1024 --pdims 2x4 --dtype double_complex --chunks 8
 """
@@ -18,7 +21,7 @@ sys.path.insert(0, ROOT)
 
 OPS = {"XY": (0, 1), "YZ": (1, 1), "ZY": (2, -1), "YX": (1, -1)}
 ES = {"float": 4, "double": 8, "float_complex": 8, "double_complex": 16}
-HBM, LINK, HANDSHAKE_US = 6.5e12, 0.66e12, 5.0
+HBM, HBM_MIX, LINK, HANDSHAKE_US, CHUNK_US = 6.45e12, 5.0e12, 0.69e12, 4.0, 10.0
 
 
 def main():
@@ -66,7 +69,10 @@ def main():
         total_staged += t_direct + t_unpack
         if len(boxes) > 1 and args.chunks > 1:
             K = args.chunks
-            pb = cd.plan_pipelined_transpose_boxes(c, args.rank, ax, d, None, None, None, None, True, K, max_boxes=8192)
+            # as the engine plans it: in place, column chunks where they apply (element size in bits 8-15 of the flags)
+            pb = cd.plan_pipelined_transpose_boxes(c, args.rank, ax, d, None, None, None, None, 1 + (es << 8), K,
+                                                   max_boxes=8192)
+            K = 1 + max(b["step"] for b in pb)
             unp, peers = [0] * K, [set() for _ in range(K)]
             for b in pb:
                 n = int(np.prod(b["extent"])) * es
@@ -75,8 +81,8 @@ def main():
                 else:
                     peers[b["step"]].add(b["peer_rank"])
             exposed = unp[-1]
-            t_chunked = wire / LINK * 1e3 + (K + 1) * HANDSHAKE_US * 1e-3 + 2 * exposed / HBM * 1e3
-            print("   chunked, K = %d, in place: peers per step %s; unpacked beside later pushes %.0f %%, after the last "
+            t_chunked = max(wire / LINK, 4 * S / HBM_MIX) * 1e3 + (K * CHUNK_US + HANDSHAKE_US) * 1e-3 + 2 * exposed / HBM * 1e3
+            print("   fused, %d chunks, in place: peers per step %s; unpacked beside later pushes %.0f %%, after the last "
                   "push %.0f %%  -> model %.3f ms" % (K, sorted({len(p) for p in peers}),
                                                       100 * (1 - exposed / max(sum(unp), 1)), 100 * exposed / max(sum(unp), 1),
                                                       t_chunked))
@@ -84,7 +90,7 @@ def main():
             total_chunked += t_chunked
         else:
             total_chunked += t_direct + t_unpack
-    print("\nround trip, model: out of place (direct) %.2f ms; in place staged %.2f ms; in place chunked (K = %d) %.2f ms" %
+    print("\nround trip, model: out of place (direct) %.2f ms; in place, separate launches %.2f ms; in place fused (K = %d) %.2f ms" %
           (total_direct, total_staged, args.chunks, total_chunked))
 
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Turns the JSON lines scripts/r2_gpu_confirm.sh leaves in gpurun_out/ into one markdown table per GPU count
+"""Turns the JSON lines the scripts/r2_*.sh runbooks leave in gpurun_out/ into one markdown table per GPU count
 (label, ms per round trip, per-operation ms, roofline fraction, path), next to the default schedule of the same run, so
 that the winners can be made defaults and the table can be committed under profiles/.
     python scripts/r2_summarize.py [gpurun_out] > profiles/r2_schedules.md"""

@@ -4,7 +4,10 @@ The copy kernels of different ranks and streams run concurrently; what keeps the
 (b) events between the caller's stream and the side stream of the chunked schedule, and (c) the in-kernel handshake:
   entry : no access of a launch begins before every member of its communicator has STARTED the same launch
           (a member's launch starts after everything earlier on its stream);
-  exit  : a launch does not COMPLETE before every member has finished its accesses.
+  exit  : a launch does not COMPLETE before every member has finished its accesses;
+  step  : (fused staged schedule, kernels.cu rowCopyPhasedKernel) inside ONE launch per rank, the unpack of chunk s
+          begins only after every member has finished pushing chunks 0..s; pushes of different chunks and unpacks of
+          different chunks are otherwise unordered (CTAs drift), and there is NO exit handshake.
 This test restates the launch structure of engine.cc (runTranspose: direct / staged / chunked, sender- and
 receiver-driven) as a graph of such orderings, takes the boxes of every launch from the planner entry points of
 libcudecomp.so, and requires a happens-before path between any two accesses of different launches that touch the same
@@ -128,6 +131,10 @@ def build_chain(d, mode, inplace, K=4, broken=None):
         if P == 1:
             # engine.cc: one rank per communicator -> local path: out of place one direct copy, in place through `work`
             eff = "staged" if inplace else "direct"
+        if eff == "fused":
+            fused_launches(g, cfg, n, op, opi, ax, direction, inplace, K, src_name, dst_name, last_main, broken)
+            cur = [dst_name] * n
+            continue
         plans = {}
         for r in range(n):
             if eff in ("chunked", "pull_chunked"):
@@ -184,6 +191,52 @@ def build_chain(d, mode, inplace, K=4, broken=None):
     return g
 
 
+def fused_launches(g, cfg, n, op, opi, ax, direction, inplace, K, src_name, dst_name, last_main, broken):
+    """engine.cc runFusedStaged: one phased launch per rank. Column chunks where the planner uses them (element size 8,
+    no row-length floor on these small grids)."""
+    flags = int(inplace) + (8 << 8) + 4
+    plans = {r: cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, None, None, None, None, flags, K) for r in range(n)}
+    if not any(plans.values()):  # chunking does not apply: the plain staged plan as ONE step
+        plans = {r: [dict(b, step=0) for b in cd.plan_transpose_boxes(cfg, r, ax, direction, None, None, None, None, 1)]
+                 for r in range(n)}
+    steps = 1 + max(b["step"] for r in range(n) for b in plans[r])
+    groups = {}
+    for r in range(n):
+        members = tuple(sorted({b["peer_rank"] for b in plans[r] if not b["is_unpack"]} | {r}))
+        groups[r] = members
+    kern, push, unpack = {}, {}, {}
+    for r in range(n):
+        kern[r] = g.launch(r, "main", "%s#%d fused r%d" % (op, opi, r), [last_main[r]] if last_main[r] is not None else [])
+        for s in range(steps):
+            P = g.launch(r, "main", "%s#%d push%d r%d" % (op, opi, s, r), [kern[r]["start"]])
+            g.edge(P["done"], kern[r]["done"])
+            for b in plans[r]:
+                if not b["is_unpack"] and b["step"] == s:
+                    P["reads"].append(((r, src_name), cells(b, "src")))
+                    P["writes"].append(((b["peer_rank"], "work"), cells(b, "dst")))
+            push[r, s] = P
+            U = g.launch(r, "main", "%s#%d unpack%d r%d" % (op, opi, s, r), [kern[r]["start"]])
+            g.edge(U["done"], kern[r]["done"])
+            for b in plans[r]:
+                if b["is_unpack"] and b["step"] == s:
+                    U["reads"].append(((r, "work"), cells(b, "src")))
+                    U["writes"].append(((r, dst_name), cells(b, "dst")))
+            unpack[r, s] = U
+        last_main[r] = kern[r]["done"]
+    for r in range(n):
+        for m in groups[r]:
+            for s in range(steps):
+                if m != r and broken != "fused_no_entry":
+                    # entry handshake: nothing of mine touches memory before every member has started its launch
+                    g.edge(kern[m]["start"], push[r, s]["begin"])
+                    g.edge(kern[m]["start"], unpack[r, s]["begin"])
+                # step flags + local counter: chunk s is unpacked after every member has pushed chunks 0..s
+                for t in range(0, s + 1):
+                    if broken == "fused_unpack_early" and t == s:
+                        continue
+                    g.edge(push[m, t]["end"], unpack[r, s]["begin"])
+
+
 def decomposition(gdims, pdims, axis_contiguous=False):
     return dict(gdims=gdims, pdims=pdims, axis_contiguous=[axis_contiguous] * 3, mem_order=None, gdims_dist=None,
                 col_major=False, halos={str(a): [0, 0, 0] for a in range(3)}, pads={str(a): [0, 0, 0] for a in range(3)})
@@ -196,7 +249,8 @@ GRIDS = [([8, 6, 10], [2, 2], False), ([7, 9, 8], [2, 2], True), ([8, 8, 8], [1,
 @pytest.mark.parametrize("gdims,pdims,ac", GRIDS, ids=["%dx%d%s" % (p[0], p[1], "_ac" if a else "") for _, p, a in GRIDS])
 @pytest.mark.parametrize("mode,inplace", [("direct", False), ("pull", False), ("staged", True), ("staged", False),
                                           ("pull_staged", True), ("pull_staged", False), ("chunked", True),
-                                          ("chunked", False), ("pull_chunked", True), ("pull_chunked", False)])
+                                          ("chunked", False), ("pull_chunked", True), ("pull_chunked", False),
+                                          ("fused", True), ("fused", False)])
 def test_schedules_are_race_free(gdims, pdims, ac, mode, inplace):
     g = build_chain(decomposition(gdims, pdims, ac), mode, inplace, K=3)
     assert g.races() == []
@@ -210,3 +264,8 @@ def test_the_checker_sees_known_races():
     assert build_chain(d, "pull", True).races()
     # an unpack that does not wait for the push that delivers its data
     assert build_chain(d, "chunked", True, K=3, broken="unpack_does_not_wait").races()
+    # fused schedule: an unpack that only waits for the chunk BEFORE its own; no entry handshake (a peer of the next
+    # operation pushes into a workspace that is still being unpacked -- the exit handshake the fused launch omits is not
+    # what protects it, the next launch's entry handshake is)
+    assert build_chain(d, "fused", True, K=3, broken="fused_unpack_early").races()
+    assert build_chain(d, "fused", True, K=3, broken="fused_no_entry").races()
