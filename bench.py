@@ -183,6 +183,23 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def index_pattern(torch, pinfo, gdims, es, device):
+    """The reference tests' known answer for a pencil WITHOUT halos or padding (tests/ctest/transpose_tests.cc:333-354):
+    every element carries its global linear index, here as an integer bit pattern so that no float rounding is
+    involved: int32 for 4-byte elements (index mod 2^32), int64 for 8-byte ones, the pair (index, ~index) for 16-byte
+    ones. `pinfo` is a cudecompPencilInfo_t (shape / lo / order by memory position). Flat tensor in memory order."""
+    gstride = [1, gdims[0], gdims[0] * gdims[1]]
+    idt = torch.int32 if es == 4 else torch.int64
+    terms = []
+    for k in range(3):
+        v = (torch.arange(pinfo.shape[k], device=device, dtype=torch.int64) + pinfo.lo[k]) * gstride[pinfo.order[k]]
+        terms.append(v.to(idt))
+    g = (terms[2][:, None, None] + terms[1][None, :, None] + terms[0][None, None, :]).reshape(-1)
+    if es == 16:
+        return torch.stack([g, ~g], dim=1).reshape(-1)
+    return g
+
+
 def mem_available_bytes():
     try:
         with open("/proc/meminfo") as f:
@@ -384,19 +401,10 @@ def run_native(args, rank, world, local_rank):
     parity = None
     if not args.no_parity:
         infos = [cd.cudecompGetPencilInfo(handle, gd, ax)[1] for ax in range(3)]
-        gstride = [1, args.n, args.n * args.n]
         idt = torch.int32 if es == 4 else torch.int64
 
         def expected(ax):
-            p = infos[ax]
-            terms = []
-            for k in range(3):
-                v = (torch.arange(p.shape[k], device=dev, dtype=torch.int64) + p.lo[k]) * gstride[p.order[k]]
-                terms.append(v.to(idt))
-            g = (terms[2][:, None, None] + terms[1][None, :, None] + terms[0][None, None, :]).reshape(-1)
-            if es == 16:
-                return torch.stack([g, ~g], dim=1).reshape(-1)
-            return g
+            return index_pattern(torch, infos[ax], [args.n] * 3, es, dev)
 
         def as_ints(t, nelem):
             return t.view(idt)[: nelem * (2 if es == 16 else 1)]

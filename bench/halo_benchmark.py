@@ -14,6 +14,34 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def halo_pattern(torch, p, grid, halo, periods, es, device, halo_cells):
+    """Known answer of the reference's halo tests (tests/ctest/halo_tests.cc:197-236) as integer bit patterns, for a
+    pencil with halos and no padding. halo_cells False: initializePencil -- interior cells carry their global linear
+    index, halo cells are unset (-1). True: initializeReference -- the state after the halos of all three dimensions were
+    updated: every cell carries the index of the (periodically wrapped) global cell it mirrors, -1 where there is none.
+    int32 for 4-byte elements (index mod 2^32), int64 for 8-byte ones, (index, ~index) pairs for 16-byte ones."""
+    idt = torch.int32 if es == 4 else torch.int64
+    gstride = [1, grid[0], grid[0] * grid[1]]
+    terms, masks = [], []
+    for k in range(3):
+        ax_g = p.order[k]
+        g = torch.arange(p.shape[k], device=device, dtype=torch.int64) + (p.lo[k] - halo[ax_g])
+        inside = (g >= p.lo[k]) & (g <= p.hi[k])
+        if halo_cells:
+            valid = torch.ones_like(inside) if periods[ax_g] else ((g >= 0) & (g < grid[ax_g]))
+            g = torch.remainder(g, grid[ax_g])
+        else:
+            valid = inside
+        terms.append(g * gstride[ax_g])
+        masks.append(valid)
+    idx = terms[2][:, None, None] + terms[1][None, :, None] + terms[0][None, None, :]
+    ok = masks[2][:, None, None] & masks[1][None, :, None] & masks[0][None, None, :]
+    out = torch.where(ok, idx, torch.full_like(idx, -1)).to(idt).reshape(-1)
+    if es == 16:
+        out = torch.stack([out, ~out], dim=1).reshape(-1)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grid", type=int, nargs=3, default=[2048, 2048, 1024])
@@ -56,28 +84,10 @@ def main():
               "of the (periodically wrapped) global cell it mirrors, -1 where there is none: the comparator of the "
               "reference's tests/ctest/halo_tests.cc:229-272, on the device, on every rank"}
     idt = torch.int32 if es == 4 else torch.int64
-    gstride = [1, args.grid[0], args.grid[0] * args.grid[1]]
 
     def pattern(p, halo_cells):
-        """halo_cells False: interior = index, halo cells unset (-1); True: the expected state after all three updates."""
-        terms, masks = [], []
-        for k in range(3):
-            ax_g = p.order[k]
-            g = torch.arange(p.shape[k], device=dev, dtype=torch.int64) + (p.lo[k] - args.halo[ax_g])
-            inside = (g >= p.lo[k]) & (g <= p.hi[k])
-            if halo_cells:
-                valid = torch.ones_like(inside) if periods[ax_g] else ((g >= 0) & (g < args.grid[ax_g]))
-                g = torch.remainder(g, args.grid[ax_g])
-            else:
-                valid = inside
-            terms.append(g * gstride[ax_g])
-            masks.append(valid)
-        idx = terms[2][:, None, None] + terms[1][None, :, None] + terms[0][None, None, :]
-        ok = masks[2][:, None, None] & masks[1][None, :, None] & masks[0][None, None, :]
-        out = torch.where(ok, idx, torch.full_like(idx, -1)).to(idt).reshape(-1)
-        if es == 16:
-            out = torch.stack([out, ~out], dim=1).reshape(-1)
-        return out
+        return halo_pattern(torch, p, args.grid, args.halo, periods, es, dev, halo_cells)
+
     for ax in range(3):
         res, p = cd.cudecompGetPencilInfo(handle, gd, ax, args.halo)
         cd.check(res)
