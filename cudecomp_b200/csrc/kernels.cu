@@ -1,17 +1,27 @@
 // Box-copy kernels for sm_100a. See kernels.h.
 //
 // Data path per box: coalesced 16-byte loads from the local pencil (LDG.128, streaming), 16-byte stores
-// to the destination (STG.128) which is either local HBM or a peer GPU's memory mapped over NVLink.
+// to the destination (STG.128) which is either local HBM or a peer GPU's memory mapped over NVLink
+// (32-byte LDG/STG.256 in launches that store into peers: +3 % on the wire, measured).
 // The kernels are persistent: a fixed grid of CTAs walks the tile list, and consecutive tiles belong
 // to different peers so every peer's ingress is fed evenly for the whole duration of the launch.
+// Kernels: rowCopyKernel (contiguous rows on both sides), transposeVecKernel / transposeKernel (memory
+// orders differ: 16-byte micro-tile transpose through a swizzled shared tile / element-wise fallback),
+// rowCopyPhasedKernel (the fused staged schedule of in-place calls: push chunk s, unpack chunk s - lag,
+// per-chunk flags), rowCopyBulkKernel (TMA variant, opt-in).
 //
 // Cross-GPU ordering lives in the same launch (no host synchronisation, no second kernel):
 //   entry : CTA 0 stores the operation's epoch into slot [me] of each peer's signal pad; every CTA then
 //           waits until the local pad shows that epoch for each peer. A peer's kernel only starts after
 //           that peer's earlier stream work, so from here on its buffers may be overwritten.
-//   exit  : each CTA fences its stores (fence.sys) and bumps a local counter; the last CTA publishes
-//           "done" to every peer and waits for every peer's "done". Kernel completion therefore means
-//           both "my data has landed everywhere" and "everyone's data has landed here".
+//   exit  : each CTA fences its stores (one thread, after a CTA barrier: the fence is cumulative) and bumps a
+//           local counter; the last CTA publishes "done" to every peer and waits for every peer's "done".
+//           Kernel completion therefore means both "my data has landed everywhere" and "everyone's data
+//           has landed here".
+//   step  : (phased kernel) after its share of chunk s a CTA fences and bumps counter[s]; the last CTA
+//           publishes (epoch, s) to every peer with red.max; unpack tiles of chunk s wait for every peer's
+//           (epoch, s) and for counter[s] == grid. No exit handshake: the last chunk's waits subsume it.
+// A wait that times out records an error for the host and the launch leaves WITHOUT moving (more) data.
 #include "kernels.h"
 
 #include <atomic>
