@@ -309,6 +309,53 @@ def test_emulated_fused_staged_schedule_equals_oracle(d, s, K, inplace, lag, lat
             assert np.array_equal(outs[r], ref_out[r]), (d, s, op, K, inplace, lag, late, r)
 
 
+@pytest.mark.parametrize("gdims,pdims,es,K,tile_bytes,flags", [
+    ([256, 64, 48], [2, 2], 16, 4, 4096, 0),             # plane chunks, boxes of several hundred tiles
+    ([1024, 24, 20], [2, 2], 16, 4, 4096, (16 << 8)),    # column chunks with the engine's 2 KiB row rule (Y<->Z along x)
+    ([512, 40, 36], [1, 4], 8, 8, 8192, (8 << 8)),       # 4 KiB rows: column chunks reduce 8 chunks to 2
+    ([250, 60, 44], [4, 1], 4, 5, 4096, 0),              # uneven splits, 4-byte elements
+])
+def test_emulated_fused_schedule_with_many_segments(gdims, pdims, es, K, tile_bytes, flags):
+    """The hypothesis examples above are tiny (every box is one tile, one segment). Here boxes have hundreds of tiles, so
+    phases hold many 64-tile segments per box, partly filled last segments and the head / tail split of the pushes; in
+    place, earliest legal order, head 25 % and lag 1 as the engine runs it."""
+    d = dict(gdims=gdims, pdims=pdims, axis_contiguous=[False] * 3, mem_order=None, gdims_dist=None, col_major=False,
+             halos={str(a): [0, 0, 0] for a in range(3)}, pads={str(a): [0, 0, 0] for a in range(3)})
+    cfg, o = make_config(d), make_oracle(d)
+    n = o.nranks
+    dt = DT[es]
+    rng = np.random.default_rng(11)
+    for op, (ax, direction) in OPS.items():
+        a, b = orc.transpose_axes(op)
+        plans = [cd.plan_pipelined_transpose_boxes(cfg, r, ax, direction, None, None, None, None, 1 + flags, K)
+                 for r in range(n)]
+        if not any(plans):
+            continue
+        nsteps = 1 + max(bx["step"] for p in plans for bx in p)
+        sizes = [max(o.pencil_info(r, a).size, o.pencil_info(r, b).size) for r in range(n)]
+        bufs = [emu.aligned_array(sizes[r], dt, 0, -3) for r in range(n)]
+        for r in range(n):
+            rand_fill(bufs[r][:o.pencil_info(r, a).size], rng)
+        ref = [x.copy() for x in bufs]
+        o.transpose(op, ref, ref)
+        works = [emu.aligned_array(max(o.transpose_workspace_size(), 1), dt, 0, -9) for _ in range(n)]
+        legal = bufs + works
+        seen_segments = 0
+        for step in range(nsteps):
+            for want_unpack in (False, True):
+                for r in range(n):
+                    bx = plans[r]
+                    srcs = [works[r] if x["is_unpack"] else bufs[r] for x in bx]
+                    dsts = [bufs[r] if x["is_unpack"] else works[x["peer_rank"]] for x in bx]
+                    st_ = emu.run_phased(bx, srcs, dsts, es, legal, nsteps, 1, want_unpack, step, tile_bytes=tile_bytes,
+                                         grid=37, kernel_variant=2, head_percent=25)
+                    assert st_ is not None
+                    seen_segments = max(seen_segments, st_["slots"])
+        assert seen_segments > 64 * 4  # more slots than one segment per box: the segment interleave was exercised
+        for r in range(n):
+            assert np.array_equal(bufs[r], ref[r]), (op, r)
+
+
 def test_kernel_selection_and_vector_width():
     """Default-layout transposes are row copies at the widest vector the alignment allows; differing memory orders go
     through the tiled transpose kernel; the bulk variant only takes over for 16-byte aligned rows of at least 2 KiB."""
