@@ -39,6 +39,7 @@ void releaseFusedCache(cudecompGridDesc_t gd) {
   for (auto& e : gd->fused_cache) {
     if (e.dev) cudaFree(e.dev);
     if (e.host) cudaFreeHost(e.host);
+    if (e.uploaded) cudaEventDestroy(e.uploaded);
   }
   gd->fused_cache.clear();
   (void)cudaGetLastError();
@@ -362,6 +363,9 @@ bool runFusedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, 
     std::memcpy(static_cast<char*>(e.host) + box_bytes, pl.segs.data(), seg_bytes);
     std::memcpy(static_cast<char*>(e.host) + box_bytes + seg_bytes, pl.phases.data(), pl.phases.size() * sizeof(PhaseDesc));
     CHECK_CUDA(cudaMemcpyAsync(e.dev, e.host, e.bytes, cudaMemcpyHostToDevice, stream));
+    CHECK_CUDA(cudaEventCreateWithFlags(&e.uploaded, cudaEventDisableTiming));
+    CHECK_CUDA(cudaEventRecord(e.uploaded, stream));
+    e.upload_stream = stream;
     std::memset(&e.params, 0, sizeof(e.params));
     e.params.boxes = static_cast<const KBox*>(e.dev);
     e.params.segs = reinterpret_cast<const SegDesc*>(static_cast<char*>(e.dev) + box_bytes);
@@ -375,6 +379,7 @@ bool runFusedStaged(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, 
     entry = &gd->fused_cache.back();
   }
   entry->last_use = ++tick;
+  if (stream != entry->upload_stream) CHECK_CUDA(cudaStreamWaitEvent(stream, entry->uploaded, 0));
   PhasedParams params = entry->params;
   params.sync = sync;
   LaunchConfig cfg;

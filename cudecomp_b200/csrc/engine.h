@@ -35,6 +35,8 @@ struct FusedPlanEntry {
   void* host = nullptr;    // pinned copy
   size_t bytes = 0;
   PhasedParams params{};   // sync block filled per call
+  cudaEvent_t uploaded = nullptr;      // recorded behind the upload: a call on ANOTHER stream waits for it
+  cudaStream_t upload_stream = nullptr;
   uint64_t total_slots = 0;
   uint64_t last_use = 0;
 };
