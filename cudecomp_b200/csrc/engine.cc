@@ -107,9 +107,10 @@ void checkDeviceError(cudecompGridDesc_t gd) {
   if (e == 0) return;
   // launches that gave up left without their bookkeeping: drain the device and zero this rank's counters
   cudaDeviceSynchronize();
-  if (gd->pad_slot >= 0)
-    cudaMemset(arena.mine(gd->pad_slot) + kPadCounter, 0, 8 * sizeof(uint64_t)),
-        cudaMemset(arena.mine(gd->pad_slot) + kPadPhaseCounter, 0, kMaxPhases * sizeof(uint64_t));
+  if (gd->pad_slot >= 0) {
+    cudaMemset(arena.mine(gd->pad_slot) + kPadCounter, 0, 8 * sizeof(uint64_t));
+    cudaMemset(arena.mine(gd->pad_slot) + kPadPhaseCounter, 0, kMaxPhases * sizeof(uint64_t));
+  }
   (void)cudaGetLastError();
   arena.clearError();
   if (e == 3) THROW_INTERNAL_ERROR("a TMA bulk copy of an earlier operation did not complete within 20 s");
