@@ -876,6 +876,30 @@ cudecompResult_t cudecompB200SelfTestMailbox(cudecompHandle_t handle, int32_t it
   }
   barrier(*handle->comm);
   box.destroy();
+
+  // The acknowledgement board behind deferred frees (peer.h AckBoard), host-only as well: every rank acknowledges a
+  // growing number of "releases" of every other rank; an owner must see the counts of all readers reach each stamp, and
+  // never a count it did not expect (cells of other (reader, owner) pairs must not be touched).
+  AckBoard board;
+  board.create(*handle->comm, handle->token ^ (0xacc0ull + static_cast<uint64_t>(handle->next_instance++)));
+  const int rounds = std::max(1, iterations / 100);
+  for (int it = 1; it <= rounds; ++it) {
+    for (int owner = 0; owner < n; ++owner)
+      if (owner != me) board.publish(owner, static_cast<uint64_t>(it) * 1000ull + static_cast<uint64_t>(owner));
+    barrier(*handle->comm);
+    for (int reader = 0; reader < n; ++reader) {
+      if (reader == me) {
+        if (board.seen(me, me) != 0) THROW_INTERNAL_ERROR("ack board self test: a rank acknowledged itself");
+        continue;
+      }
+      const uint64_t want = static_cast<uint64_t>(it) * 1000ull + static_cast<uint64_t>(me);
+      if (board.seen(reader, me) != want)
+        THROW_INTERNAL_ERROR("ack board self test: wrong count from rank " + std::to_string(reader) + " in round " +
+                             std::to_string(it));
+    }
+    barrier(*handle->comm);
+  }
+  board.destroy();
   API_CATCH()
 }
 

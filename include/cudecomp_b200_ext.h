@@ -130,7 +130,9 @@ cudecompResult_t cudecompB200GetAutotuneCandidates(const cudecompGridDescAutotun
 
 /* Host-only self test of the shared-memory descriptor mailbox (collective over the handle's communicator, no GPU
  * needed): `iterations` exchanges on alternating channels with rank groups of varying shape and randomised delays;
- * every received message is checked. Returns CUDECOMP_RESULT_SUCCESS or INTERNAL_ERROR. */
+ * every received message is checked; then the shared-memory acknowledgement board behind deferred frees (every rank
+ * acknowledges counts for every other rank, owners check what they see). Returns CUDECOMP_RESULT_SUCCESS or
+ * INTERNAL_ERROR. */
 cudecompResult_t cudecompB200SelfTestMailbox(cudecompHandle_t handle, int32_t iterations, uint32_t seed);
 
 #ifdef __cplusplus
