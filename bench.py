@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 GRID_BY_N = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
 OPS = ["XY", "YZ", "ZY", "YX"]
 NVLINK_PEAK_GBS = 770.0  # measured peer-copy rate per direction (B200_PROFILING.md), 900 nominal
+NVLINK_PACKET_FACTOR = 1.275068 / 1.073742  # bytes on the link per byte of payload for SM stores (ncu, profiles/)
 
 
 def parse_args():
@@ -549,6 +550,12 @@ def run_native(args, rank, world, local_rank):
                   "frac": (wire / t_wire / 1e9) / NVLINK_PEAK_GBS if t_wire > 0 else None,
                   "roofline_ms_per_step": wire / (NVLINK_PEAK_GBS * 1e9) * 1e3 +
                   sum(2.0 * S / (hbm_peak * 1e9) * 1e3 for op in OPS if comm[op] == 1)}
+        if t_wire > 0:
+            # ncu with NVLink counters (profiles/r2_rowcopy_peer_full.txt): SM stores leave the GPU as 128-byte packets
+            # carrying 24 bytes of protocol each, so the link itself moves 1.1875 x the payload
+            nvlink["raw_link_gbs_estimate"] = nvlink["achieved"] * NVLINK_PACKET_FACTOR
+            nvlink["raw_link_frac_of_900"] = nvlink["achieved"] * NVLINK_PACKET_FACTOR / 900.0
+            nvlink["packet_overhead_source"] = "profiles/r2_rowcopy_peer_full.txt (nvltx__bytes / nvltx__bytes_data_user)"
         if t_wire > 0:
             # With more than one rank in the communicator the dominant launches are bound by NVLink egress, not HBM:
             # algorithmic bytes per launch = the bytes that must leave this GPU, peak = measured peer-copy rate.
