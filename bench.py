@@ -535,7 +535,7 @@ def run_native(args, rank, world, local_rank):
     achieved = 2.0 * S / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": measured_traffic(world, args),
-                "kernel": "cdb::transposeKernel<uint4>" if args.axis_contiguous else "cdb::rowCopyKernel<uint4>",
+                "kernel": dominant_kernel(args, world, es),
                 "peak_source": peak_src,
                 "per_op_ms": dict(zip(OPS, op_ms)), "algorithmic_bytes_per_launch": 2.0 * S,
                 "slowest_op": OPS[slowest]}
@@ -596,6 +596,20 @@ def run_native(args, rank, world, local_rank):
     cd.MPI_Finalize()
     if world > 1:
         dist.destroy_process_group()
+
+
+def dominant_kernel(args, world, es):
+    """Name of the kernel most of the step's device time goes to (csrc/kernels.cu), as the engine selects it."""
+    t = {4: "unsigned int", 8: "uint2", 16: "uint4"}[es]
+    if args.axis_contiguous:
+        return "cdb::transposeKernel<%s>" % t if args.kernel_variant == 3 else "cdb::transposeVecKernel<%s>" % t
+    if args.bulk:
+        return "cdb::rowCopyBulkKernel"
+    wide = args.wide or (world > 1 and not args.no_wire_wide and args.kernel_variant == 0)
+    v = "cdb::Vec32" if wide else {4: "unsigned int", 8: "uint2", 16: "uint4"}[min(es, 16)]
+    if world > 1 and (args.inplace or args.staged) and args.staged_mode == 0:
+        return "cdb::rowCopyPhasedKernel<%s>" % v
+    return "cdb::rowCopyKernel<%s>" % (v if es == 16 or wide else "uint4")
 
 
 def measured_traffic(world, args):
