@@ -166,6 +166,10 @@ class Oracle:
     def set_threads(self, n):
         self.lib.oracle_set_threads(int(n))
 
+    def release(self):
+        """Frees the library's persistent staging regions (they are as large as the pencils that went through it)."""
+        self.lib.oracle_release()
+
 
 # ------------------------------------------------------------------------------------------------------------
 # Analytic known-answer pattern (numpy). dtype names follow cudecompDataType_t.
