@@ -4,7 +4,8 @@
 // Replaces reference include/internal/cudecomp_kernels.cuh:125-270 (the batched strided copy used for
 // pack and unpack), the cuTENSOR permute call in include/internal/transpose.h:80-157, and the exchange
 // backends of include/internal/comm_routines.h:260-425 (nearest prior art: the SM-driven NVSHMEM put
-// kernel, cudecomp_kernels.cuh:86-122).
+// kernel, cudecomp_kernels.cuh:86-122), and -- the phased launch -- the pipelined exchange that overlaps per-peer
+// pack / send / unpack on auxiliary streams (comm_routines.h:427-631, cudecompAlltoallPipelined).
 #ifndef CUDECOMP_B200_KERNELS_H
 #define CUDECOMP_B200_KERNELS_H
 
