@@ -3,6 +3,8 @@ and linked with libcudecomp.so, then run on one rank (geometry queries and argum
 import os
 import subprocess
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -56,3 +58,39 @@ def test_real_mpi_application_through_the_adapter(tmp_path):
         for r, p in enumerate(procs):
             out, _ = p.communicate(timeout=120)
             assert p.returncode == 0 and "real-MPI caller OK rank %d of %d" % (r, nranks) in out, out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_two_descriptors_one_destroyed_while_the_other_works(tmp_path, nranks):
+    """tests/c_caller/two_descriptors.cc: known-answer round trips on two live descriptors, out of place and in place;
+    one descriptor is destroyed (its peer mappings go with it) and the other carries on, also on a second stream."""
+    from tests._launcher import free_port
+    exe = str(tmp_path / "two_descriptors")
+    lib_dir = os.path.join(ROOT, "cudecomp_b200", "lib")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(ROOT, "include", "mpi_shim"), "-I" + os.path.join(cuda, "include"),
+           os.path.join(ROOT, "tests", "c_caller", "two_descriptors.cc"), "-L" + lib_dir, "-lcudecomp",
+           "-L" + os.path.join(cuda, "lib64"), "-lcudart_static", "-ldl", "-lpthread", "-lrt",
+           "-Wl,-rpath," + lib_dir, "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    port = free_port()
+    procs = []
+    for r in range(nranks):
+        env = dict(os.environ)
+        env.update(RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(nranks), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        env.setdefault("CUDECOMP_B200_DEVICE_TIMEOUT", "60")
+        env.setdefault("CUDECOMP_B200_HOST_TIMEOUT", "120")
+        procs.append(subprocess.Popen([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=300)[0])
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    for r, p in enumerate(procs):
+        assert p.returncode == 0 and "two descriptors OK rank %d of %d" % (r, nranks) in outs[r], "\n".join(outs)
