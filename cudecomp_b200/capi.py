@@ -140,7 +140,8 @@ API_SYMBOLS = [
 EXT_SYMBOLS = ["cudecompB200GetLaunchCount", "cudecompB200GetLastPath", "cudecompB200SetTuning",
                "cudecompB200CheckErrors", "cudecompB200SetPipelineChunks", "cudecompB200SetStagedMode", "cudecompB200SetKernelVariant", "cudecompB200DescribeTransposeBoxes", "cudecompB200DescribeHaloBoxes",
                "cudecompB200PlanTransposeBoxes", "cudecompB200PlanHaloBoxes", "cudecompB200PlanPipelinedTransposeBoxes",
-               "cudecompB200SelfTestMailbox", "cudecompB200GetAutotuneCandidates"]
+               "cudecompB200SelfTestMailbox", "cudecompB200GetAutotuneCandidates", "cudecompB200GetCumemState",
+               "cudecompB200ProbeFdPassing"]
 MPI_SHIM_SYMBOLS = ["MPI_Init", "MPI_Init_thread", "MPI_Initialized", "MPI_Finalize", "MPI_Finalized", "MPI_Abort",
                     "MPI_Wtime", "MPI_Get_processor_name", "MPI_Error_string", "MPI_Comm_rank", "MPI_Comm_size",
                     "MPI_Comm_split", "MPI_Comm_split_type", "MPI_Comm_dup", "MPI_Comm_free", "MPI_Comm_c2f",
@@ -190,6 +191,8 @@ for _n in ("cudecompUpdateHalosX", "cudecompUpdateHalosY", "cudecompUpdateHalosZ
          [cudecompHandle_t, cudecompGridDesc_t, _vp, _vp, ctypes.c_int, _i32p, _P(ctypes.c_bool), _i32, _i32p, _vp])
 _sig("cudecompB200GetLaunchCount", ctypes.c_int, [_P(ctypes.c_uint64)])
 _sig("cudecompB200GetLastPath", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32p])
+_sig("cudecompB200GetCumemState", ctypes.c_int, [cudecompHandle_t, _i32p])
+_sig("cudecompB200ProbeFdPassing", ctypes.c_int, [cudecompHandle_t, _i32p])
 _sig("cudecompB200SetTuning", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32, _i32])
 _sig("cudecompB200CheckErrors", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t])
 _sig("cudecompB200SetPipelineChunks", ctypes.c_int, [cudecompHandle_t, cudecompGridDesc_t, _i32])
@@ -434,6 +437,20 @@ def launch_count():
     n = ctypes.c_uint64(0)
     lib.cudecompB200GetLaunchCount(ctypes.byref(n))
     return n.value
+
+
+def cumem_state(handle):
+    """Outcome of CUDECOMP_ENABLE_CUMEM on this handle (cudecomp_b200_ext.h): 0 off, 1 on, 2 no fd passing, 3 no device support."""
+    p = _i32(0)
+    check(lib.cudecompB200GetCumemState(handle, ctypes.byref(p)), "cudecompB200GetCumemState")
+    return p.value
+
+
+def probe_fd_passing(handle):
+    """Collective, host only: 1 when every rank can duplicate a file descriptor of its neighbour (pidfd_getfd)."""
+    p = _i32(0)
+    check(lib.cudecompB200ProbeFdPassing(handle, ctypes.byref(p)), "cudecompB200ProbeFdPassing")
+    return p.value
 
 
 def last_path(handle, grid_desc):

@@ -20,6 +20,7 @@
 #include "nvtx_ranges.h"
 #include "errors.h"
 #include "mpi_shim.h"
+#include "vmm.h"
 
 using namespace cdb;
 
@@ -292,6 +293,30 @@ static void initHandle(cudecompHandle_t h, const CommPtr& parent) {
   if (const char* v = std::getenv("CUDECOMP_B200_DEVICE_TIMEOUT")) spin_s = std::atof(v);
   h->spin_timeout_ns = static_cast<uint64_t>(spin_s * 1e9);
   h->token = sharedToken(*h->comm);
+
+  // CUDECOMP_ENABLE_CUMEM (reference src/cudecomp.cc:596-660, docs/env_vars.rst): cudecompMalloc hands out cuMem (VMM)
+  // allocations with shareable handles. The reference leaves the sharing to NCCL / MPI; here the peers map the buffers
+  // themselves (vmm.h), so besides the device's VMM support the ranks must be able to pass file descriptors to each
+  // other. Both are checked once, collectively; a request that cannot be met is dropped with the reference's warning.
+  int64_t want[2] = {envFlag("CUDECOMP_ENABLE_CUMEM") ? 1 : 0, 0};
+  want[1] = -want[0];
+  allreduceI64(*h->comm, want, 2, ReduceOp::MIN); // {min, -max}: every rank must ask for it
+  if (want[0] != -want[1] && h->rank == 0)
+    std::printf("CUDECOMP:WARN: CUDECOMP_ENABLE_CUMEM is not set on every rank. Disabling this feature.\n");
+  if (want[0] == 1) {
+    bool fabric = false;
+    int64_t ok[2] = {(h->have_device && vmmDeviceSupported(&fabric)) ? 1 : 0, probeFdPassing(*h->comm, h->token) ? 1 : 0};
+    h->cumem_fabric = fabric && envFlag("CUDECOMP_B200_CUMEM_FABRIC");
+    if (h->cumem_fabric) ok[1] = 1; // fabric handles travel in the descriptor itself: no file descriptor needed
+    allreduceI64(*h->comm, ok, 2, ReduceOp::MIN);
+    h->cumem_state = !ok[0] ? kCumemNoDevice : (!ok[1] ? kCumemNoFdPassing : kCumemOn);
+    if (h->rank == 0 && h->cumem_state == kCumemNoDevice)
+      std::printf("CUDECOMP:WARN: CUDECOMP_ENABLE_CUMEM is set but the current device does not support CUDA VMM "
+                  "allocations with POSIX file-descriptor handles. Disabling this feature.\n");
+    if (h->rank == 0 && h->cumem_state == kCumemNoFdPassing)
+      std::printf("CUDECOMP:WARN: CUDECOMP_ENABLE_CUMEM is set but the ranks cannot pass file descriptors to each other "
+                  "(pidfd_getfd). Disabling this feature.\n");
+  }
   h->initialized = true;
 }
 
@@ -619,7 +644,12 @@ cudecompResult_t cudecompMalloc(cudecompHandle_t handle, cudecompGridDesc_t grid
   const size_t kPage = size_t(2) << 20;
   const size_t rounded = (buffer_size_bytes + kPage - 1) / kPage * kPage;
   void* p = nullptr;
-  CHECK_CUDA(cudaMalloc(&p, rounded));
+  if (handle->cumem_state == kCumemOn) {
+    // CUDECOMP_ENABLE_CUMEM: cuMemCreate (POSIX fd [+ fabric] handles, RDMA flag) + map, reference src/cudecomp.cc:1500-1570
+    p = vmmAlloc(rounded, handle->cumem_fabric);
+  } else {
+    CHECK_CUDA(cudaMalloc(&p, rounded));
+  }
   grid_desc->allocations.insert(p);
   *buffer = p;
   API_CATCH()
@@ -643,7 +673,7 @@ cudecompResult_t cudecompFree(cudecompHandle_t handle, cudecompGridDesc_t grid_d
     std::vector<int> shown;
     if (d.exportable && d.offset == 0) shown = takeDescribedTo(buffer);
     if (shown.empty()) {
-      CHECK_CUDA(cudaFree(buffer));
+      if (!vmmFree(buffer)) CHECK_CUDA(cudaFree(buffer));
     } else {
       for (int k = kReleaseSlots - 1; k > 0; --k) handle->released[k] = handle->released[k - 1];
       handle->released[0] = d.buffer_id;
@@ -710,6 +740,22 @@ cudecompResult_t cudecompB200GetLaunchCount(uint64_t* count) {
   if (!count) return CUDECOMP_RESULT_INVALID_USAGE;
   *count = launchCount();
   return CUDECOMP_RESULT_SUCCESS;
+}
+
+cudecompResult_t cudecompB200GetCumemState(cudecompHandle_t handle, int32_t* state) {
+  API_TRY
+  checkHandle(handle);
+  if (!state) THROW_INVALID_USAGE("state argument cannot be null");
+  *state = handle->cumem_state;
+  API_CATCH()
+}
+
+cudecompResult_t cudecompB200ProbeFdPassing(cudecompHandle_t handle, int32_t* ok) {
+  API_TRY
+  checkHandle(handle);
+  if (!ok) THROW_INVALID_USAGE("ok argument cannot be null");
+  *ok = probeFdPassing(*handle->comm, handle->token ^ 0xfd9a55ull) ? 1 : 0;
+  API_CATCH()
 }
 
 cudecompResult_t cudecompB200GetLastPath(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t* path) {

@@ -7,6 +7,7 @@
 #include "errors.h"
 #include "launch_params.h"
 #include "nvtx_ranges.h"
+#include "vmm.h"
 
 namespace cdb {
 
@@ -53,7 +54,7 @@ void reapReleased(cudecompHandle_t h, bool everything) {
       for (int r : list[i].waiting_for)
         if (h->acks.seen(r, h->rank) < list[i].stamp) ready = false;
     if (ready) {
-      cudaFree(list[i].ptr);
+      if (!vmmFree(list[i].ptr)) cudaFree(list[i].ptr);
       list.erase(list.begin() + i);
     } else {
       ++i;

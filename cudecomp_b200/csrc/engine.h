@@ -73,6 +73,8 @@ struct cudecompHandle {
   int wire_wide = 1;             // CUDECOMP_B200_WIRE_WIDE=0: 128-bit accesses on the wire too
   int column_chunks = 1;         // CUDECOMP_B200_COLUMN_CHUNKS=0: plane chunks only
   int transpose_geometry = 0;    // CUDECOMP_B200_TRANSPOSE_GEOM=1: 64 x 32 tiles for 8-byte vectorised transposes
+  int cumem_state = 0;           // CUDECOMP_ENABLE_CUMEM outcome (vmm.h kCumem*): 1 = cudecompMalloc uses cuMem allocations
+  bool cumem_fabric = false;     // ... created with fabric handles as well where the platform has them
   cdb::AckBoard acks;            // which of my release announcements every rank has processed
   struct Released {              // freed by the caller, still mapped by peers: the real cudaFree waits for their acks
     void* ptr;

@@ -17,6 +17,7 @@
 
 #include "errors.h"
 #include "kernels.h"
+#include "vmm.h"
 
 namespace cdb {
 
@@ -56,6 +57,7 @@ struct ExportEntry {
   uint64_t buffer_id;
   uint64_t size;
   cudaIpcMemHandle_t handle;
+  uint32_t kind; // BufDesc::kind
   bool exportable;
   std::vector<int> described_to; // world ranks that have been shown this allocation in a CallMsg
 };
@@ -75,6 +77,33 @@ void describeBuffer(const void* ptr, BufDesc* d) {
     return v && *v && std::strcmp(v, "0") != 0;
   }();
   if (disabled) return;
+  static const bool fabric = [] {
+    const char* v = std::getenv("CUDECOMP_B200_CUMEM_FABRIC");
+    return v && *v && std::strcmp(v, "0") != 0;
+  }();
+  uint64_t vbase = 0, vsize = 0, vid = 0;
+  if (vmmFind(ptr, &vbase, &vsize, &vid)) {
+    // cudecompMalloc'ed with cuMem (CUDECOMP_ENABLE_CUMEM): peers map it through its shareable handle
+    auto it = g_exports.find(vbase);
+    if (it == g_exports.end() || it->second.buffer_id != vid) {
+      ExportEntry e{};
+      e.buffer_id = vid;
+      e.size = vsize;
+      static_assert(sizeof(e.handle) == 64, "the descriptor's handle bytes hold a CUDA IPC handle, {pid, fd} or a fabric handle");
+      e.kind = vmmExport(vbase, fabric, reinterpret_cast<unsigned char*>(&e.handle));
+      e.exportable = e.kind != kShareIpc;
+      g_exports[vbase] = e;
+      it = g_exports.find(vbase);
+    }
+    const ExportEntry& e = it->second;
+    d->handle = e.handle;
+    d->offset = reinterpret_cast<uint64_t>(ptr) - vbase;
+    d->alloc_size = e.size;
+    d->buffer_id = e.buffer_id;
+    d->exportable = e.exportable ? 1u : 0u;
+    d->kind = e.kind;
+    return;
+  }
   const DriverApi& api = driverApi();
   if (!api.ok) return;
 
@@ -112,6 +141,7 @@ void describeBuffer(const void* ptr, BufDesc* d) {
   d->alloc_size = e.size;
   d->buffer_id = e.buffer_id;
   d->exportable = e.exportable ? 1u : 0u;
+  d->kind = kShareIpc;
 }
 
 void noteDescribed(const BufDesc& d, const void* ptr, const std::vector<int>& group_world, int me) {
@@ -208,23 +238,34 @@ void* PeerCache::resolve(int owner, const BufDesc& d) {
   if (it == map_.end()) {
     evictIfNeeded();
     void* base = nullptr;
-    cudaError_t err = cudaIpcOpenMemHandle(&base, d.handle, cudaIpcMemLazyEnablePeerAccess);
-    if (err != cudaSuccess) {
-      (void)cudaGetLastError();
-      THROW_CUDA_ERROR(std::string("cudaIpcOpenMemHandle failed for a buffer of rank ") + std::to_string(owner) +
-                       ": " + cudaGetErrorString(err) +
-                       " (peer-to-peer access between the ranks' GPUs is required)");
+    if (d.kind != kShareIpc) {
+      base = vmmImport(d.kind, reinterpret_cast<const unsigned char*>(&d.handle), d.alloc_size);
+    } else {
+      cudaError_t err = cudaIpcOpenMemHandle(&base, d.handle, cudaIpcMemLazyEnablePeerAccess);
+      if (err != cudaSuccess) {
+        (void)cudaGetLastError();
+        THROW_CUDA_ERROR(std::string("cudaIpcOpenMemHandle failed for a buffer of rank ") + std::to_string(owner) +
+                         ": " + cudaGetErrorString(err) +
+                         " (peer-to-peer access between the ranks' GPUs is required)");
+      }
     }
-    it = map_.emplace(k, Entry{base, 0}).first;
+    it = map_.emplace(k, Entry{base, 0, d.kind, d.alloc_size}).first;
   }
   it->second.last_use = ++tick_;
   return static_cast<char*>(it->second.base) + d.offset;
 }
 
+void PeerCache::closeImport(const Entry& e) {
+  if (e.kind != kShareIpc)
+    vmmUnimport(e.base, e.size);
+  else
+    cudaIpcCloseMemHandle(e.base);
+}
+
 void PeerCache::forgetBuffer(int owner, uint64_t buffer_id) {
   for (auto it = map_.begin(); it != map_.end();) {
     if (it->first.owner == owner && it->first.buffer_id == buffer_id) {
-      cudaIpcCloseMemHandle(it->second.base);
+      closeImport(it->second);
       it = map_.erase(it);
     } else {
       ++it;
@@ -236,7 +277,7 @@ void PeerCache::forgetBuffer(int owner, uint64_t buffer_id) {
 void PeerCache::forgetOwner(int owner) {
   for (auto it = map_.begin(); it != map_.end();) {
     if (it->first.owner == owner) {
-      cudaIpcCloseMemHandle(it->second.base);
+      closeImport(it->second);
       it = map_.erase(it);
     } else {
       ++it;
@@ -270,7 +311,7 @@ void PeerCache::evictIfNeeded() {
     auto victim = map_.begin();
     for (auto it = map_.begin(); it != map_.end(); ++it)
       if (it->second.last_use < victim->second.last_use) victim = it;
-    cudaIpcCloseMemHandle(victim->second.base);
+    closeImport(victim->second);
     map_.erase(victim);
   }
   (void)cudaGetLastError();
@@ -279,7 +320,7 @@ void PeerCache::evictIfNeeded() {
 void PeerCache::clear() {
   if (map_.empty()) return;
   cudaDeviceSynchronize();
-  for (auto& kv : map_) cudaIpcCloseMemHandle(kv.second.base);
+  for (auto& kv : map_) closeImport(kv.second);
   (void)cudaGetLastError();
   map_.clear();
 }

@@ -27,12 +27,12 @@ namespace cdb {
 
 // What a rank tells its peers about one buffer argument of the current call.
 struct BufDesc {
-  cudaIpcMemHandle_t handle; // of the allocation containing the pointer
+  cudaIpcMemHandle_t handle; // of the allocation containing the pointer (kind 0); {pid, fd} or the fabric handle (vmm.h)
   uint64_t offset;           // pointer - allocation base
   uint64_t alloc_size;
   uint64_t buffer_id;        // CU_POINTER_ATTRIBUTE_BUFFER_ID: unique per allocation, guards handle reuse
   uint32_t exportable;       // 0: cannot be mapped by peers (managed, host, pool memory, ...)
-  uint32_t pad_;
+  uint32_t kind;             // how peers map it: 0 CUDA IPC, 1 cuMem POSIX fd, 2 cuMem fabric handle (vmm.h)
 };
 
 constexpr int kReleaseSlots = 6;
@@ -107,7 +107,10 @@ private:
   struct Entry {
     void* base;
     uint64_t last_use;
+    uint32_t kind; // BufDesc::kind: decides how the mapping is closed
+    uint64_t size;
   };
+  static void closeImport(const Entry& e);
   std::map<Key, Entry> map_;
   std::map<int, uint64_t> releases_seen_; // per owner
   uint64_t tick_ = 0;

@@ -39,6 +39,17 @@ cudecompResult_t cudecompB200GetLaunchCount(uint64_t* count);
 /* Path of the last transpose/halo call on the descriptor: 0 none, 1 local, 2 direct peer stores, 3 staged. */
 cudecompResult_t cudecompB200GetLastPath(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t* path);
 
+/* Outcome of CUDECOMP_ENABLE_CUMEM (reference docs/env_vars.rst; src/cudecomp.cc:596-660) on this handle: 0 not
+ * requested, 1 on (cudecompMalloc hands out cuMemCreate / cuMemMap allocations with POSIX-fd [+ fabric] handles and
+ * peers map them through those handles instead of CUDA IPC), 2 requested but the ranks cannot pass file descriptors to
+ * each other (pidfd_getfd), 3 requested but the device / driver lacks VMM support with POSIX-fd handles. In states 2
+ * and 3 the library has printed the reference's "Disabling this feature" warning and allocates with cudaMalloc. */
+cudecompResult_t cudecompB200GetCumemState(cudecompHandle_t handle, int32_t* state);
+
+/* Host-only, collective over the handle's communicator: can every rank duplicate a file descriptor of its neighbour
+ * (pidfd_getfd)? This is how POSIX-fd handles of cuMem allocations reach the importing rank. ok = 1 / 0 on every rank. */
+cudecompResult_t cudecompB200ProbeFdPassing(cudecompHandle_t handle, int32_t* ok);
+
 /* grid_ctas: CTAs per launch (0 = all resident CTAs); force_staged != 0 routes every exchange through the workspace. */
 cudecompResult_t cudecompB200SetTuning(cudecompHandle_t handle, cudecompGridDesc_t grid_desc, int32_t grid_ctas,
                                        int32_t force_staged);

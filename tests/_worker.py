@@ -575,6 +575,10 @@ def mailbox_selftest(handle, case):
     return dict(ok=cd.lib.cudecompB200SelfTestMailbox(handle, case.get("iterations", 2000), case.get("seed", 1)) == 0)
 
 
+def cumem_probe(handle):
+    return dict(ok=True, state=cd.cumem_state(handle), fd_passing=cd.probe_fd_passing(handle))
+
+
 def main():
     payload_path, out_dir = sys.argv[1], sys.argv[2]
     with open(payload_path) as f:
@@ -595,6 +599,8 @@ def main():
                 results.append(shim_battery(rank, int(os.environ["WORLD_SIZE"])))
             elif payload["mode"] == "mailbox":
                 results.append(mailbox_selftest(handle, case))
+            elif payload["mode"] == "cumem":
+                results.append(cumem_probe(handle))
             elif payload["mode"] == "plan":
                 results.append(plan_case(handle, rank, case))
             elif payload["mode"] in ("api", "api_gpu"):

@@ -4,6 +4,8 @@
 // schedule); then descriptor A and its buffers go away and descriptor B runs the same round trips again -- its mappings
 // of the peers' buffers were dropped with A and must be re-created on demand -- the in-place one on a second stream, so
 // that the cached schedule tables are used from a stream other than the one that uploaded them.
+// With CUDECOMP_ENABLE_CUMEM=1 in the environment all of this runs on cuMem (VMM) allocations that the peers map through
+// POSIX file descriptors instead of CUDA IPC handles (csrc/vmm.h).
 // Built and run by tests/test_c_caller.py (g++ against include/ and cudecomp_b200/lib, plus the CUDA runtime).
 // Run on 2 (or 4) ranks with RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT set; ranks share GPUs when there are fewer.
 #include <cstdint>
@@ -13,6 +15,7 @@
 
 #include <cuda_runtime.h>
 #include <cudecomp.h>
+#include <cudecomp_b200_ext.h>
 
 #define CHECK(call)                                                                                                    \
   do {                                                                                                                 \
@@ -126,6 +129,8 @@ int main() {
 
   cudecompHandle_t h;
   CHECK(cudecompInit(&h, MPI_COMM_WORLD));
+  int32_t cumem = -1; // CUDECOMP_ENABLE_CUMEM=1: cudecompMalloc hands out cuMem allocations, mapped by the peers through fds
+  CHECK(cudecompB200GetCumemState(h, &cumem));
   Desc A, B;
   make(h, size, 1, &A);     // X<->Y on the wire
   make(h, size / 2, 2, &B); // 2 ranks: Y<->Z on the wire; 4 ranks: both
@@ -157,6 +162,6 @@ int main() {
   CHECK(cudecompFinalize(h));
   MPI_Finalize();
   if (!ok) return 1;
-  std::printf("two descriptors OK rank %d of %d\n", rank, size);
+  std::printf("two descriptors OK rank %d of %d, cumem state %d\n", rank, size, static_cast<int>(cumem));
   return 0;
 }

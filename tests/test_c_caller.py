@@ -61,10 +61,13 @@ def test_real_mpi_application_through_the_adapter(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("cumem", [0, 1], ids=["cuda_ipc", "cumem_posix_fd"])
 @pytest.mark.parametrize("nranks", [2, 4])
-def test_two_descriptors_one_destroyed_while_the_other_works(tmp_path, nranks):
+def test_two_descriptors_one_destroyed_while_the_other_works(tmp_path, nranks, cumem):
     """tests/c_caller/two_descriptors.cc: known-answer round trips on two live descriptors, out of place and in place;
-    one descriptor is destroyed (its peer mappings go with it) and the other carries on, also on a second stream."""
+    one descriptor is destroyed (its peer mappings go with it) and the other carries on, also on a second stream.
+    Once on cudaMalloc + CUDA IPC (the default), once with CUDECOMP_ENABLE_CUMEM=1 (reference docs/env_vars.rst): the
+    buffers are cuMem allocations and the peers map them through POSIX file descriptors."""
     from tests._launcher import free_port
     exe = str(tmp_path / "two_descriptors")
     lib_dir = os.path.join(ROOT, "cudecomp_b200", "lib")
@@ -81,6 +84,9 @@ def test_two_descriptors_one_destroyed_while_the_other_works(tmp_path, nranks):
     for r in range(nranks):
         env = dict(os.environ)
         env.update(RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(nranks), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        env.pop("CUDECOMP_ENABLE_CUMEM", None)
+        if cumem:
+            env["CUDECOMP_ENABLE_CUMEM"] = "1"
         env.setdefault("CUDECOMP_B200_DEVICE_TIMEOUT", "60")
         env.setdefault("CUDECOMP_B200_HOST_TIMEOUT", "120")
         procs.append(subprocess.Popen([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
@@ -93,4 +99,5 @@ def test_two_descriptors_one_destroyed_while_the_other_works(tmp_path, nranks):
             if p.poll() is None:
                 p.kill()
     for r, p in enumerate(procs):
-        assert p.returncode == 0 and "two descriptors OK rank %d of %d" % (r, nranks) in outs[r], "\n".join(outs)
+        assert p.returncode == 0 and "two descriptors OK rank %d of %d, cumem state %d" % (r, nranks, cumem) in outs[r], \
+            "\n".join(outs)

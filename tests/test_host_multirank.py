@@ -220,6 +220,51 @@ def test_descriptor_mailbox_stress(nranks):
         assert all(c["ok"] for c in results[r]), results[r]
 
 
+@pytest.mark.parametrize("nranks", [1, 2, 5])
+def test_cumem_request_is_settled_collectively_at_init(nranks):
+    """CUDECOMP_ENABLE_CUMEM (reference docs/env_vars.rst, src/cudecomp.cc:596-660): without the variable the feature is
+    off; with it the ranks check together (a) that file descriptors -- the POSIX-fd handles of cuMem allocations -- can
+    be passed between them and (b) that the device supports VMM allocations. On this GPU-less host (b) fails on every
+    rank alike, the reference's warning is printed once, and allocation stays on cudaMalloc; (a) must work among the
+    processes of one host."""
+    results, logs = run_ranks(nranks, "cumem", [dict(name="probe")], timeout=120)
+    for r in range(nranks):
+        assert results[r][0] == dict(ok=True, state=0, fd_passing=1), results[r]
+    assert "CUDECOMP:WARN" not in logs[0]
+    results, logs = run_ranks(nranks, "cumem", [dict(name="probe")], timeout=120,
+                              extra_env=dict(CUDECOMP_ENABLE_CUMEM="1"))
+    for r in range(nranks):
+        assert results[r][0] == dict(ok=True, state=3, fd_passing=1), results[r]
+    assert "CUDECOMP:WARN: CUDECOMP_ENABLE_CUMEM is set but the current device does not support CUDA VMM" in logs[0]
+    assert all("CUDECOMP:WARN" not in logs[r] for r in range(1, nranks))
+
+
+def test_cumem_request_on_a_subset_of_the_ranks_is_dropped(tmp_path):
+    """The variable set on rank 0 only: every rank must still take the same path (off), with a warning."""
+    import os
+    import subprocess
+    import sys
+    from tests._launcher import free_port, ROOT
+    port = free_port()
+    procs = []
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from cudecomp_b200 import capi as cd\n"
+            "assert cd.MPI_Init() == 0\n"
+            "res, h = cd.cudecompInit(cd.MPI_COMM_WORLD); cd.check(res)\n"
+            "print('state', cd.cumem_state(h)); cd.check(cd.cudecompFinalize(h)); cd.MPI_Finalize()\n") % ROOT
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        env.pop("CUDECOMP_ENABLE_CUMEM", None)
+        if r == 0:
+            env["CUDECOMP_ENABLE_CUMEM"] = "1"
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("state 0" in o for o in outs), outs
+    assert "CUDECOMP_ENABLE_CUMEM is not set on every rank" in outs[0]
+
+
 def test_sixteen_ranks_plans_and_mailbox():
     """Communicators of 16 ranks (one launch carries at most 16 boxes, kernels.h kMaxBoxes): 4x4 and both slab grids,
     planned by 16 real processes, executed with numpy and compared with the oracle; then the mailbox with 16 members."""
