@@ -4,7 +4,8 @@
 // Replaces the reference's transport setup (NCCL communicators src/cudecomp.cc:59-72,1152-1182; NVSHMEM
 // symmetric heap :1470-1496; cuMem fabric handles :1508-1602).  Design:
 //   * every buffer a peer must write (workspace, and the user's output / halo buffer when it is plain
-//     device memory) is exported lazily with CUDA IPC and imported once per peer (PeerCache);
+//     device memory) is exported lazily with CUDA IPC and imported once per peer (PeerCache); cudecompMalloc'ed
+//     buffers of the CUDECOMP_ENABLE_CUMEM path travel as POSIX file descriptors or fabric handles instead (vmm.h);
 //   * per collective call the members of the row/column communicator swap one small descriptor through a
 //     shared-memory mailbox (Mailbox) -- which buffer + offset each rank is using in THIS call and
 //     whether it could be exported -- so all members take the same direct/staged decision without a
