@@ -67,3 +67,29 @@ def test_runbooks_only_use_flags_bench_py_knows():
             assert parsed.n in (512, 640, 1024)
     finally:
         sys.argv = old_argv
+
+
+def test_reference_sweep_on_the_cpu_runs_the_committed_case_lists():
+    """scripts/ref_sweep_cpu.py: the reference's own command lines (tests/golden/ref_cases, what the GPU suite feeds to the
+    reference's executables) parsed the way those executables parse them, planned by the library, walked by the launch
+    emulator and compared with the oracle -- here the first two lines of every configuration; the whole 8 268-line sweep
+    is recorded in profiles/r2_cpu_reference_sweep.txt."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_sweep_cpu", os.path.join(ROOT, "scripts", "ref_sweep_cpu.py"))
+    sweep = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sweep)
+    d = sweep.parse_transpose("--pr 1 --pc 4 --backend 1 --gx 128 --gy 124 --gz 132 --gd 0 0 2 --hex 0 0 0 --hey 1 1 1 "
+                              "--hez 0 0 0 --pdx 0 0 0 --pdy 1 0 1 --pdz 0 0 0 --mem_order 0 1 2 1 2 0 2 0 1 -m -o")
+    assert d["gdims"] == [128, 124, 132] and d["pdims"] == [1, 4] and d["gdims_dist"] == [128, 124, 130]
+    assert d["halos"]["1"] == [1, 1, 1] and d["pads"]["1"] == [1, 0, 1] and d["mem_order"][1] == [1, 2, 0] and d["out_of_place"]
+    d, ax, halo, periods, padding = sweep.parse_halo("--pr 2 --pc 2 --backend 1 --gx 64 --gy 66 --gz 62 --gd 0 0 0 --hex 1 --hey 0 "
+                                                     "--hez 2 --hpx 1 --hpy 0 --hpz 1 --pdx 1 --pdy 2 --pdz 3 --ax 2 --ac 1 "
+                                                     "--mem_order 2 0 1")
+    # halo_test's option table routes --pdz to padding[1] (tests/cc/halo_test.cc:274-276)
+    assert (ax, halo, periods, padding) == (2, [1, 0, 2], [True, False, True], [1, 3, 0])
+    assert d["axis_contiguous"] == [True] * 3 and d["mem_order"] == [[2, 0, 1]] * 3
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ref_sweep_cpu.py"),
+                          os.path.join(ROOT, "tests", "golden", "ref_cases"), "--jobs", "4", "--limit", "2"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "TOTAL 28 lines, 28 passed, 0 failed" in out.stdout
