@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 
 #include "errors.h"
@@ -460,12 +461,22 @@ void runTranspose(cudecompHandle_t h, cudecompGridDesc_t gd, int ax, int dir, vo
                 gd->config.transpose_comm_backend < CUDECOMP_TRANSPOSE_COMM_NVSHMEM; // NVSHMEM* values = staged schedule
   bool work_ok = true;
   bool src_ok = gd->pull_mode != 0; // receiver-driven: every member's INPUT must be mappable
+  bool anybody_inplace = false, unmappable = false;
   for (auto& m : msgs) {
-    if (m.flags & 1u) direct = false; // anybody in place: peers may not overwrite a buffer that is still being read
-    if (!m.data.exportable) direct = false;
+    if (m.flags & 1u) anybody_inplace = true; // peers may not overwrite a buffer that is still being read
+    if (!m.data.exportable) unmappable = true;
     if (!m.work.exportable) work_ok = false;
     if (!m.src.exportable) src_ok = false;
   }
+  if (direct && !anybody_inplace && unmappable && !gd->warned_unmappable) {
+    // The call would have taken the one-kernel path: say once why it does not (the reference warns on rank 0 too).
+    gd->warned_unmappable = true;
+    if (h->rank == 0)
+      std::printf("CUDECOMP:WARN: an output buffer of this transpose cannot be mapped by the peer GPUs (managed or pool memory, "
+                  "or an allocation below 2 MiB): the exchange is staged through the workspace. Pencils from cudecompMalloc "
+                  "or plain cudaMalloc (>= 2 MiB) take the direct path.\n");
+  }
+  if (anybody_inplace || unmappable) direct = false;
   // Receiver-driven staged schedule: every rank loads its blocks from the peers' inputs into its OWN workspace and
   // unpacks locally, so nothing is written into a peer's memory (the workspace need not be mappable). In place this is
   // safe for the same reason the sender-driven staged schedule is: a pencil is only overwritten by its owner's unpack,

@@ -102,6 +102,7 @@ struct cudecompGridDesc {
   int grid_ctas = 0;       // 0: all resident CTAs
   bool force_staged = false;
   int last_path = CUDECOMP_B200_PATH_NONE;
+  bool warned_unmappable = false; // the "output cannot be mapped by the peers" warning is printed once per descriptor
   std::unique_ptr<cdb::PerfReport> perf; // only when the performance report is enabled
   // chunked (pipelined) staged schedule: unpack kernels run on a side stream beside the next chunk's push
   int pipeline_chunks = 0;
