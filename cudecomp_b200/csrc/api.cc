@@ -298,7 +298,9 @@ static void initHandle(cudecompHandle_t h, const CommPtr& parent) {
   // allocations with shareable handles. The reference leaves the sharing to NCCL / MPI; here the peers map the buffers
   // themselves (vmm.h), so besides the device's VMM support the ranks must be able to pass file descriptors to each
   // other. Both are checked once, collectively; a request that cannot be met is dropped with the reference's warning.
-  int64_t want[2] = {envFlag("CUDECOMP_ENABLE_CUMEM") ? 1 : 0, 0};
+  // (CUDECOMP_ENABLE_NCCL_UBR requests the same allocation path in the reference, src/cudecomp.cc:603; there is no NCCL
+  // communicator to register the buffers with here, so that is all it does.)
+  int64_t want[2] = {(envFlag("CUDECOMP_ENABLE_CUMEM") || envFlag("CUDECOMP_ENABLE_NCCL_UBR")) ? 1 : 0, 0};
   want[1] = -want[0];
   allreduceI64(*h->comm, want, 2, ReduceOp::MIN); // {min, -max}: every rank must ask for it
   if (want[0] != -want[1] && h->rank == 0)

@@ -237,6 +237,9 @@ def test_cumem_request_is_settled_collectively_at_init(nranks):
         assert results[r][0] == dict(ok=True, state=3, fd_passing=1), results[r]
     assert "CUDECOMP:WARN: CUDECOMP_ENABLE_CUMEM is set but the current device does not support CUDA VMM" in logs[0]
     assert all("CUDECOMP:WARN" not in logs[r] for r in range(1, nranks))
+    # CUDECOMP_ENABLE_NCCL_UBR asks for the same allocation path (reference src/cudecomp.cc:603)
+    results, _ = run_ranks(nranks, "cumem", [dict(name="probe")], timeout=120, extra_env=dict(CUDECOMP_ENABLE_NCCL_UBR="1"))
+    assert all(results[r][0]["state"] == 3 for r in range(nranks))
 
 
 def test_cumem_request_on_a_subset_of_the_ranks_is_dropped(tmp_path):
