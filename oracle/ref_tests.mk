@@ -1,5 +1,5 @@
 # Builds the REFERENCE's own test executables -- the legacy ones (tests/cc/transpose_test.cc, tests/cc/halo_test.cc), its
-# FFT benchmark and two of its current GoogleTest suites (tests/ctest/halo_tests.cc, api_tests.cc) --, unmodified,
+# FFT benchmark, its example programs and two of its current GoogleTest suites (tests/ctest/halo_tests.cc, api_tests.cc) --, unmodified,
 # from the sources where they lie under /root/reference, against THIS repo's cudecomp.h, MPI shim and libcudecomp.so.
 # The binaries contain the reference's own known-answer generator and comparator (transpose_test.cc:103-155), so a
 # pass is the reference's verdict on this library. Outputs go to oracle/_ref/ only (git-ignored; travels to the GPU box).
@@ -34,7 +34,21 @@ CTEST_FLAGS := -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -x cu -Xco
                -Xlinker -rpath -Xlinker '$$ORIGIN/../../cudecomp_b200/lib'
 CTESTS := $(OUT)/ctest_halo_tests $(OUT)/ctest_api_tests
 
-all: $(BINS) $(BENCH) $(CTESTS)
+# the reference's example programs (examples/cc: basic usage with and without autotuning, the Taylor-Green solver),
+# unmodified: compile-and-link proof of the boundary for real applications (tests/test_ref_examples_link.py)
+EXAMPLES := $(OUT)/example_basic_usage $(OUT)/example_basic_usage_autotune $(OUT)/example_tg
+
+all: $(BINS) $(BENCH) $(CTESTS) $(EXAMPLES)
+
+$(OUT)/example_basic_usage: $(REF)/examples/cc/basic_usage/basic_usage.cu $(ROOT)/cudecomp_b200/lib/libcudecomp.so
+	@mkdir -p $(OUT)
+	$(NVCC) $(FLAGS) $< -o $@
+$(OUT)/example_basic_usage_autotune: $(REF)/examples/cc/basic_usage/basic_usage_autotune.cu $(ROOT)/cudecomp_b200/lib/libcudecomp.so
+	@mkdir -p $(OUT)
+	$(NVCC) $(FLAGS) $< -o $@
+$(OUT)/example_tg: $(REF)/examples/cc/taylor_green/tg.cu $(ROOT)/cudecomp_b200/lib/libcudecomp.so
+	@mkdir -p $(OUT)
+	$(NVCC) $(FLAGS) $< -lcufft -o $@
 
 $(OUT)/gen/backend_config.h:
 	@mkdir -p $(OUT)/gen
