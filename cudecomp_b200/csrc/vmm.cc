@@ -147,7 +147,9 @@ int duplicateFdOf(int pid, int fd) {
   const int pidfd = static_cast<int>(syscall(SYS_pidfd_open, pid, 0));
   if (pidfd < 0) return -1;
   const int got = static_cast<int>(syscall(SYS_pidfd_getfd, pidfd, fd, 0));
+  const int saved = errno; // what the caller reports; close() below may overwrite it
   close(pidfd);
+  errno = saved;
   return got;
 }
 
@@ -163,6 +165,12 @@ bool probeFdPassing(Comm& comm, uint64_t token) {
     close(mine.fd);
     mine.fd = -1;
   }
+  struct CloseOnExit { // the offer is closed on every way out, exceptions of the collectives included
+    int fd;
+    ~CloseOnExit() {
+      if (fd >= 0) close(fd);
+    }
+  } offer{mine.fd};
   std::vector<Offer> all(comm.size());
   allgather(comm, &mine, sizeof(mine), all.data());
   int64_t ok = mine.fd >= 0 ? 1 : 0;
@@ -175,7 +183,6 @@ bool probeFdPassing(Comm& comm, uint64_t token) {
     if (fd >= 0) close(fd);
   }
   allreduceI64(comm, &ok, 1, ReduceOp::MIN); // also: nobody closes its offer before everybody has read
-  if (mine.fd >= 0) close(mine.fd);
   return ok != 0;
 }
 
