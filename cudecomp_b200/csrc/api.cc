@@ -162,6 +162,21 @@ void checkRankOrder(int r) {
   if (r < CUDECOMP_RANK_ORDER_DEFAULT || r > CUDECOMP_RANK_ORDER_COL_MAJOR) THROW_INVALID_USAGE("unknown rank order");
 }
 
+// transpose_mem_order: all unset (negative) or three permutations of {0, 1, 2} (reference src/cudecomp.cc:460-480)
+void checkMemOrder(const cudecompGridDescConfig_t* c) {
+  const bool set = c->transpose_mem_order[0][0] >= 0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      if ((c->transpose_mem_order[i][j] >= 0) != set) THROW_INVALID_USAGE("transpose_mem_order only partially set");
+  if (set) {
+    for (int i = 0; i < 3; ++i) {
+      std::set<int32_t> vals(c->transpose_mem_order[i], c->transpose_mem_order[i] + 3);
+      if (vals.size() != 3 || *vals.begin() != 0 || *vals.rbegin() != 2)
+        THROW_INVALID_USAGE("transpose_mem_order setting is invalid");
+    }
+  }
+}
+
 void checkConfig(cudecompHandle_t h, const cudecompGridDescConfig_t* c, bool autotune_transpose, bool autotune_halo) {
   if (!autotune_transpose) checkTransposeBackend(enumBits(c->transpose_comm_backend));
   if (!autotune_halo) checkHaloBackend(enumBits(c->halo_comm_backend));
@@ -176,17 +191,7 @@ void checkConfig(cudecompHandle_t h, const cudecompGridDescConfig_t* c, bool aut
     // said here rather than at the first transpose: a launch handshakes with at most kMaxPeers peers
     THROW_NOT_SUPPORTED("row / column communicators with more than 72 ranks are not supported");
   }
-  const bool set = c->transpose_mem_order[0][0] >= 0;
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j)
-      if ((c->transpose_mem_order[i][j] >= 0) != set) THROW_INVALID_USAGE("transpose_mem_order only partially set");
-  if (set) {
-    for (int i = 0; i < 3; ++i) {
-      std::set<int32_t> vals(c->transpose_mem_order[i], c->transpose_mem_order[i] + 3);
-      if (vals.size() != 3 || *vals.begin() != 0 || *vals.rbegin() != 2)
-        THROW_INVALID_USAGE("transpose_mem_order setting is invalid");
-    }
-  }
+  checkMemOrder(c);
 }
 
 bool envFlag(const char* name) {
@@ -977,6 +982,13 @@ static int32_t emitBoxes(const std::vector<BoxDesc>& push, const std::vector<Box
 static GridGeom geomFromConfig(const cudecompGridDescConfig_t* c) {
   if (!c) THROW_INVALID_USAGE("config argument cannot be null");
   if (c->pdims[0] < 1 || c->pdims[1] < 1) THROW_INVALID_USAGE("pdims values are invalid");
+  // what cudecompGridDescCreate checks before a descriptor exists (these entry points take the raw config)
+  checkMemOrder(c);
+  for (int i = 0; i < 3; ++i) {
+    if (c->gdims[i] < 1) THROW_INVALID_USAGE("gdims values must be positive");
+    if (c->gdims_dist[i] < 0 || c->gdims_dist[i] > c->gdims[i])
+      THROW_INVALID_USAGE("gdims_dist entries must be less than or equal to gdims entries");
+  }
   GridGeom g;
   const bool dist_set = c->gdims_dist[0] != 0 && c->gdims_dist[1] != 0 && c->gdims_dist[2] != 0;
   const bool order_set = c->transpose_mem_order[0][0] >= 0;
@@ -987,7 +999,8 @@ static GridGeom geomFromConfig(const cudecompGridDescConfig_t* c) {
       g.order[i][j] = order_set ? c->transpose_mem_order[i][j] : (c->transpose_axis_contiguous[i] ? (i + j) % 3 : j);
   }
   g.pdims = {c->pdims[0], c->pdims[1]};
-  g.col_major = (c->rank_order == CUDECOMP_RANK_ORDER_COL_MAJOR);
+  checkRankOrder(enumBits(c->rank_order));
+  g.col_major = (enumBits(c->rank_order) == CUDECOMP_RANK_ORDER_COL_MAJOR);
   return g;
 }
 
@@ -998,6 +1011,7 @@ int32_t cudecompB200PlanTransposeBoxes(const cudecompGridDescConfig_t* config, i
   try {
     GridGeom g = geomFromConfig(config);
     if (rank < 0 || rank >= g.pdims[0] * g.pdims[1]) THROW_INVALID_USAGE("rank out of range");
+    if (ax < 0 || ax > 2 || dir == 0 || !boxes || max_boxes < 0) THROW_INVALID_USAGE("axis / direction / boxes arguments are invalid");
     if (staged == 2 || staged == 3) { // receiver-driven plans (3: through my workspace); peer_rank owns the SOURCE
       TransposePlan pull = buildPullTransposePlan(g, pidxOfRank(g, rank), ax, dir, input_halo_extents, output_halo_extents,
                                                   input_padding, output_padding,
@@ -1022,6 +1036,7 @@ int32_t cudecompB200PlanPipelinedTransposeBoxes(const cudecompGridDescConfig_t* 
   try {
     GridGeom g = geomFromConfig(config);
     if (rank < 0 || rank >= g.pdims[0] * g.pdims[1]) THROW_INVALID_USAGE("rank out of range");
+    if (ax < 0 || ax > 2 || dir == 0 || !boxes || max_boxes < 0) THROW_INVALID_USAGE("axis / direction / boxes arguments are invalid");
     // inplace: bit 0 = in place, bit 1 = receiver-driven (peer_rank of a push box then owns the SOURCE), bits 8-15 =
     // element size in bytes (0: plane chunks only; else column chunks where they apply, as the engine plans them),
     // bit 2 = column chunks whatever the row length (tests on small grids)
@@ -1065,6 +1080,8 @@ int32_t cudecompB200PlanHaloBoxes(const cudecompGridDescConfig_t* config, int32_
   try {
     GridGeom g = geomFromConfig(config);
     if (rank < 0 || rank >= g.pdims[0] * g.pdims[1]) THROW_INVALID_USAGE("rank out of range");
+    if (ax < 0 || ax > 2 || dim < 0 || dim > 2 || !halo_extents || !boxes || max_boxes < 0)
+      THROW_INVALID_USAGE("axis / dim / halo_extents / boxes arguments are invalid");
     HaloPlan plan = buildHaloPlan(g, pidxOfRank(g, rank), ax, dim, halo_extents, halo_periods, padding,
                                   staged ? DstKind::STAGE : DstKind::FINAL);
     if (plan.nothing) return 0;
