@@ -78,6 +78,30 @@ void recvAll(int fd, void* buf, size_t n) {
   }
 }
 
+// First words of a freshly accepted connection. Anything may dial the rendezvous port (a port scanner, a health
+// check, a rank of another job): a connection that does not deliver `n` bytes within a few seconds, or closes early,
+// is not a rank of this job. Returns false instead of failing the job; the caller drops the connection and keeps
+// accepting.
+bool recvGreeting(int fd, void* buf, size_t n) {
+  timeval tv{5, 0};
+  setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+  char* p = static_cast<char*>(buf);
+  bool ok = true;
+  while (n > 0) {
+    ssize_t k = ::recv(fd, p, n, 0);
+    if (k < 0 && errno == EINTR) continue;
+    if (k <= 0) { // timeout (EAGAIN), reset or orderly close before the greeting was complete
+      ok = false;
+      break;
+    }
+    p += k;
+    n -= static_cast<size_t>(k);
+  }
+  timeval off{0, 0};
+  setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &off, sizeof(off));
+  return ok;
+}
+
 struct MsgHeader {
   uint32_t comm_id;
   uint32_t seq;
@@ -249,8 +273,7 @@ void worldInitExplicit(int rank, int size, const std::string& addr, int port) {
       for (int k = 1; k < w.size; ++k) {
         int fd = acceptOne(lfd);
         Hello hello{};
-        recvAll(fd, &hello, sizeof(hello));
-        if (hello.token != token) { // not a rank of this job
+        if (!recvGreeting(fd, &hello, sizeof(hello)) || hello.token != token) { // not a rank of this job
           ::close(fd);
           --k;
           continue;
@@ -289,8 +312,7 @@ void worldInitExplicit(int rank, int size, const std::string& addr, int port) {
       for (int k = w.rank + 1; k < w.size; ++k) {
         int pfd = acceptOne(lfd);
         Hello other{};
-        recvAll(pfd, &other, sizeof(other));
-        if (other.token != token) {
+        if (!recvGreeting(pfd, &other, sizeof(other)) || other.token != token) {
           ::close(pfd);
           --k;
           continue;

@@ -280,3 +280,58 @@ def test_sixteen_ranks_plans_and_mailbox():
         check_transposes(case, [r[i] for r in results])
     results, _ = run_ranks(16, "mailbox", [dict(name="stress16", iterations=2000, seed=9)], timeout=500)
     assert all(r[0]["ok"] for r in results)
+
+
+def test_rendezvous_survives_stray_connections():
+    """Anything may dial the rendezvous port while the ranks are still arriving (port scanners, health checks, a rank of
+    another job): connections that close at once, send garbage, or send half a greeting and then go silent must be
+    dropped -- the job neither fails nor hangs (csrc/bootstrap.cc recvGreeting)."""
+    import os
+    import socket
+    import subprocess
+    import sys
+    import time
+    from tests._launcher import free_port, ROOT
+    port = free_port()
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from cudecomp_b200 import capi as cd\n"
+            "assert cd.MPI_Init() == 0\n"
+            "res, h = cd.cudecompInit(cd.MPI_COMM_WORLD); cd.check(res)\n"
+            "cd.MPI_Barrier(); cd.check(cd.cudecompFinalize(h)); cd.MPI_Finalize(); print('rank done')\n") % ROOT
+
+    def start(rank):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        return subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                text=True)
+
+    p0 = start(0)
+    procs = [p0]
+    strays = []
+    try:
+        deadline = time.time() + 60
+        while True:  # rank 0 listens on MASTER_PORT + 1
+            try:
+                s = socket.create_connection(("127.0.0.1", port + 1), timeout=1)
+                break
+            except OSError:
+                assert time.time() < deadline and p0.poll() is None, "rank 0 never listened"
+                time.sleep(0.05)
+        s.close()                                    # closes at once
+        s = socket.create_connection(("127.0.0.1", port + 1))
+        s.sendall(b"GET / HTTP/1.0\r\n\r\n")         # a full greeting's worth of garbage
+        strays.append(s)
+        s = socket.create_connection(("127.0.0.1", port + 1))
+        s.sendall(b"\x01\x02\x03")                   # half a greeting, then silence
+        strays.append(s)
+        p1 = start(1)
+        procs.append(p1)
+        out1 = p1.communicate(timeout=120)[0]
+        out0 = p0.communicate(timeout=120)[0]
+        assert p0.returncode == 0 and "rank done" in out0, out0
+        assert p1.returncode == 0 and "rank done" in out1, out1
+    finally:
+        for s in strays:
+            s.close()
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
