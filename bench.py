@@ -281,7 +281,11 @@ def run_native(args, rank, world, local_rank):
     cpu_first = None
     if rank == 0 and not args.no_cpu_baseline:
         pd0 = tuple(int(v) for v in args.pdims.split("x")) if args.pdims else GRID_BY_N.get(world, (1, world))
-        cpu_first = cpu_baseline(args, pd0)
+        try:
+            cpu_first = cpu_baseline(args, pd0)
+        except Exception as e:  # noqa: BLE001 -- a reported baseline, never a reason to lose the bench line
+            cpu_first = {"value": None, "unit": "GB/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                         "sample": "failed: %r" % (e,)}
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
