@@ -213,15 +213,46 @@ def mem_available_bytes():
     return 0
 
 
-def cpu_sample_nz(args, pd, budget_s, gbs_guess=15.0, steps=1):
+def calibrate_cpu_gbs(args, pd):
+    """Effective GB/s of the oracle on THIS host, from one timed round trip on a thin z-slab (well under a second): what
+    the time budget of the CPU legs is planned with. Falls back to 15 GB/s (a 16-core host) if the probe fails."""
+    try:
+        import numpy as np
+        from oracle import oracle as orc
+        n = args.n
+        nz = min(n, max(pd[1] * 4, 16))
+        o = orc.Oracle([n, n, nz], pd, (args.axis_contiguous,) * 3)
+        o.set_threads(len(os.sched_getaffinity(0)))
+        dt = orc.NP_DTYPES[args.dtype]
+        a = [np.ones(max(o.pencil_info(r, ax).size for ax in range(3)), dt) for r in range(o.nranks)]
+        b = [np.zeros_like(x) for x in a]
+        t = None
+        for _ in range(2):  # the first pass also allocates the oracle's staging regions
+            t0 = time.perf_counter()
+            cur, other = a, b
+            for op in OPS:
+                o.transpose(op, cur, cur if args.inplace else other)
+                if not args.inplace:
+                    cur, other = other, cur
+            t = time.perf_counter() - t0
+        o.release()
+        return max(1.0, 4.0 * n * n * nz * np.dtype(dt).itemsize / t / 1e9)
+    except Exception:  # noqa: BLE001
+        return 15.0
+
+
+def cpu_sample_nz(args, pd, budget_s, gbs_guess=None, steps=1):
     """z extent of the CPU sample: the WHOLE grid when host memory (input + output + the oracle's send / receive staging =
     4 grids) and the time budget allow it, else the largest power-of-two z-slab that does. The x-y extent is always
-    full (what the X<->Y exchange moves); z only has to hold 4 planes per rank of the row communicator."""
+    full (what the X<->Y exchange moves); z only has to hold 4 planes per rank of the row communicator. The time is
+    planned with the oracle's measured rate on this host (calibrate_cpu_gbs), less 20 %."""
     import numpy as np
     from oracle import oracle as orc
     es = np.dtype(orc.NP_DTYPES[args.dtype]).itemsize
     n = args.n
     nz = n
+    if gbs_guess is None:
+        gbs_guess = 0.8 * calibrate_cpu_gbs(args, pd)
     avail = mem_available_bytes()
     while nz > max(pd[1] * 4, 8):
         grid_bytes = float(n) * n * nz * es
